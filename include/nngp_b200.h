@@ -1,0 +1,164 @@
+/*
+ * nngp_b200.h -- C ABI of the B200-native NNGP estimator core.
+ *
+ * This is the drop-in boundary for ONE hot path of Kangfei/NNGP-src: NNGP kernel
+ * construction + exact GP posterior inference.  The reference has no FFI of its own
+ * (it is pure Python delegating to neural-tangents on JAX/XLA:CPU + LAPACK), so each
+ * entry point below cites the reference *call site* (file:line under the reference
+ * tree) whose arithmetic it replaces; the un-vendored neural-tangents 0.6.1 callee
+ * is named in brackets.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types in any signature;
+ *   - every matrix is dense row-major FP64; a pointer may be HOST (pageable or
+ *     pinned) or DEVICE memory -- detected with cudaPointerGetAttributes; outputs
+ *     are written into the caller's buffer in the memory space it lives in;
+ *   - every call returns 0 on success or a negative nngp_status; the message is
+ *     available from nngp_last_error(); nothing aborts, throws or prints;
+ *   - a handle is bound to ONE GPU and is not re-entrant; distinct handles are
+ *     independent; every call is complete (stream-synchronised) when it returns;
+ *   - there is NO CPU fallback: without a usable sm_100 device nngp_create fails.
+ */
+#ifndef NNGP_B200_H
+#define NNGP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NNGP_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define NNGP_API __attribute__((visibility("default")))
+#else
+#define NNGP_API
+#endif
+
+typedef enum nngp_status {
+  NNGP_OK = 0,
+  NNGP_EINVAL = -1,  /* bad argument / shape / non-finite input                      */
+  NNGP_ENOTPD = -2,  /* K + lambda*I not positive definite (pivot in last_error)     */
+  NNGP_ECUDA = -3,   /* CUDA runtime / driver error                                  */
+  NNGP_ENOMEM = -4,  /* device allocation failed                                     */
+  NNGP_ESTATE = -5,  /* call needs a fitted model (nngp_fit / nngp_set_state first)  */
+  NNGP_ENODEV = -6   /* no usable sm_100 device                                      */
+} nngp_status;
+
+/*
+ * Kernel + regulariser hyper-parameters.
+ * Replaces the closure state built by
+ *   stax.serial(stax.Dense(512), stax.Relu(), stax.Dense(1))        train.py:161-164,
+ *                                        estimator.py:27-30, active/active_train.py:40-43
+ *   nt.predict.gradient_descent_mse_ensemble(..., diag_reg=1e-3)    train.py:171-172,
+ *                                        estimator.py:34-35, active/ActiveLearner.py:27-28
+ * depth = number of Dense layers (reference: 2) = depth-1 ReLU arc-cosine steps.
+ */
+typedef struct nngp_config {
+  int32_t depth;              /* >= 1                                                 */
+  double sigma_w;             /* stax.Dense W_std (reference default 1.0)             */
+  double sigma_b;             /* stax.Dense b_std (reference default None == 0.0)     */
+  double diag_reg;            /* reference: 1e-3                                      */
+  int32_t diag_reg_absolute;  /* 0: lambda = diag_reg * trace(K)/N  (nt default)      */
+  int32_t device;             /* CUDA ordinal; -1 = current device                    */
+  int64_t max_block_bytes;    /* cap of the test-row block buffer; 0 = default 16 GiB */
+  int32_t stats_level;        /* 0 none, 1 per-stage events, 2 per-kernel-class events*/
+} nngp_config;
+
+/* Per-stage device timings (CUDA events on the handle's stream) and work counters,
+ * accumulated since the last nngp_stats_reset().  Replaces the wall-clock prints at
+ * train.py:170-176,191-195 and estimator.py:44,52-54. */
+typedef struct nngp_stats_t {
+  double fit_gram_ms, fit_chol_ms, fit_solve_ms, fit_total_ms;
+  double pred_gram_ms, pred_mean_ms, pred_trsm_ms, pred_var_ms, pred_total_ms;
+  double h2d_ms, d2h_ms;
+  double gemm_ms;          /* stats_level 2: time inside the DMMA GEMM-update kernels  */
+  double gemm_flops;       /* algorithmic flops of those launches (2*M*N*K)            */
+  int64_t gemm_launches;
+  double gram_ms;          /* stats_level 2: time inside the Gram+arc-cosine kernels   */
+  double gram_flops;       /* 2*M*N*D of those launches                                */
+  double gram_evals;       /* arc-cosine evaluations ((depth-1) per Gram entry)        */
+  int64_t gram_launches;
+  int64_t kernel_launches; /* every kernel this library launched                       */
+  int64_t h2d_bytes, d2h_bytes;
+  int64_t queries;         /* test rows predicted                                      */
+} nngp_stats_t;
+
+typedef struct nngp_handle nngp_handle;
+
+/* Fill cfg with the reference's defaults (depth 2, W_std 1, no bias, diag_reg 1e-3
+ * relative) -- train.py:161-172. */
+NNGP_API void nngp_default_config(nngp_config* cfg);
+
+/* Create a handle on one GPU.  [replaces: closure construction, train.py:161-172] */
+NNGP_API int nngp_create(const nngp_config* cfg, nngp_handle** out);
+NNGP_API void nngp_destroy(nngp_handle* h);
+
+/* Message of the last failing call on this handle (or of a failed nngp_create when
+ * h == NULL).  Never NULL. */
+NNGP_API const char* nngp_last_error(const nngp_handle* h);
+
+/* The CUDA stream (cudaStream_t) every kernel of this handle is launched on, so a
+ * host can bracket calls with its own events. */
+NNGP_API void* nngp_get_stream(nngp_handle* h);
+
+/*
+ * kernel_fn(x1, x2-or-None, 'nngp')                         train.py:216 (disabled block),
+ * live via predict_fn: train.py:157-158, estimator.py:66-67.
+ * [nt: stax._inputs_to_kernel -> Dense -> Relu(ABRelu 0,1; arctan2 form) -> Dense]
+ * x1: M x D, x2: N2 x D (NULL => x2 = x1, N2 ignored), k_out: M x N2.
+ */
+NNGP_API int nngp_kernel(nngp_handle* h, const double* x1, int64_t M, const double* x2_or_null, int64_t N2,
+                int64_t D, double* k_out);
+
+/*
+ * Fit = what the first predict_fn call does lazily in the reference:
+ *   K_dd = kernel_fn(X,X); lambda = diag_reg*trace(K_dd)/N; C = chol(K_dd + lambda I);
+ *   alpha = C^-T C^-1 y                      train.py:171-172,178; estimator.py:34-40;
+ *   active/ActiveLearner.py:27-28  [nt: predict.gp_inference/_get_cho_solve/
+ *   _add_diagonal_regularizer -> scipy cho_factor/cho_solve]
+ * x_train: N x D, y_train: N (used raw, never centred).
+ */
+NNGP_API int nngp_fit(nngp_handle* h, const double* x_train, const double* y_train, int64_t N, int64_t D);
+
+/*
+ * predict_fn(x_test=X, get='nngp', compute_cov=True) followed by diag()
+ *                                           train.py:157-158,180; estimator.py:55,66-67;
+ *   active/ActiveLearner.py:44-46  [nt: gp_inference.predict_fn]
+ * mean_out[T] = K(X*,X) alpha;  var_out[T] = K(x*,x*) - || C^-1 K(X,x*) ||^2, i.e. the
+ * diagonal of the posterior covariance the reference materialises as T x T.  var_out
+ * may be NULL (compute_cov=False).  Negative variances are returned as they come.
+ */
+NNGP_API int nngp_predict(nngp_handle* h, const double* x_test, int64_t T, double* mean_out, double* var_out);
+
+/* Fitted-state export/import: used to broadcast a fit to the other ranks of a
+ * row-sharded prediction job (one process per GPU) and to save/load a model.
+ * nngp_get_dims reports N, D and the lambda actually used.
+ * nngp_get_state copies X (N x D), L (N x N row-major lower factor, upper triangle
+ * zero) and alpha (N); any pointer may be NULL to skip it.
+ * nngp_set_state installs a state produced by nngp_get_state on a handle with the
+ * same config. */
+NNGP_API int nngp_get_dims(nngp_handle* h, int64_t* N, int64_t* D, double* lambda_out);
+NNGP_API int nngp_get_state(nngp_handle* h, double* x_out, double* l_out, double* alpha_out);
+NNGP_API int nngp_set_state(nngp_handle* h, const double* x, const double* l, const double* alpha, int64_t N,
+                   int64_t D, double lambda);
+
+NNGP_API int nngp_stats(nngp_handle* h, nngp_stats_t* out);
+NNGP_API int nngp_stats_reset(nngp_handle* h);
+
+/* Diagnostics used by bench.py / the tests (not part of the reference surface):
+ *   dmma_peak: register-resident mma.sync.m8n8k4.f64 issue-rate microbenchmark -> TFLOP/s
+ *   gemm_probe: C(MxN) -= A(MxK) B(NxK)^T through the production DMMA kernel on device
+ *               scratch, `iters` launches -> average ms per launch
+ *   potrf: in-place lower Cholesky of a caller-supplied N x N row-major matrix. */
+NNGP_API int nngp_diag_dmma_peak(nngp_handle* h, double* tflops_out);
+NNGP_API int nngp_diag_gemm_probe(nngp_handle* h, int64_t M, int64_t N, int64_t K, int32_t iters, double* ms_out);
+NNGP_API int nngp_diag_potrf(nngp_handle* h, double* a, int64_t N);
+
+NNGP_API int nngp_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NNGP_B200_H */

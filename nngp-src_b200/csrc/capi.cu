@@ -1,0 +1,800 @@
+// capi.cu -- host side of the C ABI declared in include/nngp_b200.h.
+//
+// Everything here is orchestration: device buffers, TMA tensor maps, the blocked Cholesky /
+// triangular-solve schedules, and per-stage CUDA-event accounting.  All arithmetic runs in the
+// sm_100a kernels of gemm_nt.cuh (DMMA + TMA) and dense_kernels.cuh.  There is no CPU path.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/nngp_b200.h"
+#include "dense_kernels.cuh"
+#include "gemm_nt.cuh"
+
+using namespace nngp;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  template <class T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+enum EvClass { EV_GEMM = 0, EV_GRAM = 1 };
+struct EvRec {
+  cudaEvent_t a, b;
+  int cls;
+};
+
+inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+struct nngp_handle {
+  nngp_config cfg;
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  PFN_encodeTiled encode = nullptr;
+  std::string err;
+
+  // fitted state
+  bool fitted = false;
+  int64_t N = 0, D = 0, ldx = 0, ldl = 0;
+  double lambda = 0.0;
+  DevBuf X, q, L, alpha, scratch_y;
+  DevBuf flags;   // int[2]: {potrf info, non-finite input}
+  DevBuf lam_d;   // double[1]
+
+  // predict workspace
+  DevBuf xt, qt, kss, blk, mean_d, var_d;
+  // nngp_kernel workspace
+  DevBuf ka, kb, kqa, kqb, kout;
+
+  std::map<std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t>, CUtensorMap> tmaps;
+
+  nngp_stats_t st;
+  std::vector<EvRec> pending;
+  std::vector<cudaEvent_t> ev_pool;
+};
+
+namespace {
+
+int fail(nngp_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CK(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(h, e_ == cudaErrorMemoryAllocation ? NNGP_ENOMEM : NNGP_ECUDA, "%s failed: %s (%s:%d)", #expr, \
+                  cudaGetErrorString(e_), __FILE__, __LINE__);                                     \
+  } while (0)
+
+#define CKR(expr)                     \
+  do {                                \
+    int r_ = (expr);                  \
+    if (r_ != NNGP_OK) return r_;     \
+  } while (0)
+
+int ensure(nngp_handle* h, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap && b.p) return NNGP_OK;
+  if (b.p) { CK(cudaStreamSynchronize(h->stream)); CK(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+  if (bytes == 0) bytes = 256;
+  cudaError_t e = cudaMalloc(&b.p, bytes);
+  if (e != cudaSuccess) {
+    b.p = nullptr;
+    cudaGetLastError();
+    return fail(h, NNGP_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+  }
+  b.cap = bytes;
+  return NNGP_OK;
+}
+
+void release(DevBuf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+bool is_device_ptr(const void* p) {
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// ---- events ----------------------------------------------------------------------------------
+cudaEvent_t get_event(nngp_handle* h) {
+  if (!h->ev_pool.empty()) { cudaEvent_t e = h->ev_pool.back(); h->ev_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+struct StageTimer {  // level >= 1: accumulates into *dst at flush time
+  nngp_handle* h;
+  cudaEvent_t a = nullptr, b = nullptr;
+  double* dst;
+  StageTimer(nngp_handle* h_, double* dst_) : h(h_), dst(dst_) {
+    if (h->cfg.stats_level >= 1) { a = get_event(h); cudaEventRecord(a, h->stream); }
+  }
+  void stop() {
+    if (a && !b) { b = get_event(h); cudaEventRecord(b, h->stream); }
+  }
+  // call after the stream has been synchronised
+  void collect() {
+    if (a && b) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, a, b) == cudaSuccess) *dst += ms;
+      h->ev_pool.push_back(a); h->ev_pool.push_back(b);
+      a = b = nullptr;
+    }
+  }
+};
+void class_begin(nngp_handle* h, int cls, cudaEvent_t* a) {
+  *a = nullptr;
+  if (h->cfg.stats_level >= 2) { *a = get_event(h); cudaEventRecord(*a, h->stream); }
+  (void)cls;
+}
+void class_end(nngp_handle* h, int cls, cudaEvent_t a) {
+  if (a) {
+    cudaEvent_t b = get_event(h);
+    cudaEventRecord(b, h->stream);
+    h->pending.push_back({a, b, cls});
+  }
+}
+void flush_class_events(nngp_handle* h) {  // after a stream sync
+  for (auto& r : h->pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      if (r.cls == EV_GEMM) h->st.gemm_ms += ms; else h->st.gram_ms += ms;
+    }
+    h->ev_pool.push_back(r.a); h->ev_pool.push_back(r.b);
+  }
+  h->pending.clear();
+}
+
+// ---- tensor maps ------------------------------------------------------------------------------
+// Row-major FP64 matrix [rows, cols] with leading dimension ld (elements); box = 16 x box_rows,
+// SWIZZLE_128B (the layout gemm_nt_kernel's fragment loads assume).
+int get_tmap(nngp_handle* h, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+             CUtensorMap* out) {
+  auto key = std::make_tuple(base, rows, cols, ld, box_rows);
+  auto it = h->tmaps.find(key);
+  if (it != h->tmaps.end()) { *out = it->second; return NNGP_OK; }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld & 1))
+    return fail(h, NNGP_EINVAL, "internal: TMA operand not 16-byte aligned (ld=%llu)", (unsigned long long)ld);
+  CUtensorMap tm;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * sizeof(double)};
+  cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = h->encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(h, NNGP_ECUDA, "cuTensorMapEncodeTiled failed (CUresult %d; rows=%llu cols=%llu ld=%llu)", (int)r,
+                (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
+  if (h->tmaps.size() > 4096) h->tmaps.clear();
+  h->tmaps[key] = tm;
+  *out = tm;
+  return NNGP_OK;
+}
+
+struct MatView {  // a whole device matrix a tensor map is built over
+  const double* base;
+  int64_t rows, cols, ld;
+};
+
+// ---- GEMM launches ----------------------------------------------------------------------------
+template <int EPI>
+int launch_gemm(nngp_handle* h, const MatView& A, int a_row0, int a_col0, const MatView& B, int b_row0, int b_col0,
+                GemmParams p) {
+  if (p.M <= 0 || p.N <= 0) return NNGP_OK;
+  CUtensorMap tmA, tmB;
+  CKR(get_tmap(h, A.base, A.rows, A.cols, A.ld, GEMM_BM, &tmA));
+  CKR(get_tmap(h, B.base, B.rows, B.cols, B.ld, GEMM_BN, &tmB));
+  p.a_row0 = a_row0; p.a_col0 = a_col0; p.b_row0 = b_row0; p.b_col0 = b_col0;
+  dim3 grid((p.N + GEMM_BN - 1) / GEMM_BN, (p.M + GEMM_BM - 1) / GEMM_BM, 1);
+  if (grid.y > 65535) return fail(h, NNGP_EINVAL, "internal: GEMM row range too large (%d rows)", p.M);
+  cudaEvent_t ev;
+  const int cls = (EPI == EPI_GRAM) ? EV_GRAM : EV_GEMM;
+  class_begin(h, cls, &ev);
+  gemm_nt_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(tmA, tmB, p);
+  class_end(h, cls, ev);
+  CK(cudaGetLastError());
+  h->st.kernel_launches++;
+  const double frac = p.lower ? 0.5 : 1.0;  // algorithmic work of a lower-triangular range
+  const double flops = 2.0 * (double)p.M * (double)p.N * (double)p.ktiles * GEMM_BK * frac;
+  if (EPI == EPI_GRAM) {
+    h->st.gram_launches++;
+    h->st.gram_flops += flops;
+    h->st.gram_evals += (double)p.M * (double)p.N * frac * p.steps;
+  } else {
+    h->st.gemm_launches++;
+    h->st.gemm_flops += flops;
+  }
+  return NNGP_OK;
+}
+
+// K(A rows, B rows) -> out (M x N, ld ldo).  A: M x D (lda), B: N x D (ldb); qa/qb layer-0 diagonals.
+int run_gram(nngp_handle* h, const double* A, int64_t lda, int64_t M, const double* qa, const double* B, int64_t ldb,
+             int64_t N, const double* qb, int64_t D, double* out, int64_t ldo, int lower) {
+  GemmParams p{};
+  p.M = (int)M; p.N = (int)N;
+  p.ktiles = (int)((D + GEMM_BK - 1) / GEMM_BK);
+  p.C = out; p.ldc = ldo; p.lower = lower;
+  p.q1 = qa; p.q2 = qb;
+  const double sw2 = h->cfg.sigma_w * h->cfg.sigma_w, sb2 = h->cfg.sigma_b * h->cfg.sigma_b;
+  p.scale = sw2 / (double)D; p.sw2 = sw2; p.sb2 = sb2; p.steps = h->cfg.depth - 1;
+  MatView a{A, M, D, lda}, b{B, N, D, ldb};
+  // the flop counter must use the true D, not the padded k extent
+  const double before = h->st.gram_flops;
+  CKR(launch_gemm<EPI_GRAM>(h, a, 0, 0, b, 0, 0, p));
+  h->st.gram_flops = before + 2.0 * (double)M * (double)N * (double)D * (lower ? 0.5 : 1.0);
+  return NNGP_OK;
+}
+
+// C(M x N at `C`, ldc) -= Aop[a_row0:+M, a_col0:+K] * Bop[b_row0:+N, b_col0:+K]^T ; K % 16 == 0.
+int run_gemm_sub(nngp_handle* h, const MatView& A, int64_t a_row0, int64_t a_col0, const MatView& B, int64_t b_row0,
+                 int64_t b_col0, int64_t M, int64_t N, int64_t K, double* C, int64_t ldc, int lower) {
+  if (K <= 0) return NNGP_OK;
+  if (K % GEMM_BK) return fail(h, NNGP_EINVAL, "internal: GEMM K=%lld not a multiple of 16", (long long)K);
+  GemmParams p{};
+  p.M = (int)M; p.N = (int)N; p.ktiles = (int)(K / GEMM_BK);
+  p.C = C; p.ldc = ldc; p.lower = lower;
+  return launch_gemm<EPI_SUB>(h, A, (int)a_row0, (int)a_col0, B, (int)b_row0, (int)b_col0, p);
+}
+
+// ---- blocked Cholesky (lower, in place, row-major) ----------------------------------------------
+// Right-looking over W-wide outer panels (trailing SYRK with K = W on the DMMA core), left-looking
+// over the 64-wide sub-panels inside a panel (potf2 on the diagonal block, one-thread-per-row
+// forward substitution for the block column below it).
+int chol_outer_width() {
+  static int w = [] {
+    const char* e = getenv("NNGP_CHOL_W");
+    int v = e ? atoi(e) : 256;
+    if (v < NB) v = NB;
+    return (v / NB) * NB;
+  }();
+  return w;
+}
+
+int run_potrf(nngp_handle* h, double* A, int64_t ld, int64_t N) {
+  int* info = h->flags.as<int>();
+  const int W = chol_outer_width();
+  MatView Av{A, N, N, ld};
+  for (int64_t j0 = 0; j0 < N; j0 += W) {
+    const int64_t w = std::min<int64_t>(W, N - j0);
+    for (int64_t s0 = j0; s0 < j0 + w; s0 += NB) {
+      const int64_t nb = std::min<int64_t>(NB, N - s0);
+      if (s0 > j0)  // A[s0:N, s0:s0+nb] -= A[s0:N, j0:s0] * A[s0:s0+nb, j0:s0]^T
+        CKR(run_gemm_sub(h, Av, s0, j0, Av, s0, j0, N - s0, nb, s0 - j0, A + s0 * ld + s0, ld, 0));
+      potf2_64_kernel<<<1, 256, 0, h->stream>>>(A + s0 * ld + s0, ld, (int)nb, (int)s0, info);
+      h->st.kernel_launches++;
+      const int64_t below = N - s0 - nb;
+      if (below > 0) {
+        const int grid = (int)((below + TRSM_ROWS - 1) / TRSM_ROWS);
+        trsm_rows_64_kernel<<<grid, TRSM_ROWS, TRSM_SMEM_BYTES, h->stream>>>(A + (s0 + nb) * ld + s0, ld, (int)below,
+                                                                            A + s0 * ld + s0, ld, (int)nb);
+        h->st.kernel_launches++;
+      }
+    }
+    const int64_t t0 = j0 + w;
+    if (t0 < N)  // trailing: A[t0:N, t0:N] (lower) -= A[t0:N, j0:t0] * A[t0:N, j0:t0]^T
+      CKR(run_gemm_sub(h, Av, t0, j0, Av, t0, j0, N - t0, N - t0, w, A + t0 * ld + t0, ld, 1));
+  }
+  CK(cudaGetLastError());
+  return NNGP_OK;
+}
+
+// B (rows x N, ldb) <- B * L^-T  (solve X L^T = B), L lower N x N row-major: left-looking over
+// 64-wide column blocks; the update is one DMMA GEMM with K = j0, the diagonal solve is per row.
+int run_trsm_rlt(nngp_handle* h, double* B, int64_t ldb, int64_t rows, const double* L, int64_t ldl, int64_t N) {
+  MatView Bv{B, rows, N, ldb}, Lv{L, N, N, ldl};
+  const int grid = (int)((rows + TRSM_ROWS - 1) / TRSM_ROWS);
+  for (int64_t j0 = 0; j0 < N; j0 += NB) {
+    const int64_t nb = std::min<int64_t>(NB, N - j0);
+    if (j0 > 0) CKR(run_gemm_sub(h, Bv, 0, 0, Lv, j0, 0, rows, nb, j0, B + j0, ldb, 0));
+    trsm_rows_64_kernel<<<grid, TRSM_ROWS, TRSM_SMEM_BYTES, h->stream>>>(B + j0, ldb, (int)rows, L + j0 * ldl + j0, ldl,
+                                                                        (int)nb);
+    h->st.kernel_launches++;
+  }
+  CK(cudaGetLastError());
+  return NNGP_OK;
+}
+
+// v <- L^-T L^-1 v  (two blocked substitutions, each reads L exactly once)
+int run_cho_solve_vec(nngp_handle* h, const double* L, int64_t ld, int64_t N, double* v) {
+  const int warps_per_cta = TRSV_THREADS / 32;
+  for (int64_t j0 = 0; j0 < N; j0 += NB) {
+    const int64_t nb = std::min<int64_t>(NB, N - j0);
+    const int64_t rem = N - j0 - nb;
+    int grid = (int)std::min<int64_t>(std::max<int64_t>(1, (rem + warps_per_cta - 1) / warps_per_cta), 4 * h->sm_count);
+    trsv_fwd_step_kernel<<<grid, TRSV_THREADS, 0, h->stream>>>(L, ld, (int)N, (int)j0, (int)nb, v);
+    h->st.kernel_launches++;
+  }
+  const int64_t nblk = (N + NB - 1) / NB;
+  for (int64_t jb = nblk - 1; jb >= 0; --jb) {
+    const int64_t j0 = jb * NB;
+    const int64_t nb = std::min<int64_t>(NB, N - j0);
+    int grid = (int)std::min<int64_t>(std::max<int64_t>(1, (j0 + TRSV_THREADS - 1) / TRSV_THREADS), 4 * h->sm_count);
+    trsv_bwd_step_kernel<<<grid, TRSV_THREADS, 0, h->stream>>>(L, ld, (int)j0, (int)nb, v);
+    h->st.kernel_launches++;
+  }
+  CK(cudaGetLastError());
+  return NNGP_OK;
+}
+
+// copy a caller matrix (host or device, dense rows x cols) into a padded device matrix (ld), zero pad
+int upload_matrix(nngp_handle* h, const double* src, int64_t rows, int64_t cols, double* dst, int64_t ld) {
+  if (ld != cols) CK(cudaMemsetAsync(dst, 0, (size_t)rows * ld * sizeof(double), h->stream));
+  const bool dev = is_device_ptr(src);
+  CK(cudaMemcpy2DAsync(dst, ld * sizeof(double), src, cols * sizeof(double), cols * sizeof(double), rows,
+                       dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+  if (!dev) h->st.h2d_bytes += rows * cols * (int64_t)sizeof(double);
+  return NNGP_OK;
+}
+int download(nngp_handle* h, const double* dsrc, int64_t rows, int64_t cols, int64_t ld, double* dst) {
+  const bool dev = is_device_ptr(dst);
+  CK(cudaMemcpy2DAsync(dst, cols * sizeof(double), dsrc, ld * sizeof(double), cols * sizeof(double), rows,
+                       dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+  if (!dev) h->st.d2h_bytes += rows * cols * (int64_t)sizeof(double);
+  return NNGP_OK;
+}
+
+int check_finite_async(nngp_handle* h, const double* x, int64_t ld, int64_t rows, int64_t cols) {
+  const int64_t total = rows * cols;
+  int grid = (int)std::min<int64_t>((total + 255) / 256, 8 * h->sm_count);
+  if (grid < 1) grid = 1;
+  finite_check_kernel<<<grid, 256, 0, h->stream>>>(x, ld, rows, (int)cols, h->flags.as<int>() + 1);
+  h->st.kernel_launches++;
+  return NNGP_OK;
+}
+
+int bind_device(nngp_handle* h) {
+  CK(cudaSetDevice(h->device));
+  return NNGP_OK;
+}
+
+void drop_fit(nngp_handle* h) { h->fitted = false; }
+
+int alloc_state(nngp_handle* h, int64_t N, int64_t D) {
+  h->N = N; h->D = D;
+  h->ldx = round_up(D, 2);
+  h->ldl = round_up(N, 16);
+  CKR(ensure(h, h->X, (size_t)N * h->ldx * sizeof(double)));
+  CKR(ensure(h, h->q, (size_t)N * sizeof(double)));
+  CKR(ensure(h, h->L, (size_t)N * h->ldl * sizeof(double)));
+  CKR(ensure(h, h->alpha, (size_t)h->ldl * sizeof(double)));
+  return NNGP_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int nngp_abi_version(void) { return NNGP_B200_ABI_VERSION; }
+
+void nngp_default_config(nngp_config* cfg) {
+  if (!cfg) return;
+  memset(cfg, 0, sizeof *cfg);
+  cfg->depth = 2;
+  cfg->sigma_w = 1.0;
+  cfg->sigma_b = 0.0;
+  cfg->diag_reg = 1e-3;
+  cfg->diag_reg_absolute = 0;
+  cfg->device = -1;
+  cfg->max_block_bytes = 0;
+  cfg->stats_level = 1;
+}
+
+const char* nngp_last_error(const nngp_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int nngp_create(const nngp_config* cfg, nngp_handle** out) {
+  nngp_handle* h = nullptr;
+  if (!cfg || !out) return fail(h, NNGP_EINVAL, "nngp_create: null argument");
+  *out = nullptr;
+  if (cfg->depth < 1) return fail(h, NNGP_EINVAL, "nngp_create: depth must be >= 1 (got %d)", cfg->depth);
+  if (!(cfg->sigma_w > 0.0) || !(cfg->sigma_b >= 0.0) || !(cfg->diag_reg >= 0.0))
+    return fail(h, NNGP_EINVAL, "nngp_create: need sigma_w > 0, sigma_b >= 0, diag_reg >= 0");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(h, NNGP_ENODEV, "nngp_create: no CUDA device visible (this library has no CPU path)");
+  }
+  int dev = cfg->device;
+  if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+  if (dev >= ndev) return fail(h, NNGP_ENODEV, "nngp_create: device %d out of range (%d visible)", dev, ndev);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess)
+    return fail(h, NNGP_ECUDA, "nngp_create: cudaGetDeviceProperties failed");
+  if (prop.major != 10)
+    return fail(h, NNGP_ENODEV, "nngp_create: device %d is sm_%d%d; this library is built for sm_100a only", dev,
+                prop.major, prop.minor);
+  nngp_handle* nh = new nngp_handle();
+  nh->cfg = *cfg;
+  if (nh->cfg.max_block_bytes <= 0) nh->cfg.max_block_bytes = (int64_t)16 << 30;
+  nh->device = dev;
+  nh->sm_count = prop.multiProcessorCount;
+  memset(&nh->st, 0, sizeof nh->st);
+  h = nh;
+  auto bail = [&](int code) { std::string m = h->err; nngp_destroy(h); g_create_error = m; return code; };
+  if (cudaSetDevice(dev) != cudaSuccess) { fail(h, NNGP_ECUDA, "cudaSetDevice(%d) failed", dev); return bail(NNGP_ECUDA); }
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    fail(h, NNGP_ECUDA, "cudaStreamCreate failed");
+    return bail(NNGP_ECUDA);
+  }
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+      qres != cudaDriverEntryPointSuccess) {
+    fail(h, NNGP_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+    return bail(NNGP_ECUDA);
+  }
+  h->encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  cudaError_t e1 = cudaFuncSetAttribute(gemm_nt_kernel<EPI_GRAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+  cudaError_t e2 = cudaFuncSetAttribute(gemm_nt_kernel<EPI_SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+  cudaError_t e3 = cudaFuncSetAttribute(trsm_rows_64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM_BYTES);
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+    fail(h, NNGP_ECUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s",
+         cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+    return bail(NNGP_ECUDA);
+  }
+  if (ensure(h, h->flags, 2 * sizeof(int)) != NNGP_OK || ensure(h, h->lam_d, sizeof(double)) != NNGP_OK)
+    return bail(NNGP_ENOMEM);
+  cudaMemsetAsync(h->flags.p, 0, 2 * sizeof(int), h->stream);
+  cudaStreamSynchronize(h->stream);
+  *out = h;
+  return NNGP_OK;
+}
+
+void nngp_destroy(nngp_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (DevBuf* b : {&h->X, &h->q, &h->L, &h->alpha, &h->scratch_y, &h->flags, &h->lam_d, &h->xt, &h->qt, &h->kss,
+                    &h->blk, &h->mean_d, &h->var_d, &h->ka, &h->kb, &h->kqa, &h->kqb, &h->kout})
+    release(*b);
+  for (auto& r : h->pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto e : h->ev_pool) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+void* nngp_get_stream(nngp_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+int nngp_stats(nngp_handle* h, nngp_stats_t* out) {
+  if (!h || !out) return NNGP_EINVAL;
+  *out = h->st;
+  return NNGP_OK;
+}
+int nngp_stats_reset(nngp_handle* h) {
+  if (!h) return NNGP_EINVAL;
+  memset(&h->st, 0, sizeof h->st);
+  return NNGP_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+int nngp_kernel(nngp_handle* h, const double* x1, int64_t M, const double* x2, int64_t N2, int64_t D, double* k_out) {
+  if (!h) return NNGP_EINVAL;
+  if (!x1 || !k_out || M <= 0 || D <= 0 || (x2 && N2 <= 0))
+    return fail(h, NNGP_EINVAL, "nngp_kernel: bad argument (M=%lld N2=%lld D=%lld)", (long long)M, (long long)N2, (long long)D);
+  CKR(bind_device(h));
+  const int64_t Nn = x2 ? N2 : M;
+  if (M > 65535LL * GEMM_BM || Nn > 0x7fffffffLL || D > 0x7fffffffLL)
+    return fail(h, NNGP_EINVAL, "nngp_kernel: shape too large for one call");
+  const int64_t ldx = round_up(D, 2), ldo = round_up(Nn, 2);
+  const double sw2 = h->cfg.sigma_w * h->cfg.sigma_w, sb2 = h->cfg.sigma_b * h->cfg.sigma_b;
+  CKR(ensure(h, h->ka, (size_t)M * ldx * 8));
+  CKR(ensure(h, h->kqa, (size_t)M * 8));
+  CKR(ensure(h, h->kout, (size_t)M * ldo * 8));
+  CK(cudaMemsetAsync(h->flags.p, 0, 2 * sizeof(int), h->stream));
+  CKR(upload_matrix(h, x1, M, D, h->ka.as<double>(), ldx));
+  CKR(check_finite_async(h, h->ka.as<double>(), ldx, M, D));
+  row_sqnorm_kernel<<<(unsigned)((M * 32 + 255) / 256), 256, 0, h->stream>>>(h->ka.as<double>(), ldx, (int)M, (int)D, sw2, sb2, h->kqa.as<double>());
+  h->st.kernel_launches++;
+  const double* bptr = h->ka.as<double>();
+  const double* qb = h->kqa.as<double>();
+  if (x2) {
+    CKR(ensure(h, h->kb, (size_t)Nn * ldx * 8));
+    CKR(ensure(h, h->kqb, (size_t)Nn * 8));
+    CKR(upload_matrix(h, x2, Nn, D, h->kb.as<double>(), ldx));
+    CKR(check_finite_async(h, h->kb.as<double>(), ldx, Nn, D));
+    row_sqnorm_kernel<<<(unsigned)((Nn * 32 + 255) / 256), 256, 0, h->stream>>>(h->kb.as<double>(), ldx, (int)Nn, (int)D, sw2, sb2, h->kqb.as<double>());
+    h->st.kernel_launches++;
+    bptr = h->kb.as<double>();
+    qb = h->kqb.as<double>();
+  }
+  CKR(run_gram(h, h->ka.as<double>(), ldx, M, h->kqa.as<double>(), bptr, ldx, Nn, qb, D, h->kout.as<double>(), ldo, 0));
+  CKR(download(h, h->kout.as<double>(), M, Nn, ldo, k_out));
+  int flags[2];
+  CK(cudaMemcpyAsync(flags, h->flags.p, sizeof flags, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  flush_class_events(h);
+  if (flags[1]) return fail(h, NNGP_EINVAL, "nngp_kernel: non-finite value in the inputs");
+  return NNGP_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+int nngp_fit(nngp_handle* h, const double* x_train, const double* y_train, int64_t N, int64_t D) {
+  if (!h) return NNGP_EINVAL;
+  if (!x_train || !y_train || N <= 0 || D <= 0)
+    return fail(h, NNGP_EINVAL, "nngp_fit: bad argument (N=%lld D=%lld)", (long long)N, (long long)D);
+  if (N > 65535LL * GEMM_BM || D > 0x7fffffffLL) return fail(h, NNGP_EINVAL, "nngp_fit: N=%lld too large", (long long)N);
+  CKR(bind_device(h));
+  drop_fit(h);
+  CKR(alloc_state(h, N, D));
+  const double sw2 = h->cfg.sigma_w * h->cfg.sigma_w, sb2 = h->cfg.sigma_b * h->cfg.sigma_b;
+  double* X = h->X.as<double>();
+  double* L = h->L.as<double>();
+  double* alpha = h->alpha.as<double>();
+  double* q = h->q.as<double>();
+
+  StageTimer t_total(h, &h->st.fit_total_ms), t_h2d(h, &h->st.h2d_ms);
+  CK(cudaMemsetAsync(h->flags.p, 0, 2 * sizeof(int), h->stream));
+  CKR(upload_matrix(h, x_train, N, D, X, h->ldx));
+  CKR(upload_matrix(h, y_train, N, 1, alpha, 1));
+  t_h2d.stop();
+  CKR(check_finite_async(h, X, h->ldx, N, D));
+  CKR(check_finite_async(h, alpha, 1, N, 1));
+
+  StageTimer t_gram(h, &h->st.fit_gram_ms);
+  row_sqnorm_kernel<<<(unsigned)((N * 32 + 255) / 256), 256, 0, h->stream>>>(X, h->ldx, (int)N, (int)D, sw2, sb2, q);
+  h->st.kernel_launches++;
+  CKR(run_gram(h, X, h->ldx, N, q, X, h->ldx, N, q, D, L, h->ldl, 1));
+  diag_reg_kernel<<<1, 1024, 0, h->stream>>>(L, h->ldl, (int)N, h->cfg.diag_reg, h->cfg.diag_reg_absolute, h->lam_d.as<double>());
+  h->st.kernel_launches++;
+  t_gram.stop();
+
+  StageTimer t_chol(h, &h->st.fit_chol_ms);
+  CKR(run_potrf(h, L, h->ldl, N));
+  t_chol.stop();
+
+  StageTimer t_solve(h, &h->st.fit_solve_ms);
+  CKR(run_cho_solve_vec(h, L, h->ldl, N, alpha));
+  t_solve.stop();
+  t_total.stop();
+
+  int flags[2];
+  CK(cudaMemcpyAsync(flags, h->flags.p, sizeof flags, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(&h->lambda, h->lam_d.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  t_total.collect(); t_h2d.collect(); t_gram.collect(); t_chol.collect(); t_solve.collect();
+  flush_class_events(h);
+  if (flags[1]) return fail(h, NNGP_EINVAL, "nngp_fit: non-finite value in x_train / y_train");
+  if (flags[0])
+    return fail(h, NNGP_ENOTPD, "nngp_fit: K + lambda*I is not positive definite (pivot %d of %lld, lambda=%.6g)",
+                flags[0] - 1, (long long)N, h->lambda);
+  h->fitted = true;
+  return NNGP_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+int nngp_predict(nngp_handle* h, const double* x_test, int64_t T, double* mean_out, double* var_out) {
+  if (!h) return NNGP_EINVAL;
+  if (!h->fitted) return fail(h, NNGP_ESTATE, "nngp_predict: no fitted model (call nngp_fit or nngp_set_state)");
+  if (!x_test || !mean_out || T <= 0) return fail(h, NNGP_EINVAL, "nngp_predict: bad argument (T=%lld)", (long long)T);
+  CKR(bind_device(h));
+  const int64_t N = h->N, D = h->D, ldx = h->ldx, ldl = h->ldl;
+  const double sw2 = h->cfg.sigma_w * h->cfg.sigma_w, sb2 = h->cfg.sigma_b * h->cfg.sigma_b;
+
+  // Row-block size: a whole number of full DMMA waves (2 CTAs/SM x 128 rows) that fits the buffer cap.
+  const int64_t wave_rows = 2LL * h->sm_count * GEMM_BM;
+  int64_t cap_rows = h->cfg.max_block_bytes / (ldl * 8);
+  if (cap_rows >= wave_rows) cap_rows = cap_rows / wave_rows * wave_rows;
+  cap_rows = std::max<int64_t>(cap_rows, GEMM_BM);
+  cap_rows = std::min<int64_t>(cap_rows, 65535LL * GEMM_BM);
+  const int64_t TB = std::min<int64_t>(round_up(T, 2), cap_rows);
+
+  CKR(ensure(h, h->xt, (size_t)TB * ldx * 8));
+  CKR(ensure(h, h->qt, (size_t)TB * 8));
+  CKR(ensure(h, h->kss, (size_t)TB * 8));
+  CKR(ensure(h, h->blk, (size_t)TB * ldl * 8));
+  CKR(ensure(h, h->mean_d, (size_t)T * 8));
+  if (var_out) CKR(ensure(h, h->var_d, (size_t)T * 8));
+  CK(cudaMemsetAsync(h->flags.p, 0, 2 * sizeof(int), h->stream));
+
+  double* xt = h->xt.as<double>();
+  double* blk = h->blk.as<double>();
+  StageTimer t_total(h, &h->st.pred_total_ms);
+  std::vector<StageTimer> timers;
+  timers.reserve(8 * ((T + TB - 1) / TB) + 8);
+  for (int64_t t0 = 0; t0 < T; t0 += TB) {
+    const int64_t rows = std::min<int64_t>(TB, T - t0);
+    timers.emplace_back(h, &h->st.h2d_ms);
+    CKR(upload_matrix(h, x_test + t0 * D, rows, D, xt, ldx));
+    timers.back().stop();
+    CKR(check_finite_async(h, xt, ldx, rows, D));
+
+    timers.emplace_back(h, &h->st.pred_gram_ms);
+    row_sqnorm_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, h->stream>>>(xt, ldx, (int)rows, (int)D, sw2, sb2, h->qt.as<double>());
+    h->st.kernel_launches++;
+    CKR(run_gram(h, xt, ldx, rows, h->qt.as<double>(), h->X.as<double>(), ldx, N, h->q.as<double>(), D, blk, ldl, 0));
+    timers.back().stop();
+
+    timers.emplace_back(h, &h->st.pred_mean_ms);
+    gemv_rows_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, h->stream>>>(blk, ldl, (int)rows, (int)N, h->alpha.as<double>(), h->mean_d.as<double>() + t0);
+    h->st.kernel_launches++;
+    timers.back().stop();
+
+    if (var_out) {
+      timers.emplace_back(h, &h->st.pred_trsm_ms);
+      CKR(run_trsm_rlt(h, blk, ldl, rows, h->L.as<double>(), ldl, N));
+      timers.back().stop();
+      timers.emplace_back(h, &h->st.pred_var_ms);
+      q_final_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, h->stream>>>(h->qt.as<double>(), (int)rows, h->cfg.depth - 1, sw2, sb2, h->kss.as<double>());
+      var_rows_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, h->stream>>>(blk, ldl, (int)rows, (int)N, h->kss.as<double>(), h->var_d.as<double>() + t0);
+      h->st.kernel_launches += 2;
+      timers.back().stop();
+    }
+  }
+  timers.emplace_back(h, &h->st.d2h_ms);
+  CKR(download(h, h->mean_d.as<double>(), T, 1, 1, mean_out));
+  if (var_out) CKR(download(h, h->var_d.as<double>(), T, 1, 1, var_out));
+  timers.back().stop();
+  t_total.stop();
+  int flags[2];
+  CK(cudaMemcpyAsync(flags, h->flags.p, sizeof flags, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  t_total.collect();
+  for (auto& t : timers) t.collect();
+  flush_class_events(h);
+  if (flags[1]) return fail(h, NNGP_EINVAL, "nngp_predict: non-finite value in x_test");
+  h->st.queries += T;
+  return NNGP_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+int nngp_get_dims(nngp_handle* h, int64_t* N, int64_t* D, double* lambda_out) {
+  if (!h) return NNGP_EINVAL;
+  if (!h->fitted) return fail(h, NNGP_ESTATE, "nngp_get_dims: no fitted model");
+  if (N) *N = h->N;
+  if (D) *D = h->D;
+  if (lambda_out) *lambda_out = h->lambda;
+  return NNGP_OK;
+}
+
+int nngp_get_state(nngp_handle* h, double* x_out, double* l_out, double* alpha_out) {
+  if (!h) return NNGP_EINVAL;
+  if (!h->fitted) return fail(h, NNGP_ESTATE, "nngp_get_state: no fitted model");
+  CKR(bind_device(h));
+  if (x_out) CKR(download(h, h->X.as<double>(), h->N, h->D, h->ldx, x_out));
+  if (l_out) {
+    dim3 grid((unsigned)((h->N + 255) / 256), (unsigned)std::min<int64_t>(h->N, 4096));
+    zero_upper_kernel<<<grid, 256, 0, h->stream>>>(h->L.as<double>(), h->ldl, (int)h->N);
+    h->st.kernel_launches++;
+    CKR(download(h, h->L.as<double>(), h->N, h->N, h->ldl, l_out));
+  }
+  if (alpha_out) CKR(download(h, h->alpha.as<double>(), h->N, 1, 1, alpha_out));
+  CK(cudaStreamSynchronize(h->stream));
+  return NNGP_OK;
+}
+
+int nngp_set_state(nngp_handle* h, const double* x, const double* l, const double* alpha, int64_t N, int64_t D,
+                   double lambda) {
+  if (!h) return NNGP_EINVAL;
+  if (!x || !l || !alpha || N <= 0 || D <= 0) return fail(h, NNGP_EINVAL, "nngp_set_state: bad argument");
+  CKR(bind_device(h));
+  drop_fit(h);
+  CKR(alloc_state(h, N, D));
+  const double sw2 = h->cfg.sigma_w * h->cfg.sigma_w, sb2 = h->cfg.sigma_b * h->cfg.sigma_b;
+  CKR(upload_matrix(h, x, N, D, h->X.as<double>(), h->ldx));
+  CKR(upload_matrix(h, l, N, N, h->L.as<double>(), h->ldl));
+  CKR(upload_matrix(h, alpha, N, 1, h->alpha.as<double>(), 1));
+  row_sqnorm_kernel<<<(unsigned)((N * 32 + 255) / 256), 256, 0, h->stream>>>(h->X.as<double>(), h->ldx, (int)N, (int)D, sw2, sb2, h->q.as<double>());
+  h->st.kernel_launches++;
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  h->lambda = lambda;
+  h->fitted = true;
+  return NNGP_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+int nngp_diag_dmma_peak(nngp_handle* h, double* tflops_out) {
+  if (!h || !tflops_out) return NNGP_EINVAL;
+  CKR(bind_device(h));
+  const int iters = 4096;
+  const int ctas = h->sm_count * 4;
+  cudaEvent_t a = get_event(h), b = get_event(h);
+  dmma_peak_kernel<<<ctas, 256, 0, h->stream>>>(64, h->lam_d.as<double>());  // warm-up
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(a, h->stream);
+    dmma_peak_kernel<<<ctas, 256, 0, h->stream>>>(iters, h->lam_d.as<double>());
+    cudaEventRecord(b, h->stream);
+    CK(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    const double flops = (double)ctas * 8 /*warps*/ * (double)iters * 16 * 512.0;
+    best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  h->st.kernel_launches += 6;
+  h->ev_pool.push_back(a); h->ev_pool.push_back(b);
+  *tflops_out = best;
+  return NNGP_OK;
+}
+
+int nngp_diag_gemm_probe(nngp_handle* h, int64_t M, int64_t N, int64_t K, int32_t iters, double* ms_out) {
+  if (!h || !ms_out || M <= 0 || N <= 0 || K <= 0 || K % GEMM_BK || iters <= 0)
+    return fail(h, NNGP_EINVAL, "nngp_diag_gemm_probe: bad argument");
+  CKR(bind_device(h));
+  DevBuf A, B, C;
+  const int64_t ld = round_up(K, 16), ldc = round_up(N, 16);
+  int rc = ensure(h, A, (size_t)M * ld * 8);
+  if (rc == NNGP_OK) rc = ensure(h, B, (size_t)N * ld * 8);
+  if (rc == NNGP_OK) rc = ensure(h, C, (size_t)M * ldc * 8);
+  if (rc != NNGP_OK) { release(A); release(B); release(C); return rc; }
+  cudaMemsetAsync(A.p, 0, (size_t)M * ld * 8, h->stream);
+  cudaMemsetAsync(B.p, 0, (size_t)N * ld * 8, h->stream);
+  cudaMemsetAsync(C.p, 0, (size_t)M * ldc * 8, h->stream);
+  MatView Av{A.as<double>(), M, K, ld}, Bv{B.as<double>(), N, K, ld};
+  rc = run_gemm_sub(h, Av, 0, 0, Bv, 0, 0, M, N, K, C.as<double>(), ldc, 0);  // warm-up
+  cudaEvent_t a = get_event(h), b = get_event(h);
+  cudaEventRecord(a, h->stream);
+  for (int i = 0; i < iters && rc == NNGP_OK; ++i) rc = run_gemm_sub(h, Av, 0, 0, Bv, 0, 0, M, N, K, C.as<double>(), ldc, 0);
+  cudaEventRecord(b, h->stream);
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  h->ev_pool.push_back(a); h->ev_pool.push_back(b);
+  flush_class_events(h);
+  h->tmaps.clear();  // the scratch operands are about to be freed
+  release(A); release(B); release(C);
+  if (rc != NNGP_OK) return rc;
+  if (e != cudaSuccess) return fail(h, NNGP_ECUDA, "gemm probe failed: %s", cudaGetErrorString(e));
+  *ms_out = ms / iters;
+  return NNGP_OK;
+}
+
+int nngp_diag_potrf(nngp_handle* h, double* a, int64_t N) {
+  if (!h || !a || N <= 0) return NNGP_EINVAL;
+  CKR(bind_device(h));
+  const int64_t ld = round_up(N, 16);
+  DevBuf A;
+  CKR(ensure(h, A, (size_t)N * ld * 8));
+  int rc = NNGP_OK;
+  cudaMemsetAsync(h->flags.p, 0, 2 * sizeof(int), h->stream);
+  rc = upload_matrix(h, a, N, N, A.as<double>(), ld);
+  if (rc == NNGP_OK) rc = run_potrf(h, A.as<double>(), ld, N);
+  if (rc == NNGP_OK) rc = download(h, A.as<double>(), N, N, ld, a);
+  int flags[2] = {0, 0};
+  cudaMemcpyAsync(flags, h->flags.p, sizeof flags, cudaMemcpyDeviceToHost, h->stream);
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  flush_class_events(h);
+  h->tmaps.clear();
+  release(A);
+  if (rc != NNGP_OK) return rc;
+  if (e != cudaSuccess) return fail(h, NNGP_ECUDA, "potrf failed: %s", cudaGetErrorString(e));
+  if (flags[0]) return fail(h, NNGP_ENOTPD, "nngp_diag_potrf: not positive definite (pivot %d)", flags[0] - 1);
+  return NNGP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,361 @@
+// dense_kernels.cuh -- the small kernels around the DMMA GEMM core:
+//   row_sqnorm / q_final          layer-0 kernel diagonal and K(x,x)            (K2, K9)
+//   diag_reg                      lambda = diag_reg * trace(K)/N ; K += lambda I (K4)
+//   potf2_64                      64x64 diagonal-block Cholesky in shared memory  (K5 panel)
+//   trsm_rows_64                  X L_JJ^T = B, one thread per row                (K5 panel, K10)
+//   trsv_fwd_step / trsv_bwd_step blocked forward / backward substitution         (K6)
+//   gemv_rows                     mean = K_* alpha, one warp per test row          (K8)
+//   var_rows                      var = K(x,x) - ||V_row||^2, one warp per row     (K10/K11)
+// All reductions have a fixed order: results are bitwise reproducible and independent of how
+// test rows are sharded over GPUs.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace nngp {
+
+constexpr int NB = 64;  // diagonal block size of the blocked factorisation / solves
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// q[r] = sw2 * sum_j x[r][j]^2 / D + sb2 ; one warp per row.
+__global__ void row_sqnorm_kernel(const double* __restrict__ x, long long ldx, int rows, int D, double sw2,
+                                  double sb2, double* __restrict__ q) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const double* xr = x + (long long)warp * ldx;
+  double s = 0.0;
+  for (int j = lane; j < D; j += 32) {
+    const double v = xr[j];
+    s = fma(v, v, s);
+  }
+  s = warp_sum(s);
+  if (lane == 0) q[warp] = sw2 * (s / (double)D) + sb2;
+}
+
+// kss[r] = layer-(depth-1) diagonal: q <- sw2*q/2 + sb2, `steps` times.
+__global__ void q_final_kernel(const double* __restrict__ q, int rows, int steps, double sw2, double sb2,
+                               double* __restrict__ kss) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  double v = q[i];
+  for (int s = 0; s < steps; ++s) v = sw2 * (0.5 * v) + sb2;
+  kss[i] = v;
+}
+
+// Single CTA: lambda = reg * (absolute ? 1 : trace(K)/N); K[i][i] += lambda.  lambda -> *lambda_out.
+__global__ void diag_reg_kernel(double* __restrict__ K, long long ld, int N, double reg, int absolute,
+                                double* __restrict__ lambda_out) {
+  __shared__ double red[32];
+  __shared__ double lam_s;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) s += K[(long long)i * ld + i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) {
+      const double r = reg > 0.0 ? reg : 0.0;
+      lam_s = absolute ? r : r * (v / (double)N);
+      *lambda_out = lam_s;
+    }
+  }
+  __syncthreads();
+  const double lam = lam_s;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) K[(long long)i * ld + i] += lam;
+}
+
+// In-place lower Cholesky of the n x n (n <= 64) block at A (row-major, ld).  One CTA, 256 threads.
+// On a non-positive pivot: *info = global pivot index + 1 (first failure wins), block left as is.
+__global__ void __launch_bounds__(256) potf2_64_kernel(double* __restrict__ A, long long ld, int n, int pivot0,
+                                                       int* __restrict__ info) {
+  __shared__ double As[NB][NB + 1];
+  __shared__ int bad;
+  const int tid = threadIdx.x;
+  if (tid == 0) bad = 0;
+  for (int idx = tid; idx < NB * NB; idx += 256) {
+    const int r = idx >> 6, c = idx & 63;
+    double v = (r == c) ? 1.0 : 0.0;
+    if (r < n && c <= r) v = A[(long long)r * ld + c];
+    As[r][c] = v;
+  }
+  __syncthreads();
+  for (int j = 0; j < n; ++j) {
+    const double d = As[j][j];
+    if (!(d > 0.0)) {  // also catches NaN
+      if (tid == 0) { bad = 1; atomicCAS(info, 0, pivot0 + j + 1); }
+      break;           // d is uniform across the CTA => uniform exit
+    }
+    const double piv = sqrt(d);
+    __syncthreads();  // everyone has read As[j][j]
+    if (tid == 0) As[j][j] = piv;
+    for (int i = j + 1 + tid; i < n; i += 256) As[i][j] = As[i][j] / piv;
+    __syncthreads();
+    const int m = n - j - 1;
+    for (int idx = tid; idx < m * m; idx += 256) {
+      const int ii = idx / m, kk = idx - ii * m;
+      if (kk <= ii) {
+        const int i = j + 1 + ii, k = j + 1 + kk;
+        As[i][k] = fma(-As[i][j], As[k][j], As[i][k]);
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (bad) return;
+  for (int idx = tid; idx < NB * NB; idx += 256) {
+    const int r = idx >> 6, c = idx & 63;
+    if (r < n && c <= r) A[(long long)r * ld + c] = As[r][c];
+  }
+}
+
+// X * Ljj^T = B in place, for `rows` rows of B (row-major, ldb) and the n x n (n <= 64) lower block
+// Ljj (row-major, ldl).  128 rows per CTA, one thread per row, forward substitution along the row.
+constexpr int TRSM_ROWS = 128;
+constexpr int TRSM_SMEM_BYTES = (TRSM_ROWS * (NB + 1) + NB * (NB + 1)) * 8;
+__global__ void __launch_bounds__(TRSM_ROWS) trsm_rows_64_kernel(double* __restrict__ B, long long ldb, int rows,
+                                                                const double* __restrict__ Ljj, long long ldl,
+                                                                int n) {
+  extern __shared__ double sm[];
+  double(*Bs)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm);
+  double(*Ls)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm + TRSM_ROWS * (NB + 1));
+  const int tid = threadIdx.x;
+  const int row0 = blockIdx.x * TRSM_ROWS;
+  for (int idx = tid; idx < NB * NB; idx += TRSM_ROWS) {
+    const int r = idx >> 6, c = idx & 63;
+    double v = (r == c) ? 1.0 : 0.0;
+    if (r < n && c <= r) v = Ljj[(long long)r * ldl + c];
+    Ls[r][c] = v;
+  }
+  for (int idx = tid; idx < TRSM_ROWS * NB; idx += TRSM_ROWS) {
+    const int r = idx >> 6, c = idx & 63;
+    double v = 0.0;
+    if (row0 + r < rows && c < n) v = B[(long long)(row0 + r) * ldb + c];
+    Bs[r][c] = v;
+  }
+  __syncthreads();
+  double* xr = Bs[tid];
+  for (int j = 0; j < n; ++j) {
+    double s0 = xr[j], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    const double* lj = Ls[j];
+    int k = 0;
+    for (; k + 3 < j; k += 4) {
+      s0 = fma(-xr[k], lj[k], s0);
+      s1 = fma(-xr[k + 1], lj[k + 1], s1);
+      s2 = fma(-xr[k + 2], lj[k + 2], s2);
+      s3 = fma(-xr[k + 3], lj[k + 3], s3);
+    }
+    for (; k < j; ++k) s0 = fma(-xr[k], lj[k], s0);
+    xr[j] = ((s0 + s1) + (s2 + s3)) / lj[j];
+  }
+  __syncthreads();
+  for (int idx = tid; idx < TRSM_ROWS * NB; idx += TRSM_ROWS) {
+    const int r = idx >> 6, c = idx & 63;
+    if (row0 + r < rows && c < n) B[(long long)(row0 + r) * ldb + c] = Bs[r][c];
+  }
+}
+
+// Shared helper: load the n x n lower block Ljj into Ls (identity padded) and the n rhs entries.
+__device__ __forceinline__ void load_diag_block(const double* __restrict__ Ljj, long long ldl, int n,
+                                                double (*Ls)[NB + 1]) {
+  for (int idx = threadIdx.x; idx < NB * NB; idx += blockDim.x) {
+    const int r = idx >> 6, c = idx & 63;
+    double v = (r == c) ? 1.0 : 0.0;
+    if (r < n && c <= r) v = Ljj[(long long)r * ldl + c];
+    Ls[r][c] = v;
+  }
+}
+
+// Forward step of L z = y for diagonal block [j0, j0+n): every CTA solves the 64x64 diagonal system
+// redundantly in its warp 0 (bitwise identical), CTA 0 publishes z_J into y, and all CTAs apply
+// y[r] -= L[r, j0:j0+n] . z_J to their rows r >= j0+n (one warp per row, coalesced 512 B reads).
+constexpr int TRSV_THREADS = 256;
+__global__ void __launch_bounds__(TRSV_THREADS) trsv_fwd_step_kernel(const double* __restrict__ L, long long ld,
+                                                                    int N, int j0, int n,
+                                                                    double* __restrict__ y) {
+  __shared__ double Ls[NB][NB + 1];
+  __shared__ double zs[NB];
+  load_diag_block(L + (long long)j0 * ld + j0, ld, n, Ls);
+  if (threadIdx.x < NB) zs[threadIdx.x] = (threadIdx.x < n) ? y[j0 + threadIdx.x] : 0.0;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    double y0 = zs[lane], y1 = zs[lane + 32];  // lane owns entries lane, lane+32
+    for (int k = 0; k < NB; ++k) {
+      const double num = __shfl_sync(0xffffffffu, (k < 32) ? y0 : y1, k & 31);
+      const double zk = num / Ls[k][k];
+      if (lane == (k & 31)) { if (k < 32) y0 = zk; else y1 = zk; }
+      if (lane > k) y0 = fma(-Ls[lane][k], zk, y0);
+      if (lane + 32 > k) y1 = fma(-Ls[lane + 32][k], zk, y1);
+    }
+    zs[lane] = y0;
+    zs[lane + 32] = y1;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x < n) y[j0 + threadIdx.x] = zs[threadIdx.x];
+  const int lane = threadIdx.x & 31;
+  const int warps_per_cta = TRSV_THREADS / 32;
+  const double z0 = zs[2 * lane], z1 = zs[2 * lane + 1];
+  for (long long r = (long long)j0 + n + blockIdx.x * warps_per_cta + (threadIdx.x >> 5); r < N;
+       r += (long long)gridDim.x * warps_per_cta) {
+    const double* lr = L + r * ld + j0;
+    double s = 0.0;
+    if (2 * lane + 1 < n) {
+      const double2 v = *reinterpret_cast<const double2*>(lr + 2 * lane);
+      s = fma(v.x, z0, v.y * z1);
+    } else if (2 * lane < n) {
+      s = lr[2 * lane] * z0;
+    }
+    s = warp_sum(s);
+    if (lane == 0) y[r] -= s;
+  }
+}
+
+// Backward step of L^T a = z for diagonal block [j0, j0+n): every CTA solves Ljj^T a_J = z_J
+// redundantly, CTA 0 publishes a_J into z, and all CTAs apply z[c] -= sum_i L[j0+i][c] a_i to the
+// columns c < j0 (one thread per column, coalesced row reads).
+__global__ void __launch_bounds__(TRSV_THREADS) trsv_bwd_step_kernel(const double* __restrict__ L, long long ld,
+                                                                    int j0, int n, double* __restrict__ z) {
+  __shared__ double Ls[NB][NB + 1];
+  __shared__ double as[NB];
+  load_diag_block(L + (long long)j0 * ld + j0, ld, n, Ls);
+  if (threadIdx.x < NB) as[threadIdx.x] = (threadIdx.x < n) ? z[j0 + threadIdx.x] : 0.0;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    double y0 = as[lane], y1 = as[lane + 32];
+    for (int k = NB - 1; k >= 0; --k) {
+      const double num = __shfl_sync(0xffffffffu, (k < 32) ? y0 : y1, k & 31);
+      const double ak = num / Ls[k][k];
+      if (lane == (k & 31)) { if (k < 32) y0 = ak; else y1 = ak; }
+      if (lane < k) y0 = fma(-Ls[k][lane], ak, y0);
+      if (lane + 32 < k) y1 = fma(-Ls[k][lane + 32], ak, y1);
+    }
+    as[lane] = y0;
+    as[lane + 32] = y1;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x < n) z[j0 + threadIdx.x] = as[threadIdx.x];
+  for (long long c = (long long)blockIdx.x * TRSV_THREADS + threadIdx.x; c < j0;
+       c += (long long)gridDim.x * TRSV_THREADS) {
+    const double* lc = L + (long long)j0 * ld + c;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int i = 0;
+    for (; i + 3 < n; i += 4) {
+      s0 = fma(lc[(long long)i * ld], as[i], s0);
+      s1 = fma(lc[(long long)(i + 1) * ld], as[i + 1], s1);
+      s2 = fma(lc[(long long)(i + 2) * ld], as[i + 2], s2);
+      s3 = fma(lc[(long long)(i + 3) * ld], as[i + 3], s3);
+    }
+    for (; i < n; ++i) s0 = fma(lc[(long long)i * ld], as[i], s0);
+    z[c] -= (s0 + s1) + (s2 + s3);
+  }
+}
+
+// mean[r] = sum_j B[r][j] * alpha[j]; one warp per row, 4 independent partial sums per lane.
+__global__ void gemv_rows_kernel(const double* __restrict__ B, long long ldb, int rows, int N,
+                                 const double* __restrict__ alpha, double* __restrict__ mean) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const double* br = B + (long long)warp * ldb;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int j = 2 * lane;
+  for (; j + 193 < N; j += 256) {
+    const double2 b0 = *reinterpret_cast<const double2*>(br + j);
+    const double2 b1 = *reinterpret_cast<const double2*>(br + j + 64);
+    const double2 b2 = *reinterpret_cast<const double2*>(br + j + 128);
+    const double2 b3 = *reinterpret_cast<const double2*>(br + j + 192);
+    const double2 a0 = *reinterpret_cast<const double2*>(alpha + j);
+    const double2 a1 = *reinterpret_cast<const double2*>(alpha + j + 64);
+    const double2 a2 = *reinterpret_cast<const double2*>(alpha + j + 128);
+    const double2 a3 = *reinterpret_cast<const double2*>(alpha + j + 192);
+    s0 = fma(b0.x, a0.x, s0); s0 = fma(b0.y, a0.y, s0);
+    s1 = fma(b1.x, a1.x, s1); s1 = fma(b1.y, a1.y, s1);
+    s2 = fma(b2.x, a2.x, s2); s2 = fma(b2.y, a2.y, s2);
+    s3 = fma(b3.x, a3.x, s3); s3 = fma(b3.y, a3.y, s3);
+  }
+  for (; j < N; j += 64) {
+    s0 = fma(br[j], alpha[j], s0);
+    if (j + 1 < N) s0 = fma(br[j + 1], alpha[j + 1], s0);
+  }
+  const double s = warp_sum((s0 + s1) + (s2 + s3));
+  if (lane == 0) mean[warp] = s;
+}
+
+// var[r] = kss[r] - sum_j V[r][j]^2; one warp per row.
+__global__ void var_rows_kernel(const double* __restrict__ V, long long ldv, int rows, int N,
+                                const double* __restrict__ kss, double* __restrict__ var) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const double* vr = V + (long long)warp * ldv;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int j = 2 * lane;
+  for (; j + 193 < N; j += 256) {
+    const double2 b0 = *reinterpret_cast<const double2*>(vr + j);
+    const double2 b1 = *reinterpret_cast<const double2*>(vr + j + 64);
+    const double2 b2 = *reinterpret_cast<const double2*>(vr + j + 128);
+    const double2 b3 = *reinterpret_cast<const double2*>(vr + j + 192);
+    s0 = fma(b0.x, b0.x, s0); s0 = fma(b0.y, b0.y, s0);
+    s1 = fma(b1.x, b1.x, s1); s1 = fma(b1.y, b1.y, s1);
+    s2 = fma(b2.x, b2.x, s2); s2 = fma(b2.y, b2.y, s2);
+    s3 = fma(b3.x, b3.x, s3); s3 = fma(b3.y, b3.y, s3);
+  }
+  for (; j < N; j += 64) {
+    s0 = fma(vr[j], vr[j], s0);
+    if (j + 1 < N) s0 = fma(vr[j + 1], vr[j + 1], s0);
+  }
+  const double s = warp_sum((s0 + s1) + (s2 + s3));
+  if (lane == 0) var[warp] = kss[warp] - s;
+}
+
+// zero the strict upper triangle of an N x N row-major matrix (state export)
+__global__ void zero_upper_kernel(double* __restrict__ A, long long ld, int N) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  for (long long i = blockIdx.y; i < N && i < j; i += gridDim.y) A[i * ld + j] = 0.0;
+}
+
+// finite check: *flag |= any non-finite in x (rows x cols, ld)
+__global__ void finite_check_kernel(const double* __restrict__ x, long long ld, long long rows, int cols,
+                                    int* __restrict__ flag) {
+  const long long total = rows * cols;
+  int bad = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    if (!isfinite(x[r * ld + c])) bad = 1;
+  }
+  if (bad) atomicOr(flag, 1);
+}
+
+// Register-resident DMMA issue-rate microbenchmark: 8 warps per CTA, 16 independent accumulators.
+__global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* __restrict__ sink) {
+  double c[16][2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { c[i][0] = 0.0; c[i][1] = 0.0; }
+  double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c[i][0]), "+d"(c[i][1])
+                   : "d"(a), "d"(b));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+  if (s == 123.456) sink[0] = s;
+}
+
+}  // namespace nngp

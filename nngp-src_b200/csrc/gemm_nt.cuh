@@ -1,0 +1,249 @@
+// gemm_nt.cuh -- the FP64 "NT" tensor-core GEMM core every dense stage of the hot path uses:
+//
+//     acc(128 x 64) = A[m0:m0+128, k0:k0+K] * B[n0:n0+64, k0:k0+K]^T      (both row-major,
+//                                                                         K contiguous)
+//
+//   * operands: TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B, box 16 doubles x {128|64} rows)
+//     into a 4-stage shared-memory ring, full/empty mbarriers, one dedicated producer warp;
+//   * math: 8 consumer warps (4 along M x 2 along N), each a 32 x 32 warp tile = 4 x 4
+//     mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4) accumulators, 64 FP64 registers per thread;
+//   * 288 threads, ~97 KB smem -> 2 CTAs per SM, so one CTA's epilogue hides under the
+//     other's main loop;
+//   * epilogues: (GRAM) the NNGP arc-cosine recursion of SURVEY Appendix A.1 applied in
+//     registers -- intermediate layer kernels never touch HBM -- or (SUB) C -= acc, the
+//     trailing/left-looking update of the blocked Cholesky and triangular solves.
+//
+// Shared-memory layout of one operand stage (what SWIZZLE_128B produces): row r occupies
+// bytes [128 r, 128 r + 128); the 16-byte chunk c of that row lands at chunk c ^ (r & 7).
+// A DMMA A/B fragment load (lane 4g+t reads row g, k = 4*k4 + t) therefore touches each of
+// the 8 chunk columns exactly twice per warp => 2 wavefronts for 256 B: conflict-free.
+#pragma once
+#include "ptx.cuh"
+
+namespace nngp {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BN = 64;
+constexpr int GEMM_BK = 16;
+constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_CONSUMER_WARPS = 8;
+constexpr int GEMM_THREADS = (GEMM_CONSUMER_WARPS + 1) * 32;
+constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * GEMM_BK * 8;  // 16 KiB
+constexpr int GEMM_B_STAGE_BYTES = GEMM_BN * GEMM_BK * 8;  //  8 KiB
+constexpr int GEMM_STAGE_TX_BYTES = GEMM_A_STAGE_BYTES + GEMM_B_STAGE_BYTES;
+// ring + barriers + 1 KiB slack so the ring can be aligned to the 1024 B swizzle atom
+constexpr int GEMM_SMEM_BYTES =
+    GEMM_STAGES * (GEMM_A_STAGE_BYTES + GEMM_B_STAGE_BYTES) + 2 * GEMM_STAGES * 8 + 1024;
+
+enum GemmEpilogue : int { EPI_GRAM = 0, EPI_SUB = 1 };
+
+struct GemmParams {
+  int M, N;            // valid output extent (rows of the A range, rows of the B range)
+  int ktiles;          // number of 16-wide K tiles
+  int a_row0, a_col0;  // origin of the A range inside tensor map A (elements)
+  int b_row0, b_col0;  // origin of the B range inside tensor map B
+  double* C;           // output, already offset to the (0,0) element of the range
+  long long ldc;
+  int lower;           // 1: tiles strictly above the diagonal of the range are skipped
+  // EPI_GRAM only
+  const double* q1;    // per-row layer-0 diagonal of the A rows  (sigma_w^2 |x|^2/D + sigma_b^2)
+  const double* q2;    // same for the B rows
+  double scale;        // sigma_w^2 / D
+  double sw2, sb2;     // sigma_w^2, sigma_b^2
+  int steps;           // depth-1 arc-cosine steps
+};
+
+// One ReLU arc-cosine step followed by the next Dense layer's affine map
+// ([nt 0.6.1 stax.ABRelu(a=0,b=1) nngp_ntk_fn + stax.Dense _affine]):
+//   s = sqrt(max(q1 q2 - k^2, 0)); theta = atan2(s, k) (pi/2 when s == k == 0)
+//   k' = sw2 * ( s/(2 pi) + (1/2 - theta/(2 pi)) k ) + sb2
+__device__ __forceinline__ double arccos_step(double k, double q1, double q2, double sw2, double sb2) {
+  const double inv_2pi = 0.15915494309189533577;
+  const double half_pi = 1.57079632679489661923;
+  double s2 = q1 * q2 - k * k;
+  double s = sqrt(fmax(s2, 0.0));
+  double theta = (s == 0.0 && k == 0.0) ? half_pi : atan2(s, k);
+  double dot_sigma = 0.5 - inv_2pi * theta;
+  double r = inv_2pi * s + dot_sigma * k;
+  return sw2 * r + sb2;
+}
+
+template <int EPI>
+__global__ void __maxnreg__(112)
+gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const GemmParams p) {
+  const int tile_n = blockIdx.x;
+  const int tile_m = blockIdx.y;
+  if (p.lower && tile_n * GEMM_BN > tile_m * GEMM_BM + (GEMM_BM - 1)) return;
+
+  extern __shared__ uint8_t smem_raw[];
+  // align the ring to the 1024 B swizzle atom
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+  uint8_t* ring = smem_raw + pad;
+  uint8_t* ringA = ring;
+  uint8_t* ringB = ring + GEMM_STAGES * GEMM_A_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ringB + GEMM_STAGES * GEMM_B_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + GEMM_STAGES;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < GEMM_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], GEMM_CONSUMER_WARPS);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const int ktiles = p.ktiles;
+
+  if (warp == GEMM_CONSUMER_WARPS) {
+    // ===== TMA producer (one elected lane) =====
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      const int arow = p.a_row0 + tile_m * GEMM_BM;
+      const int brow = p.b_row0 + tile_n * GEMM_BN;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kt = 0; kt < ktiles; ++kt) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);  // first pass over the ring falls through
+        mbar_arrive_expect_tx(&full_bar[stage], GEMM_STAGE_TX_BYTES);
+        tma_load_2d(ringA + stage * GEMM_A_STAGE_BYTES, &tmA, p.a_col0 + kt * GEMM_BK, arow, &full_bar[stage]);
+        tma_load_2d(ringB + stage * GEMM_B_STAGE_BYTES, &tmB, p.b_col0 + kt * GEMM_BK, brow, &full_bar[stage]);
+        if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+    return;
+  }
+
+  // ===== consumers =====
+  const int wm = warp >> 1;  // 0..3 : 32-row slab
+  const int wn = warp & 1;   // 0..1 : 32-col slab
+  const int g = lane >> 2;   // fragment row / col group
+  const int t = lane & 3;    // position inside the group
+
+  const int row_base = tile_m * GEMM_BM + wm * 32 + g;      // + 8*mi
+  const int col_base = tile_n * GEMM_BN + wn * 32 + 2 * t;  // + 8*ni (+0/1)
+
+  double acc[4][4][2];
+  if constexpr (EPI == EPI_SUB) {
+    // start from -C so that the stored result -(acc) = C - A B^T needs no extra registers and
+    // the C read overlaps the TMA prologue
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+      const int r = row_base + 8 * mi;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int c = col_base + 8 * ni;
+        double v0 = 0.0, v1 = 0.0;
+        if (r < p.M) {
+          const double* src = p.C + (long long)r * p.ldc + c;
+          if (c + 1 < p.N) {
+            const double2 v = *reinterpret_cast<const double2*>(src);
+            v0 = v.x; v1 = v.y;
+          } else if (c < p.N) {
+            v0 = src[0];
+          }
+        }
+        acc[mi][ni][0] = -v0;
+        acc[mi][ni][1] = -v1;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+  }
+
+  // swizzled byte offset of (row with r&7 == g, k = 4*k4 + t) inside a stage, minus 128*row
+  uint32_t koff[4];
+#pragma unroll
+  for (int k4 = 0; k4 < 4; ++k4) koff[k4] = ((uint32_t)((2 * k4 + (t >> 1)) ^ g) << 4) | ((uint32_t)(t & 1) << 3);
+
+  const uint32_t a_warp = smem_u32(ringA) + (uint32_t)(wm * 32 + g) * 128u;
+  const uint32_t b_warp = smem_u32(ringB) + (uint32_t)(wn * 32 + g) * 128u;
+
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int kt = 0; kt < ktiles; ++kt) {
+    mbar_wait(&full_bar[stage], phase);
+    const uint32_t a_st = a_warp + stage * GEMM_A_STAGE_BYTES;
+    const uint32_t b_st = b_warp + stage * GEMM_B_STAGE_BYTES;
+#pragma unroll
+    for (int k4 = 0; k4 < 4; ++k4) {
+      double a[4], b[4];
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) a[mi] = lds_f64(a_st + mi * 1024 + koff[k4]);
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) b[ni] = lds_f64(b_st + ni * 1024 + koff[k4]);
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) dmma_884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[stage]);
+    if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1u; }
+  }
+
+  // ===== epilogue (registers -> global) =====
+  if constexpr (EPI == EPI_SUB) {
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+      const int r = row_base + 8 * mi;
+      if (r >= p.M) continue;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int c = col_base + 8 * ni;
+        double* dst = p.C + (long long)r * p.ldc + c;
+        if (c + 1 < p.N) {
+          *reinterpret_cast<double2*>(dst) = make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
+        } else if (c < p.N) {
+          dst[0] = -acc[mi][ni][0];
+        }
+      }
+    }
+  } else {
+    double q2v[4][2];
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      const int c = col_base + 8 * ni;
+      q2v[ni][0] = (c < p.N) ? p.q2[c] : 0.0;
+      q2v[ni][1] = (c + 1 < p.N) ? p.q2[c + 1] : 0.0;
+    }
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+      const int r = row_base + 8 * mi;
+      if (r >= p.M) continue;
+      const double q1r = p.q1[r];
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int c = col_base + 8 * ni;
+        double k0 = p.scale * acc[mi][ni][0] + p.sb2;
+        double k1 = p.scale * acc[mi][ni][1] + p.sb2;
+        double qa = q1r, qb0 = q2v[ni][0], qb1 = q2v[ni][1];
+        for (int s = 0; s < p.steps; ++s) {
+          k0 = arccos_step(k0, qa, qb0, p.sw2, p.sb2);
+          k1 = arccos_step(k1, qa, qb1, p.sw2, p.sb2);
+          qa = p.sw2 * (0.5 * qa) + p.sb2;
+          qb0 = p.sw2 * (0.5 * qb0) + p.sb2;
+          qb1 = p.sw2 * (0.5 * qb1) + p.sb2;
+        }
+        double* dst = p.C + (long long)r * p.ldc + c;
+        if (c + 1 < p.N) {
+          *reinterpret_cast<double2*>(dst) = make_double2(k0, k1);
+        } else if (c < p.N) {
+          dst[0] = k0;
+        }
+      }
+    }
+  }
+}
+
+}  // namespace nngp

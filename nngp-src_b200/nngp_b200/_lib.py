@@ -1,0 +1,243 @@
+"""ctypes binding of the C ABI in ``include/nngp_b200.h`` (``libnngp_b200.so``).
+
+This module is the ONLY way the Python host layer reaches arithmetic: every kernel /
+fit / predict call goes through the shared library's sm_100a CUDA kernels.  There is no
+CPU fallback -- if the library is missing, or no B200 is visible, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = Path(os.environ.get("NNGP_B200_LIB", _PKG_DIR.parent / "libnngp_b200.so"))
+
+NNGP_OK, NNGP_EINVAL, NNGP_ENOTPD, NNGP_ECUDA, NNGP_ENOMEM, NNGP_ESTATE, NNGP_ENODEV = 0, -1, -2, -3, -4, -5, -6
+
+
+class NngpConfig(C.Structure):
+    _fields_ = [
+        ("depth", C.c_int32),
+        ("sigma_w", C.c_double),
+        ("sigma_b", C.c_double),
+        ("diag_reg", C.c_double),
+        ("diag_reg_absolute", C.c_int32),
+        ("device", C.c_int32),
+        ("max_block_bytes", C.c_int64),
+        ("stats_level", C.c_int32),
+    ]
+
+
+class NngpStats(C.Structure):
+    _fields_ = (
+        [(n, C.c_double) for n in (
+            "fit_gram_ms", "fit_chol_ms", "fit_solve_ms", "fit_total_ms",
+            "pred_gram_ms", "pred_mean_ms", "pred_trsm_ms", "pred_var_ms", "pred_total_ms",
+            "h2d_ms", "d2h_ms", "gemm_ms", "gemm_flops")]
+        + [("gemm_launches", C.c_int64)]
+        + [(n, C.c_double) for n in ("gram_ms", "gram_flops", "gram_evals")]
+        + [(n, C.c_int64) for n in ("gram_launches", "kernel_launches", "h2d_bytes", "d2h_bytes", "queries")]
+    )
+
+    def as_dict(self) -> dict:
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+# every symbol include/nngp_b200.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+_I64 = C.c_int64
+_DP = C.POINTER(C.c_double)
+EXPORTS = {
+    "nngp_abi_version": (C.c_int, []),
+    "nngp_default_config": (None, [C.POINTER(NngpConfig)]),
+    "nngp_create": (C.c_int, [C.POINTER(NngpConfig), C.POINTER(_P)]),
+    "nngp_destroy": (None, [_P]),
+    "nngp_last_error": (C.c_char_p, [_P]),
+    "nngp_get_stream": (_P, [_P]),
+    "nngp_kernel": (C.c_int, [_P, _P, _I64, _P, _I64, _I64, _P]),
+    "nngp_fit": (C.c_int, [_P, _P, _P, _I64, _I64]),
+    "nngp_predict": (C.c_int, [_P, _P, _I64, _P, _P]),
+    "nngp_get_dims": (C.c_int, [_P, C.POINTER(_I64), C.POINTER(_I64), _DP]),
+    "nngp_get_state": (C.c_int, [_P, _P, _P, _P]),
+    "nngp_set_state": (C.c_int, [_P, _P, _P, _P, _I64, _I64, C.c_double]),
+    "nngp_stats": (C.c_int, [_P, C.POINTER(NngpStats)]),
+    "nngp_stats_reset": (C.c_int, [_P]),
+    "nngp_diag_dmma_peak": (C.c_int, [_P, _DP]),
+    "nngp_diag_gemm_probe": (C.c_int, [_P, _I64, _I64, _I64, C.c_int32, _DP]),
+    "nngp_diag_potrf": (C.c_int, [_P, _P, _I64]),
+}
+
+_lib = None
+
+
+class NngpError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"nngp_b200 error {code}: {msg}")
+        self.code = code
+
+
+def load() -> C.CDLL:
+    """Load libnngp_b200.so (built in-tree by ``__graft_entry__.build()``). Fails loudly if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nngp_b200 has no CPU fallback)")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _raise(lib, handle, code: int):
+    msg = lib.nngp_last_error(handle)
+    msg = msg.decode("utf-8", "replace") if msg else ""
+    if code == NNGP_EINVAL:
+        raise ValueError(f"nngp_b200: {msg}")
+    if code == NNGP_ENOTPD:
+        raise np.linalg.LinAlgError(f"nngp_b200: {msg}")
+    raise NngpError(code, msg)
+
+
+def _ptr(a):
+    """(pointer, keepalive) for a numpy array (host) or a torch CUDA/CPU tensor (device/host)."""
+    if a is None:
+        return None, None
+    if isinstance(a, np.ndarray):
+        if a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"]:
+            a = np.ascontiguousarray(a, dtype=np.float64)
+        return C.c_void_p(a.ctypes.data), a
+    if hasattr(a, "data_ptr"):  # torch tensor
+        import torch
+        if a.dtype != torch.float64 or not a.is_contiguous():
+            a = a.to(torch.float64).contiguous()
+        return C.c_void_p(a.data_ptr()), a
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return C.c_void_p(a.ctypes.data), a
+
+
+class Handle:
+    """RAII wrapper of ``nngp_handle*`` (one GPU, not re-entrant)."""
+
+    def __init__(self, depth=2, sigma_w=1.0, sigma_b=0.0, diag_reg=1e-3, diag_reg_absolute=False,
+                 device=-1, max_block_bytes=0, stats_level=1):
+        self._lib = load()
+        cfg = NngpConfig()
+        self._lib.nngp_default_config(C.byref(cfg))
+        cfg.depth, cfg.sigma_w, cfg.sigma_b = int(depth), float(sigma_w), float(sigma_b)
+        cfg.diag_reg, cfg.diag_reg_absolute = float(diag_reg), int(bool(diag_reg_absolute))
+        cfg.device, cfg.max_block_bytes, cfg.stats_level = int(device), int(max_block_bytes), int(stats_level)
+        self.cfg = cfg
+        h = C.c_void_p()
+        rc = self._lib.nngp_create(C.byref(cfg), C.byref(h))
+        if rc != NNGP_OK:
+            _raise(self._lib, None, rc)
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.nngp_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _ck(self, rc):
+        if rc != NNGP_OK:
+            _raise(self._lib, self._h, rc)
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.nngp_get_stream(self._h) or 0)
+
+    def kernel(self, x1, x2=None, out=None):
+        x1p, k1 = _ptr(x1)
+        M, D = k1.shape
+        x2p, k2 = _ptr(x2)
+        N2 = k2.shape[0] if k2 is not None else M
+        if k2 is not None and k2.shape[1] != D:
+            raise ValueError(f"nngp_b200: x1 has {D} features but x2 has {k2.shape[1]}")
+        if out is None:
+            out = np.empty((M, N2), dtype=np.float64)
+        op, _ko = _ptr(out)
+        self._ck(self._lib.nngp_kernel(self._h, x1p, M, x2p, N2, D, op))
+        return out
+
+    def fit(self, x, y):
+        xp, kx = _ptr(x)
+        yp, ky = _ptr(y)
+        N, D = kx.shape
+        if int(np.prod(ky.shape)) != N:
+            raise ValueError(f"nngp_b200: y_train has {int(np.prod(ky.shape))} entries for {N} training rows")
+        self._ck(self._lib.nngp_fit(self._h, xp, yp, N, D))
+
+    def predict(self, x, want_var=True, mean_out=None, var_out=None):
+        xp, kx = _ptr(x)
+        T = kx.shape[0]
+        if mean_out is None:
+            mean_out = np.empty(T, dtype=np.float64)
+        if want_var and var_out is None:
+            var_out = np.empty(T, dtype=np.float64)
+        mp, _km = _ptr(mean_out)
+        vp, _kv = _ptr(var_out) if want_var else (None, None)
+        self._ck(self._lib.nngp_predict(self._h, xp, T, mp, vp))
+        return mean_out, (var_out if want_var else None)
+
+    def dims(self):
+        n, d, lam = _I64(), _I64(), C.c_double()
+        self._ck(self._lib.nngp_get_dims(self._h, C.byref(n), C.byref(d), C.byref(lam)))
+        return n.value, d.value, lam.value
+
+    def get_state(self, x=True, l=True, alpha=True, out=None):
+        """Copy the fitted state out. ``out`` may be a dict of preallocated arrays/tensors (host or device)."""
+        n, d, lam = self.dims()
+        out = dict(out or {})
+        if x and "x" not in out:
+            out["x"] = np.empty((n, d))
+        if l and "l" not in out:
+            out["l"] = np.empty((n, n))
+        if alpha and "alpha" not in out:
+            out["alpha"] = np.empty(n)
+        xp, _a = _ptr(out.get("x") if x else None)
+        lp, _b = _ptr(out.get("l") if l else None)
+        ap, _c = _ptr(out.get("alpha") if alpha else None)
+        self._ck(self._lib.nngp_get_state(self._h, xp, lp, ap))
+        out["lambda"] = lam
+        return out
+
+    def set_state(self, x, l, alpha, lam):
+        xp, kx = _ptr(x)
+        lp, _kl = _ptr(l)
+        ap, _ka = _ptr(alpha)
+        N, D = kx.shape
+        self._ck(self._lib.nngp_set_state(self._h, xp, lp, ap, N, D, float(lam)))
+
+    def stats(self) -> dict:
+        s = NngpStats()
+        self._ck(self._lib.nngp_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def stats_reset(self):
+        self._ck(self._lib.nngp_stats_reset(self._h))
+
+    def dmma_peak_tflops(self) -> float:
+        v = C.c_double()
+        self._ck(self._lib.nngp_diag_dmma_peak(self._h, C.byref(v)))
+        return v.value
+
+    def gemm_probe_ms(self, M, N, K, iters=10) -> float:
+        v = C.c_double()
+        self._ck(self._lib.nngp_diag_gemm_probe(self._h, M, N, K, iters, C.byref(v)))
+        return v.value
+
+    def potrf(self, a: np.ndarray) -> np.ndarray:
+        a = np.array(a, dtype=np.float64, order="C", copy=True)
+        self._ck(self._lib.nngp_diag_potrf(self._h, C.c_void_p(a.ctypes.data), a.shape[0]))
+        return np.tril(a)

@@ -1,0 +1,139 @@
+"""CPU ORACLE -- TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED AGAINST THE REFERENCE.
+
+A numpy/scipy FP64 restatement of the one hot path of Kangfei/NNGP-src that this repo replaces:
+NNGP kernel construction + exact GP posterior inference.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may
+import this module, and only as the checker / CPU baseline -- never the product path
+(``nngp_b200`` never imports it and has no CPU fallback).
+
+Why "parity unpinned": the reference delegates ALL arithmetic on this path to the third-party
+package **neural-tangents 0.6.1** on **jax 0.3.23 / jaxlib 0.3.22** (pins: reference
+``nngp.yaml:78,79,88``), which is neither vendored under the reference tree nor installable here
+(no network), and the reference ships no tests, golden vectors or fixtures for the path
+(SURVEY.md section 4 / 8c).  This file therefore restates neural-tangents' published algorithm and is
+anchored on the reference's own call sites; it is pinned instead by (i) analytic known answers,
+(ii) a 50-digit mpmath restatement (``oracle/mp_oracle.py`` -> ``tests/golden/mp_small.npz``) and
+(iii) a finite-width Monte-Carlo check of the conventions (``tests/test_oracle.py``).
+
+Reference call sites restated (file:line under the reference tree):
+  * model        stax.serial(Dense(512), Relu(), Dense(1))            train.py:161-164,
+                 neuroestimator/estimator/estimator.py:27-30, active/active_train.py:40-43
+  * FP64         config.update("jax_enable_x64", True)                train.py:24, estimator.py:12
+  * fit          nt.predict.gradient_descent_mse_ensemble(kernel_fn, X, Y, diag_reg=1e-3)
+                                                                      train.py:171-172, estimator.py:34-35,
+                                                                      active/ActiveLearner.py:27-28
+  * predict      predict_fn(x_test=X, get='nngp', compute_cov=True)   train.py:157-158, estimator.py:66-67
+  * std          np.sqrt(np.diag(pred_cov))                           train.py:180, estimator.py:55,
+                                                                      active/ActiveLearner.py:46
+  * AL selection std/max(mean); argsort(std)[-budget:]                active/ActiveLearner.py:46-54
+[nt-upstream] callees restated: stax._inputs_to_kernel, stax.Dense (_affine), stax.ABRelu(a=0,b=1)
+(0.6.1 arctan2 form), predict._add_diagonal_regularizer, predict._get_cho_solve, predict.gp_inference.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.linalg as sla
+
+TWO_PI = 2.0 * np.pi
+
+
+def layer0_diag(x: np.ndarray, sigma_w: float = 1.0, sigma_b: float = 0.0) -> np.ndarray:
+    """q0 = sigma_w^2 |x|^2 / D + sigma_b^2   [nt: _inputs_to_kernel (/channel count) then Dense._affine]."""
+    x = np.asarray(x, dtype=np.float64)
+    return sigma_w**2 * (np.einsum("ij,ij->i", x, x) / x.shape[1]) + sigma_b**2
+
+
+def final_diag(q0: np.ndarray, depth: int = 2, sigma_w: float = 1.0, sigma_b: float = 0.0) -> np.ndarray:
+    """K(x,x) after depth-1 ReLU steps: q <- sigma_w^2 q/2 + sigma_b^2   [nt: ABRelu nngp_fn_diag + Dense]."""
+    q = np.array(q0, dtype=np.float64, copy=True)
+    for _ in range(depth - 1):
+        q = sigma_w**2 * (0.5 * q) + sigma_b**2
+    return q
+
+
+def kernel_fn(x1: np.ndarray, x2: np.ndarray | None = None, depth: int = 2, sigma_w: float = 1.0,
+              sigma_b: float = 0.0, chunk: int = 2048) -> np.ndarray:
+    """NNGP kernel K(x1, x2) of a depth-`depth` Dense/ReLU network.
+
+    k0 = sigma_w^2 x1.x2^T / D + sigma_b^2, then depth-1 times
+      s = sqrt(max(q1 q2 - k^2, 0)); theta = arctan2(s, k) (pi/2 where s == k == 0)
+      k <- sigma_w^2 ( s/(2 pi) + (1/2 - theta/(2 pi)) k ) + sigma_b^2 ;  q <- sigma_w^2 q/2 + sigma_b^2
+    Row-chunked so the elementwise temporaries stay bounded.
+    """
+    x1 = np.asarray(x1, dtype=np.float64)
+    x2 = x1 if x2 is None else np.asarray(x2, dtype=np.float64)
+    D = x1.shape[1]
+    sw2, sb2 = sigma_w**2, sigma_b**2
+    q1_all, q2 = layer0_diag(x1, sigma_w, sigma_b), layer0_diag(x2, sigma_w, sigma_b)
+    out = np.empty((x1.shape[0], x2.shape[0]), dtype=np.float64)
+    factor = 1.0 / TWO_PI
+    for r0 in range(0, x1.shape[0], chunk):
+        r1 = min(r0 + chunk, x1.shape[0])
+        k = sw2 * ((x1[r0:r1] @ x2.T) / D) + sb2
+        q1, q2l = q1_all[r0:r1].copy(), q2.copy()
+        for _ in range(depth - 1):
+            prod = q1[:, None] * q2l[None, :]
+            s = np.sqrt(np.maximum(prod - k * k, 0.0))
+            theta = np.arctan2(s, k)
+            theta[(s == 0.0) & (k == 0.0)] = np.pi / 2
+            k = sw2 * (factor * s + (0.5 - factor * theta) * k) + sb2
+            q1 = sw2 * (0.5 * q1) + sb2
+            q2l = sw2 * (0.5 * q2l) + sb2
+        out[r0:r1] = k
+    return out
+
+
+class Fit:
+    """What the first predict_fn call computes and caches in the reference (Appendix A.2)."""
+
+    def __init__(self, x, y, depth=2, sigma_w=1.0, sigma_b=0.0, diag_reg=1e-3, diag_reg_absolute=False):
+        self.x = np.asarray(x, dtype=np.float64)
+        self.y = np.asarray(y, dtype=np.float64).reshape(-1)
+        self.depth, self.sigma_w, self.sigma_b = depth, sigma_w, sigma_b
+        n = self.x.shape[0]
+        k = kernel_fn(self.x, None, depth, sigma_w, sigma_b)
+        reg = max(diag_reg, 0.0)
+        self.lam = reg if diag_reg_absolute else reg * (np.trace(k) / n)   # [nt: _add_diagonal_regularizer]
+        k[np.diag_indices(n)] += self.lam
+        self.c = sla.cholesky(k, lower=True, overwrite_a=True, check_finite=False)  # [nt: cho_factor]
+        self.alpha = sla.cho_solve((self.c, True), self.y, check_finite=False)      # [nt: cho_solve]
+
+    def predict(self, x_test, want_var=True, chunk=4096):
+        """mean = K_* alpha ; var_i = K(x_i,x_i) - ||C^-1 K_*[i,:]^T||^2 (Appendix A.3, diagonal only)."""
+        x_test = np.asarray(x_test, dtype=np.float64)
+        t = x_test.shape[0]
+        mean = np.empty(t)
+        var = np.empty(t) if want_var else None
+        for r0 in range(0, t, chunk):
+            r1 = min(r0 + chunk, t)
+            ks = kernel_fn(x_test[r0:r1], self.x, self.depth, self.sigma_w, self.sigma_b)
+            mean[r0:r1] = ks @ self.alpha
+            if want_var:
+                v = sla.solve_triangular(self.c, ks.T, lower=True, check_finite=False, overwrite_b=True)
+                kss = final_diag(layer0_diag(x_test[r0:r1], self.sigma_w, self.sigma_b), self.depth,
+                                 self.sigma_w, self.sigma_b)
+                var[r0:r1] = kss - np.einsum("ij,ij->j", v, v)
+        return mean, var
+
+    def predict_full_cov(self, x_test):
+        """The reference's literal output: (mean (T,1), cov (T,T))  [nt: gp_inference.predict_fn]."""
+        x_test = np.asarray(x_test, dtype=np.float64)
+        ks = kernel_fn(x_test, self.x, self.depth, self.sigma_w, self.sigma_b)
+        ktt = kernel_fn(x_test, None, self.depth, self.sigma_w, self.sigma_b)
+        mean = ks @ self.alpha
+        cov = ktt - ks @ sla.cho_solve((self.c, True), ks.T, check_finite=False)
+        return mean[:, None], cov
+
+
+def active_select(mean, std, budget: int):
+    """Deterministic branch of ActiveLearner.active_test (active/ActiveLearner.py:46-54, biased_sample=False)."""
+    s = np.asarray(std).reshape(-1) / np.max(mean, 0)
+    num = budget if s.shape[0] > budget else s.shape[0]
+    return np.argsort(s)[-num:]
+
+
+def q_error_stats(pred_log2, true_log2):
+    """Symmetric q-error 2**|err| summary (util.py:152-167 prints the signed ratio 2**err)."""
+    qe = 2.0 ** np.abs(np.asarray(pred_log2).reshape(-1) - np.asarray(true_log2).reshape(-1))
+    return {"median": float(np.median(qe)), "mean": float(np.mean(qe)), "p95": float(np.quantile(qe, 0.95)),
+            "max": float(np.max(qe))}

@@ -1,0 +1,51 @@
+"""CPU: the C-ABI shared library loads and exports every symbol include/nngp_b200.h declares.
+No compute call is made (there is no GPU here); nngp_create must fail loudly, not fall back."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+HEADER = ROOT / "include" / "nngp_b200.h"
+
+
+def declared_functions():
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    return sorted(set(re.findall(r"\b(nngp_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    from nngp_b200 import _lib
+    return _lib
+
+
+def test_header_and_binding_agree(lib):
+    funcs = declared_functions()
+    assert len(funcs) >= 15
+    assert sorted(lib.EXPORTS) == funcs
+
+
+def test_library_exports_every_declared_symbol(lib):
+    cdll = ctypes.CDLL(str(lib.LIB_PATH))
+    for name in declared_functions():
+        assert hasattr(cdll, name), f"{name} declared in include/nngp_b200.h but not exported"
+    assert cdll.nngp_abi_version() == 1
+
+
+def test_struct_layouts_match_header(lib):
+    # nngp_config: int32, 3 doubles, 2 int32, int64, int32 -> 56 bytes with natural alignment
+    assert ctypes.sizeof(lib.NngpConfig) == 56
+    assert ctypes.sizeof(lib.NngpStats) == 8 * 22
+
+
+def test_no_cpu_fallback_without_gpu(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu tests")
+    with pytest.raises(Exception) as ei:
+        lib.Handle()
+    assert "no CUDA device" in str(ei.value) or "error" in str(ei.value).lower()

@@ -1,0 +1,102 @@
+"""CPU: pins the numpy/scipy oracle (the parity checker) -- no GPU, no CUDA library involved.
+
+The reference ships no tests or golden vectors for this path, so the pins are:
+analytic known answers, the 50-digit mpmath restatement (tests/golden/mp_small.npz), a finite-width
+Monte-Carlo check of the /D and no-bias conventions, and the forest-workload invariants.
+"""
+import numpy as np
+import pytest
+
+import nngp_oracle as o
+
+
+def rel(a, b):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+def test_analytic_known_answers():
+    rng = np.random.default_rng(0)
+    x = rng.uniform(0, 1000, (6, 8))
+    d = x.shape[1]
+    k = o.kernel_fn(x, None, depth=2)
+    # K(x,x) = |x|^2 / (2D)
+    assert rel(np.diag(k), np.einsum("ij,ij->i", x, x) / (2 * d)) < 1e-14
+    # orthogonal rows: K = sqrt(q q') / (2 pi)
+    a = np.zeros((1, 8)); a[0, :4] = rng.uniform(1, 9, 4)
+    b = np.zeros((1, 8)); b[0, 4:] = rng.uniform(1, 9, 4)
+    qa, qb = a @ a.T / 8, b @ b.T / 8
+    assert rel(o.kernel_fn(a, b), np.sqrt(qa * qb) / (2 * np.pi)) < 1e-15
+    # x' = -x: K = 0 ; x' = c x: K = c |x|^2 / (2D)
+    assert abs(o.kernel_fn(a, -a)[0, 0]) < 1e-15 * qa[0, 0]
+    assert rel(o.kernel_fn(a, 3.5 * a), 3.5 * qa / 2) < 1e-15
+    # general closed form: sqrt(q q') (sin t + (pi - t) cos t) / (2 pi)
+    u, v = x[:1], x[1:2]
+    qu, qv = (u @ u.T / d)[0, 0], (v @ v.T / d)[0, 0]
+    t = np.arccos((u @ v.T / d)[0, 0] / np.sqrt(qu * qv))
+    assert rel(o.kernel_fn(u, v)[0, 0], np.sqrt(qu * qv) * (np.sin(t) + (np.pi - t) * np.cos(t)) / (2 * np.pi)) < 1e-12
+    # depth-L diagonal q_L = q_0 / 2^(L-1); zero rows hit the theta = pi/2 branch and give 0
+    assert rel(np.diag(o.kernel_fn(x, None, depth=4)), np.einsum("ij,ij->i", x, x) / d / 8) < 1e-14
+    z = np.zeros((2, 8))
+    assert np.all(o.kernel_fn(z, x) == 0.0) and np.all(np.isfinite(o.kernel_fn(z, z)))
+
+
+@pytest.mark.parametrize("case", ["ref_d2", "d3", "sigma_variant", "d1_linear", "abs_reg", "degenerate"])
+def test_oracle_matches_mpmath_golden(mp_golden, case):
+    g = mp_golden[case]
+    depth, sw, sb, reg, absolute = g["cfg"]
+    depth, absolute = int(depth), bool(absolute)
+    kdd = o.kernel_fn(g["x_train"], None, depth, sw, sb)
+    ktd = o.kernel_fn(g["x_test"], g["x_train"], depth, sw, sb)
+    scale = np.max(np.abs(g["K_dd"]))
+    # entries: 1e-14 relative to the kernel scale (near-duplicate rows lose relative accuracy in s, not in K)
+    assert np.max(np.abs(kdd - g["K_dd"])) < 1e-14 * scale
+    assert np.max(np.abs(ktd - g["K_td"])) < 1e-14 * scale
+    fit = o.Fit(g["x_train"], g["y_train"], depth, sw, sb, reg, absolute)
+    assert abs(fit.lam - g["lam"]) < 1e-14 * abs(g["lam"])
+    mean, var = fit.predict(g["x_test"])
+    assert np.max(np.abs(mean - g["mean"])) < 1e-9 * np.max(np.abs(g["mean"]))
+    assert np.max(np.abs(var - g["var"])) < 1e-9 * np.max(np.abs(g["var"]))
+    m2, cov = fit.predict_full_cov(g["x_test"])
+    assert m2.shape == (len(mean), 1) and cov.shape == (len(mean), len(mean))
+    assert np.max(np.abs(np.diag(cov) - g["var"])) < 1e-8 * np.max(np.abs(g["var"]))
+
+
+def test_finite_width_monte_carlo_conventions():
+    """f(x) = v . relu(W x / sqrt(D)) / sqrt(width): covariance -> K; guards /D, W_std=1, no bias."""
+    rng = np.random.default_rng(5)
+    d, width, nets = 6, 2048, 200
+    x = rng.uniform(0, 3, (4, d))
+    acc = np.zeros((4, 4))
+    for _ in range(nets):
+        w = rng.standard_normal((width, d))
+        v = rng.standard_normal(width)
+        f = (np.maximum(x @ w.T / np.sqrt(d), 0.0) * v).sum(1) / np.sqrt(width)
+        acc += np.outer(f, f)
+    emp = acc / nets
+    k = o.kernel_fn(x, None, depth=2)
+    assert np.max(np.abs(emp - k)) / np.max(k) < 0.2  # 200 draws: ~10% sampling noise
+    # a sharper check through the closed-form expectation of relu(u)relu(u') per hidden unit
+    w = rng.standard_normal((400000, d))
+    h = np.maximum(x @ w.T / np.sqrt(d), 0.0)
+    assert np.max(np.abs(h @ h.T / w.shape[0] - k)) / np.max(k) < 1e-2
+
+
+def test_forest_workload_invariants(forest):
+    xtr, ytr, xte, yte = forest["x_train"], forest["y_train"], forest["x_test"], forest["y_test"]
+    assert xtr.shape == (10800, 20) and xte.shape == (3600, 20) and xtr.dtype == np.float64
+    # lambda = 1e-3 * trace(K)/N = 1e-3 * mean(|x|^2) / (2 D): independent of the solver
+    lam = 1e-3 * np.mean(np.einsum("ij,ij->i", xtr, xtr) / 40.0)
+    assert abs(lam - 185.5609) < 1e-3     # SURVEY.md section 6 probe value
+    sub = slice(0, 1500)
+    fit = o.Fit(xtr[sub], ytr[sub])
+    mean, var = fit.predict(xte[:300])
+    assert np.all(var > 0) and np.all(np.isfinite(mean))
+    qe = o.q_error_stats(mean, yte[:300])
+    assert qe["median"] < 10.0            # the estimator is doing something sensible
+
+
+def test_active_selection_rule():
+    mean = np.array([[4.0], [8.0], [2.0], [6.0]])
+    std = np.array([0.4, 0.1, 0.9, 0.2])
+    assert list(o.active_select(mean, std, 2)) == [0, 2]
+    assert sorted(o.active_select(mean, std, 10)) == [0, 1, 2, 3]
