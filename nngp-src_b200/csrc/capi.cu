@@ -328,14 +328,14 @@ int run_trsm_rlt(nngp_handle* h, double* B, int64_t ldb, int64_t rows, const dou
   return NNGP_OK;
 }
 
-// v <- L^-T L^-1 v  (two blocked substitutions, each reads L exactly once)
-int run_cho_solve_vec(nngp_handle* h, const double* L, int64_t ld, int64_t N, double* v) {
+// v <- L^-T L^-1 v  (two blocked substitutions, each reads L exactly once); tmp: N doubles of scratch
+int run_cho_solve_vec(nngp_handle* h, const double* L, int64_t ld, int64_t N, double* v, double* tmp) {
   const int warps_per_cta = TRSV_THREADS / 32;
   for (int64_t j0 = 0; j0 < N; j0 += NB) {
     const int64_t nb = std::min<int64_t>(NB, N - j0);
     const int64_t rem = N - j0 - nb;
     int grid = (int)std::min<int64_t>(std::max<int64_t>(1, (rem + warps_per_cta - 1) / warps_per_cta), 4 * h->sm_count);
-    trsv_fwd_step_kernel<<<grid, TRSV_THREADS, 0, h->stream>>>(L, ld, (int)N, (int)j0, (int)nb, v);
+    trsv_fwd_step_kernel<<<grid, TRSV_THREADS, 0, h->stream>>>(L, ld, (int)N, (int)j0, (int)nb, v, tmp);
     h->st.kernel_launches++;
   }
   const int64_t nblk = (N + NB - 1) / NB;
@@ -343,7 +343,7 @@ int run_cho_solve_vec(nngp_handle* h, const double* L, int64_t ld, int64_t N, do
     const int64_t j0 = jb * NB;
     const int64_t nb = std::min<int64_t>(NB, N - j0);
     int grid = (int)std::min<int64_t>(std::max<int64_t>(1, (j0 + TRSV_THREADS - 1) / TRSV_THREADS), 4 * h->sm_count);
-    trsv_bwd_step_kernel<<<grid, TRSV_THREADS, 0, h->stream>>>(L, ld, (int)j0, (int)nb, v);
+    trsv_bwd_step_kernel<<<grid, TRSV_THREADS, 0, h->stream>>>(L, ld, (int)j0, (int)nb, tmp, v);
     h->st.kernel_launches++;
   }
   CK(cudaGetLastError());
@@ -391,6 +391,7 @@ int alloc_state(nngp_handle* h, int64_t N, int64_t D) {
   CKR(ensure(h, h->q, (size_t)N * sizeof(double)));
   CKR(ensure(h, h->L, (size_t)N * h->ldl * sizeof(double)));
   CKR(ensure(h, h->alpha, (size_t)h->ldl * sizeof(double)));
+  CKR(ensure(h, h->scratch_y, (size_t)h->ldl * sizeof(double)));
   return NNGP_OK;
 }
 
@@ -577,7 +578,7 @@ int nngp_fit(nngp_handle* h, const double* x_train, const double* y_train, int64
   t_chol.stop();
 
   StageTimer t_solve(h, &h->st.fit_solve_ms);
-  CKR(run_cho_solve_vec(h, L, h->ldl, N, alpha));
+  CKR(run_cho_solve_vec(h, L, h->ldl, N, alpha, h->scratch_y.as<double>()));
   t_solve.stop();
   t_total.stop();
 

@@ -175,12 +175,14 @@ __device__ __forceinline__ void load_diag_block(const double* __restrict__ Ljj, 
 }
 
 // Forward step of L z = y for diagonal block [j0, j0+n): every CTA solves the 64x64 diagonal system
-// redundantly in its warp 0 (bitwise identical), CTA 0 publishes z_J into y, and all CTAs apply
+// redundantly in its warp 0 (bitwise identical), CTA 0 publishes z_J into zout (a different buffer:
+// other CTAs may still be reading y_J), and all CTAs apply
 // y[r] -= L[r, j0:j0+n] . z_J to their rows r >= j0+n (one warp per row, coalesced 512 B reads).
 constexpr int TRSV_THREADS = 256;
 __global__ void __launch_bounds__(TRSV_THREADS) trsv_fwd_step_kernel(const double* __restrict__ L, long long ld,
                                                                     int N, int j0, int n,
-                                                                    double* __restrict__ y) {
+                                                                    double* __restrict__ y,
+                                                                    double* __restrict__ zout) {
   __shared__ double Ls[NB][NB + 1];
   __shared__ double zs[NB];
   load_diag_block(L + (long long)j0 * ld + j0, ld, n, Ls);
@@ -200,7 +202,7 @@ __global__ void __launch_bounds__(TRSV_THREADS) trsv_fwd_step_kernel(const doubl
     zs[lane + 32] = y1;
   }
   __syncthreads();
-  if (blockIdx.x == 0 && threadIdx.x < n) y[j0 + threadIdx.x] = zs[threadIdx.x];
+  if (blockIdx.x == 0 && threadIdx.x < n) zout[j0 + threadIdx.x] = zs[threadIdx.x];
   const int lane = threadIdx.x & 31;
   const int warps_per_cta = TRSV_THREADS / 32;
   const double z0 = zs[2 * lane], z1 = zs[2 * lane + 1];
@@ -220,10 +222,11 @@ __global__ void __launch_bounds__(TRSV_THREADS) trsv_fwd_step_kernel(const doubl
 }
 
 // Backward step of L^T a = z for diagonal block [j0, j0+n): every CTA solves Ljj^T a_J = z_J
-// redundantly, CTA 0 publishes a_J into z, and all CTAs apply z[c] -= sum_i L[j0+i][c] a_i to the
+// redundantly, CTA 0 publishes a_J into aout (not z: see above), and all CTAs apply z[c] -= sum_i L[j0+i][c] a_i to the
 // columns c < j0 (one thread per column, coalesced row reads).
 __global__ void __launch_bounds__(TRSV_THREADS) trsv_bwd_step_kernel(const double* __restrict__ L, long long ld,
-                                                                    int j0, int n, double* __restrict__ z) {
+                                                                    int j0, int n, double* __restrict__ z,
+                                                                    double* __restrict__ aout) {
   __shared__ double Ls[NB][NB + 1];
   __shared__ double as[NB];
   load_diag_block(L + (long long)j0 * ld + j0, ld, n, Ls);
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(TRSV_THREADS) trsv_bwd_step_kernel(const doubl
     as[lane + 32] = y1;
   }
   __syncthreads();
-  if (blockIdx.x == 0 && threadIdx.x < n) z[j0 + threadIdx.x] = as[threadIdx.x];
+  if (blockIdx.x == 0 && threadIdx.x < n) aout[j0 + threadIdx.x] = as[threadIdx.x];
   for (long long c = (long long)blockIdx.x * TRSV_THREADS + threadIdx.x; c < j0;
        c += (long long)gridDim.x * TRSV_THREADS) {
     const double* lc = L + (long long)j0 * ld + c;

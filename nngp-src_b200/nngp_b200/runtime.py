@@ -1,0 +1,40 @@
+"""Process-wide runtime knobs of the host layer: which GPU new handles bind to, input coercion."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from . import _lib
+
+_device = int(os.environ.get("NNGP_B200_DEVICE", os.environ.get("LOCAL_RANK", "-1")))
+_stats_level = int(os.environ.get("NNGP_B200_STATS", "1"))
+_max_block_bytes = int(os.environ.get("NNGP_B200_MAX_BLOCK_BYTES", "0"))
+
+
+def set_device(index: int) -> None:
+    """GPU ordinal for handles created from now on (-1 = the CUDA current device)."""
+    global _device
+    _device = int(index)
+
+
+def get_device() -> int:
+    return _device
+
+
+def new_handle(spec, diag_reg=0.0, diag_reg_absolute=False) -> "_lib.Handle":
+    return _lib.Handle(depth=spec.depth, sigma_w=spec.sigma_w, sigma_b=spec.sigma_b, diag_reg=diag_reg,
+                       diag_reg_absolute=diag_reg_absolute, device=_device, max_block_bytes=_max_block_bytes,
+                       stats_level=_stats_level)
+
+
+def as_matrix(x, name="x"):
+    """numpy float64 C-contiguous 2-D view of x, or x itself if it is a float64 torch tensor."""
+    if hasattr(x, "data_ptr") and hasattr(x, "is_contiguous"):   # torch tensor: host or device, zero-copy
+        if x.dim() != 2:
+            raise ValueError(f"{name} must be 2-D, got shape {tuple(x.shape)}")
+        return x
+    a = np.ascontiguousarray(np.asarray(x), dtype=np.float64)
+    if a.ndim != 2:
+        raise ValueError(f"{name} must be 2-D [rows, features], got shape {a.shape}")
+    return a

@@ -1,0 +1,221 @@
+"""GPU parity tests proper: the sm_100a CUDA path, called through the C ABI (ctypes), against the CPU
+oracle on identical seeded inputs, the committed golden fixtures, and size-independent properties.
+
+Tolerances (north_star): kernel entries and predicted log-cardinalities within 1e-6 relative in FP64
+(1e-3 on q-error).  The asserted bounds below are tighter where FP64 re-association allows it.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import nngp_oracle as oracle  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from nngp_b200 import _lib
+    _lib.load()
+    return _lib
+
+
+@pytest.fixture(scope="module")
+def synth():
+    from nngp_b200 import synth as s
+    return s
+
+
+def relmax(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(float(np.max(np.abs(b))), 1e-300))
+
+
+# ---------------------------------------------------------------------------------------------- kernel_fn
+@pytest.mark.parametrize("m,n,d", [(1, 1, 1), (5, 7, 3), (64, 64, 16), (129, 65, 17), (300, 200, 20), (1000, 900, 130)])
+def test_gram_only_depth1_is_exact_gemm(lib, m, n, d):
+    rng = np.random.default_rng(m * 1000 + n)
+    a, b = rng.standard_normal((m, d)), rng.standard_normal((n, d))
+    h = lib.Handle(depth=1)
+    assert relmax(h.kernel(a, b), a @ b.T / d) < 1e-13
+
+
+@pytest.mark.parametrize("depth,sw,sb", [(2, 1.0, 0.0), (3, 1.0, 0.0), (2, 1.5, 0.05), (4, 1.2, 0.1)])
+def test_kernel_entries_match_oracle(lib, synth, depth, sw, sb):
+    x1, x2 = synth.encodings(700, 40, 3), synth.encodings(450, 40, 4)
+    x1[5] = x1[4]; x1[6] = 0.0; x2[0] = x1[4]; x2[1] = 2 * x1[4]; x2[2] = 0.0   # duplicates / zero rows
+    h = lib.Handle(depth=depth, sigma_w=sw, sigma_b=sb)
+    assert relmax(h.kernel(x1, x2), oracle.kernel_fn(x1, x2, depth, sw, sb)) < 1e-12
+    k = h.kernel(x1)
+    assert relmax(k, oracle.kernel_fn(x1, None, depth, sw, sb)) < 1e-12
+    assert np.array_equal(k, k.T) or relmax(k, k.T) < 1e-15    # symmetric input -> symmetric kernel
+
+
+def test_kernel_analytic_known_answers(lib):
+    h = lib.Handle(depth=2)
+    rng = np.random.default_rng(0)
+    x = rng.uniform(0, 1000, (6, 8))
+    k = h.kernel(x)
+    assert relmax(np.diag(k), np.einsum("ij,ij->i", x, x) / 16) < 1e-14          # K(x,x) = |x|^2/(2D)
+    a = np.zeros((1, 8)); a[0, :4] = [1, 2, 3, 4]
+    b = np.zeros((1, 8)); b[0, 4:] = [4, 3, 2, 1]
+    assert relmax(h.kernel(a, b), np.sqrt((a @ a.T / 8) * (b @ b.T / 8)) / (2 * np.pi)) < 1e-15  # orthogonal
+    assert abs(h.kernel(a, -a)[0, 0]) < 1e-15                                    # antiparallel -> 0
+    assert relmax(h.kernel(a, 3.5 * a), 3.5 * (a @ a.T / 8) / 2) < 1e-15         # parallel
+    z = np.zeros((2, 8))
+    assert np.all(h.kernel(z, x) == 0.0)                                         # theta = pi/2 branch
+
+
+@pytest.mark.parametrize("case", ["ref_d2", "d3", "sigma_variant", "d1_linear", "abs_reg", "degenerate"])
+def test_against_mpmath_golden(lib, mp_golden, case):
+    g = mp_golden[case]
+    depth, sw, sb, reg, absolute = g["cfg"]
+    h = lib.Handle(depth=int(depth), sigma_w=sw, sigma_b=sb, diag_reg=reg, diag_reg_absolute=bool(absolute))
+    scale = np.max(np.abs(g["K_dd"]))
+    assert np.max(np.abs(h.kernel(g["x_train"]) - g["K_dd"])) < 1e-13 * scale
+    assert np.max(np.abs(h.kernel(g["x_test"], g["x_train"]) - g["K_td"])) < 1e-13 * scale
+    h.fit(g["x_train"], g["y_train"])
+    assert abs(h.dims()[2] - g["lam"]) < 1e-13 * abs(g["lam"])
+    mean, var = h.predict(g["x_test"])
+    assert np.max(np.abs(mean - g["mean"])) < 1e-8 * np.max(np.abs(g["mean"]))
+    assert np.max(np.abs(var - g["var"])) < 1e-8 * np.max(np.abs(g["var"]))
+    assert relmax(h.get_state()["alpha"], g["alpha"]) < 1e-7
+
+
+# ---------------------------------------------------------------------------------------------- Cholesky
+@pytest.mark.parametrize("n", [1, 8, 64, 65, 128, 200, 257, 513, 1000])
+def test_blocked_cholesky_matches_lapack(lib, n):
+    import scipy.linalg as sla
+    rng = np.random.default_rng(n)
+    a = rng.standard_normal((n, n + 8))
+    spd = a @ a.T + n * np.eye(n)
+    l = lib.Handle().potrf(spd)
+    assert relmax(l, sla.cholesky(spd, lower=True)) < 1e-12
+    assert relmax(l @ l.T, spd) < 1e-13
+
+
+def test_not_positive_definite_is_reported(lib):
+    h = lib.Handle()
+    with pytest.raises(np.linalg.LinAlgError):
+        h.potrf(-np.eye(70))
+    x = np.ones((40, 6))
+    hh = lib.Handle(diag_reg=0.0)        # rank-1 kernel, no regulariser -> singular
+    with pytest.raises(np.linalg.LinAlgError):
+        hh.fit(x, np.ones(40))
+
+
+# ---------------------------------------------------------------------------------------------- fit + predict
+@pytest.mark.parametrize("n,t,d,depth", [(40, 12, 20, 2), (700, 300, 24, 2), (1500, 1000, 64, 3), (2500, 700, 128, 2),
+                                         (130, 1, 7, 2)])
+def test_fit_predict_match_oracle(lib, synth, n, t, d, depth):
+    d2 = d + (d % 2)
+    xtr, ytr, xte, _ = synth.make_problem(n, t, d2)
+    xtr, xte = xtr[:, :d], xte[:, :d]                      # odd D exercises the padded operand path
+    h = lib.Handle(depth=depth)
+    h.fit(xtr, ytr)
+    ref = oracle.Fit(xtr, ytr, depth)
+    st = h.get_state()
+    assert abs(st["lambda"] - ref.lam) < 1e-13 * ref.lam
+    assert relmax(st["l"], ref.c) < 1e-9
+    assert np.all(np.triu(st["l"], 1) == 0.0)
+    mean, var = h.predict(xte)
+    rm, rv = ref.predict(xte)
+    assert relmax(mean, rm) < 1e-6 and relmax(var, rv) < 1e-6
+    assert np.max(np.abs(2.0 ** np.abs(mean - rm) - 1.0)) < 1e-3          # q-error gate
+    m_only, none = h.predict(xte, want_var=False)
+    assert none is None and np.array_equal(m_only, mean)                   # compute_cov=False path
+
+
+def test_forest_workload_parity(lib, forest):
+    """Config C1: the reference's shipped forest queries, N=10800 / T=3600 / D=20 / depth 2."""
+    h = lib.Handle()
+    h.fit(forest["x_train"], forest["y_train"])
+    ref = oracle.Fit(forest["x_train"], forest["y_train"])
+    assert abs(h.dims()[2] - ref.lam) < 1e-12 * ref.lam
+    mean, var = h.predict(forest["x_test"])
+    rm, rv = ref.predict(forest["x_test"])
+    assert relmax(mean, rm) < 1e-6
+    assert np.max(np.abs(var - rv) / np.abs(rv)) < 1e-6
+    assert np.max(np.abs(2.0 ** np.abs(mean - rm) - 1.0)) < 1e-3
+    q, rq = oracle.q_error_stats(mean, forest["y_test"]), oracle.q_error_stats(rm, forest["y_test"])
+    assert abs(q["median"] - rq["median"]) < 1e-3 * rq["median"]
+
+
+def test_row_blocking_and_sharding_are_bitwise_invariant(lib, synth):
+    """k-GPU == 1-GPU: a test row's result must not depend on which block / shard it is in."""
+    xtr, ytr, xte, _ = synth.make_problem(900, 1000, 32)
+    h = lib.Handle()
+    h.fit(xtr, ytr)
+    mean, var = h.predict(xte)
+    small = lib.Handle(max_block_bytes=256 * 912 * 8)       # forces 256-row blocks
+    st = h.get_state()
+    small.set_state(st["x"], st["l"], st["alpha"], st["lambda"])
+    m2, v2 = small.predict(xte)
+    assert np.array_equal(mean, m2) and np.array_equal(var, v2)
+    parts = [small.predict(xte[a:b]) for a, b in ((0, 123), (123, 700), (700, 1000))]
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), mean)
+    assert np.array_equal(np.concatenate([p[1] for p in parts]), var)
+
+
+def test_full_size_properties_c2(lib, synth):
+    """BASELINE config C2 sizes (N=8192, D=128, depth 2): size-independent properties + sampled oracle check."""
+    xtr, ytr, xte, _ = synth.make_problem(8192, 8192, 128)
+    h = lib.Handle()
+    h.fit(xtr, ytr)
+    n, d, lam = h.dims()
+    assert (n, d) == (8192, 128)
+    assert abs(lam - 1e-3 * np.mean(np.einsum("ij,ij->i", xtr, xtr)) / 256) < 1e-12 * lam   # lambda from the diagonal
+    # (a) predicting the training rows: K_* = K_dd  =>  mean = y - lambda*alpha, var = lambda - lambda^2 [A^-1]_ii
+    alpha = h.get_state(x=False, l=False)["alpha"]
+    mean_tr, var_tr = h.predict(xtr)
+    assert np.max(np.abs(mean_tr - (ytr - lam * alpha))) < 1e-6 * np.max(np.abs(ytr))
+    assert np.all(var_tr > 0) and np.all(var_tr < lam * (1 + 1e-9))
+    # (b) linearity of the posterior mean in y
+    h2 = lib.Handle()
+    h2.fit(xtr, 3.0 * ytr + 1.0)
+    h3 = lib.Handle()
+    h3.fit(xtr, np.ones_like(ytr))
+    m1, v1 = h.predict(xte[:2048])
+    m2, v2 = h2.predict(xte[:2048])
+    m3, _ = h3.predict(xte[:2048])
+    assert np.max(np.abs(m2 - (3.0 * m1 + m3))) < 1e-6 * np.max(np.abs(m2))
+    assert np.array_equal(v1, v2)                                            # variance does not depend on y
+    # (c) sampled oracle parity at full N
+    ref = oracle.Fit(xtr, ytr)
+    rm, rv = ref.predict(xte[:512])
+    assert relmax(m1[:512], rm) < 1e-6 and np.max(np.abs(v1[:512] - rv) / np.abs(rv)) < 1e-6
+
+
+def test_state_roundtrip_and_device_pointers(lib, synth):
+    import torch
+    xtr, ytr, xte, _ = synth.make_problem(600, 300, 16)
+    h = lib.Handle()
+    h.fit(xtr, ytr)
+    mean, var = h.predict(xte)
+    st = h.get_state()
+    h2 = lib.Handle()
+    h2.set_state(st["x"], st["l"], st["alpha"], st["lambda"])
+    m2, v2 = h2.predict(xte)
+    assert np.array_equal(mean, m2) and np.array_equal(var, v2)
+    # device-resident inputs/outputs (what the sharded predictor and bench.py use)
+    xd = torch.from_numpy(xte).cuda()
+    md, vd = torch.empty(300, dtype=torch.float64, device="cuda"), torch.empty(300, dtype=torch.float64, device="cuda")
+    h.predict(xd, mean_out=md, var_out=vd)
+    assert np.array_equal(md.cpu().numpy(), mean) and np.array_equal(vd.cpu().numpy(), var)
+
+
+def test_error_conventions(lib, synth):
+    h = lib.Handle()
+    xtr, ytr, xte, _ = synth.make_problem(64, 8, 8)
+    with pytest.raises(lib.NngpError):
+        h.predict(xte)                                   # not fitted
+    bad = xtr.copy(); bad[3, 2] = np.nan
+    with pytest.raises(ValueError):
+        h.fit(bad, ytr)                                  # non-finite input
+    with pytest.raises(ValueError):
+        h.fit(xtr, ytr[:-1])                             # shape mismatch
+    with pytest.raises(ValueError):
+        lib.Handle(depth=0)
+    h.fit(xtr, ytr)
+    with pytest.raises(ValueError):
+        h.predict(np.full((4, 8), np.inf))
+    mean, var = h.predict(xte)                           # handle still usable after errors
+    assert np.all(np.isfinite(mean))

@@ -204,6 +204,6 @@ if __name__ == "__main__":
     for fn in (s_env, s_gemm, s_kernel, s_potrf, s_fit, s_forest, s_peak, s_perf):
         fn()
     os.makedirs(ROOT / "gpurun_out", exist_ok=True)
-    with open(ROOT / "gpurun_out" / "diag.json", "w") as fh:
+    with open(ROOT / "gpurun_out" / ("diag_" + "_".join(STAGES) + ".json"), "w") as fh:
         json.dump(OUT, fh, indent=1, default=float)
     print("DIAG COMPLETE")
