@@ -73,74 +73,113 @@ __global__ void diag_reg_kernel(double* __restrict__ K, long long ld, int N, dou
   for (int i = threadIdx.x; i < N; i += blockDim.x) K[(long long)i * ld + i] += lam;
 }
 
-// In-place lower Cholesky of the n x n (n <= 64) block at A (row-major, ld).  One CTA, 256 threads.
+// In-place lower Cholesky of the n x n (n <= 64) block at A (row-major, ld).  One CTA, 256 threads as a
+// 16 x 16 grid, each thread owning a 4 x 4 register sub-block (right-looking, two barriers per column;
+// the pivot column is scaled by the reciprocal pivot as LAPACK dpotf2 does).
 // On a non-positive pivot: *info = global pivot index + 1 (first failure wins), block left as is.
 __global__ void __launch_bounds__(256) potf2_64_kernel(double* __restrict__ A, long long ld, int n, int pivot0,
                                                        int* __restrict__ info) {
-  __shared__ double As[NB][NB + 1];
-  __shared__ int bad;
+  __shared__ double colj[NB];
+  __shared__ double diag_s;
   const int tid = threadIdx.x;
-  if (tid == 0) bad = 0;
-  for (int idx = tid; idx < NB * NB; idx += 256) {
-    const int r = idx >> 6, c = idx & 63;
-    double v = (r == c) ? 1.0 : 0.0;
-    if (r < n && c <= r) v = A[(long long)r * ld + c];
-    As[r][c] = v;
-  }
-  __syncthreads();
-  for (int j = 0; j < n; ++j) {
-    const double d = As[j][j];
-    if (!(d > 0.0)) {  // also catches NaN
-      if (tid == 0) { bad = 1; atomicCAS(info, 0, pivot0 + j + 1); }
-      break;           // d is uniform across the CTA => uniform exit
+  const int tx = tid & 15, ty = tid >> 4;
+  double v[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int r = ty * 4 + a, c = tx * 4 + b;
+      v[a][b] = (r < n && c <= r) ? A[(long long)r * ld + c] : ((r == c) ? 1.0 : 0.0);
     }
-    const double piv = sqrt(d);
-    __syncthreads();  // everyone has read As[j][j]
-    if (tid == 0) As[j][j] = piv;
-    for (int i = j + 1 + tid; i < n; i += 256) As[i][j] = As[i][j] / piv;
+  bool bad = false;
+  for (int j = 0; j < n; ++j) {
+    const int jb = j >> 2, ja = j & 3;
+    if (ty == jb && tx == jb) {
+      double d = 0.0;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) if (a == ja) d = v[a][a];
+      diag_s = d;
+    }
     __syncthreads();
-    const int m = n - j - 1;
-    for (int idx = tid; idx < m * m; idx += 256) {
-      const int ii = idx / m, kk = idx - ii * m;
-      if (kk <= ii) {
-        const int i = j + 1 + ii, k = j + 1 + kk;
-        As[i][k] = fma(-As[i][j], As[k][j], As[i][k]);
+    const double d = diag_s;
+    if (!(d > 0.0)) {  // also catches NaN; d is CTA-uniform => uniform exit
+      if (tid == 0) atomicCAS(info, 0, pivot0 + j + 1);
+      bad = true;
+      break;
+    }
+    if (tx == jb) {  // owners of column j: scale and publish
+      const double piv = sqrt(d);
+      const double rinv = 1.0 / piv;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int r = ty * 4 + a;
+        double cur = 0.0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) if (b == ja) cur = v[a][b];
+        const double l = (r > j) ? cur * rinv : ((r == j) ? piv : cur);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) if (b == ja) v[a][b] = l;
+        colj[r] = (r > j) ? l : 0.0;
       }
     }
     __syncthreads();
+    double lr[4], lc[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) lr[a] = colj[ty * 4 + a];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) lc[b] = (tx * 4 + b > j) ? colj[tx * 4 + b] : 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) v[a][b] = fma(-lr[a], lc[b], v[a][b]);
   }
-  __syncthreads();
   if (bad) return;
-  for (int idx = tid; idx < NB * NB; idx += 256) {
-    const int r = idx >> 6, c = idx & 63;
-    if (r < n && c <= r) A[(long long)r * ld + c] = As[r][c];
-  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int r = ty * 4 + a, c = tx * 4 + b;
+      if (r < n && c <= r) A[(long long)r * ld + c] = v[a][b];
+    }
 }
 
 // X * Ljj^T = B in place, for `rows` rows of B (row-major, ldb) and the n x n (n <= 64) lower block
-// Ljj (row-major, ldl).  128 rows per CTA, one thread per row, forward substitution along the row.
+// Ljj (row-major, ldl).  128 rows per CTA, one thread per row, forward substitution along the row
+// (reciprocal diagonal, as optimised BLAS dtrsm does).  Global loads are batched 8 deep per thread.
 constexpr int TRSM_ROWS = 128;
-constexpr int TRSM_SMEM_BYTES = (TRSM_ROWS * (NB + 1) + NB * (NB + 1)) * 8;
+constexpr int TRSM_SMEM_BYTES = (TRSM_ROWS * (NB + 1) + NB * (NB + 1) + NB) * 8;
 __global__ void __launch_bounds__(TRSM_ROWS) trsm_rows_64_kernel(double* __restrict__ B, long long ldb, int rows,
                                                                 const double* __restrict__ Ljj, long long ldl,
                                                                 int n) {
   extern __shared__ double sm[];
   double(*Bs)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm);
   double(*Ls)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm + TRSM_ROWS * (NB + 1));
+  double* rdiag = sm + TRSM_ROWS * (NB + 1) + NB * (NB + 1);
   const int tid = threadIdx.x;
   const int row0 = blockIdx.x * TRSM_ROWS;
-  for (int idx = tid; idx < NB * NB; idx += TRSM_ROWS) {
-    const int r = idx >> 6, c = idx & 63;
-    double v = (r == c) ? 1.0 : 0.0;
-    if (r < n && c <= r) v = Ljj[(long long)r * ldl + c];
-    Ls[r][c] = v;
+  const int c = tid & 63, rsub = tid >> 6;  // thread covers column c of rows rsub, rsub+2, ...
+  for (int r0 = 0; r0 < NB; r0 += 16) {
+    double t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int r = r0 + 2 * u + rsub;
+      t[u] = (r < n && c <= r) ? Ljj[(long long)r * ldl + c] : ((r == c) ? 1.0 : 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) Ls[r0 + 2 * u + rsub][c] = t[u];
   }
-  for (int idx = tid; idx < TRSM_ROWS * NB; idx += TRSM_ROWS) {
-    const int r = idx >> 6, c = idx & 63;
-    double v = 0.0;
-    if (row0 + r < rows && c < n) v = B[(long long)(row0 + r) * ldb + c];
-    Bs[r][c] = v;
+  for (int r0 = 0; r0 < TRSM_ROWS; r0 += 16) {
+    double t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int r = r0 + 2 * u + rsub;
+      t[u] = (row0 + r < rows && c < n) ? B[(long long)(row0 + r) * ldb + c] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) Bs[r0 + 2 * u + rsub][c] = t[u];
   }
+  __syncthreads();
+  if (tid < NB) rdiag[tid] = 1.0 / Ls[tid][tid];
   __syncthreads();
   double* xr = Bs[tid];
   for (int j = 0; j < n; ++j) {
@@ -154,24 +193,32 @@ __global__ void __launch_bounds__(TRSM_ROWS) trsm_rows_64_kernel(double* __restr
       s3 = fma(-xr[k + 3], lj[k + 3], s3);
     }
     for (; k < j; ++k) s0 = fma(-xr[k], lj[k], s0);
-    xr[j] = ((s0 + s1) + (s2 + s3)) / lj[j];
+    xr[j] = ((s0 + s1) + (s2 + s3)) * rdiag[j];
   }
   __syncthreads();
-  for (int idx = tid; idx < TRSM_ROWS * NB; idx += TRSM_ROWS) {
-    const int r = idx >> 6, c = idx & 63;
+  for (int r0 = 0; r0 < TRSM_ROWS; r0 += 2) {
+    const int r = r0 + rsub;
     if (row0 + r < rows && c < n) B[(long long)(row0 + r) * ldb + c] = Bs[r][c];
   }
 }
 
-// Shared helper: load the n x n lower block Ljj into Ls (identity padded) and the n rhs entries.
+// Shared helper: load the n x n lower block Ljj into Ls (identity padded), 8 loads in flight per thread,
+// and the reciprocal diagonal into rd.  blockDim.x must be 256.
 __device__ __forceinline__ void load_diag_block(const double* __restrict__ Ljj, long long ldl, int n,
-                                                double (*Ls)[NB + 1]) {
-  for (int idx = threadIdx.x; idx < NB * NB; idx += blockDim.x) {
-    const int r = idx >> 6, c = idx & 63;
-    double v = (r == c) ? 1.0 : 0.0;
-    if (r < n && c <= r) v = Ljj[(long long)r * ldl + c];
-    Ls[r][c] = v;
+                                                double (*Ls)[NB + 1], double* rd) {
+  const int c = threadIdx.x & 63, rsub = threadIdx.x >> 6;  // 4 row phases
+  for (int r0 = 0; r0 < NB; r0 += 32) {
+    double t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int r = r0 + 4 * u + rsub;
+      t[u] = (r < n && c <= r) ? Ljj[(long long)r * ldl + c] : ((r == c) ? 1.0 : 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) Ls[r0 + 4 * u + rsub][c] = t[u];
   }
+  __syncthreads();
+  if (threadIdx.x < NB) rd[threadIdx.x] = 1.0 / Ls[threadIdx.x][threadIdx.x];
 }
 
 // Forward step of L z = y for diagonal block [j0, j0+n): every CTA solves the 64x64 diagonal system
@@ -185,7 +232,8 @@ __global__ void __launch_bounds__(TRSV_THREADS) trsv_fwd_step_kernel(const doubl
                                                                     double* __restrict__ zout) {
   __shared__ double Ls[NB][NB + 1];
   __shared__ double zs[NB];
-  load_diag_block(L + (long long)j0 * ld + j0, ld, n, Ls);
+  __shared__ double rd[NB];
+  load_diag_block(L + (long long)j0 * ld + j0, ld, n, Ls, rd);
   if (threadIdx.x < NB) zs[threadIdx.x] = (threadIdx.x < n) ? y[j0 + threadIdx.x] : 0.0;
   __syncthreads();
   if (threadIdx.x < 32) {
@@ -193,7 +241,7 @@ __global__ void __launch_bounds__(TRSV_THREADS) trsv_fwd_step_kernel(const doubl
     double y0 = zs[lane], y1 = zs[lane + 32];  // lane owns entries lane, lane+32
     for (int k = 0; k < NB; ++k) {
       const double num = __shfl_sync(0xffffffffu, (k < 32) ? y0 : y1, k & 31);
-      const double zk = num / Ls[k][k];
+      const double zk = num * rd[k];
       if (lane == (k & 31)) { if (k < 32) y0 = zk; else y1 = zk; }
       if (lane > k) y0 = fma(-Ls[lane][k], zk, y0);
       if (lane + 32 > k) y1 = fma(-Ls[lane + 32][k], zk, y1);
@@ -229,7 +277,8 @@ __global__ void __launch_bounds__(TRSV_THREADS) trsv_bwd_step_kernel(const doubl
                                                                     double* __restrict__ aout) {
   __shared__ double Ls[NB][NB + 1];
   __shared__ double as[NB];
-  load_diag_block(L + (long long)j0 * ld + j0, ld, n, Ls);
+  __shared__ double rd[NB];
+  load_diag_block(L + (long long)j0 * ld + j0, ld, n, Ls, rd);
   if (threadIdx.x < NB) as[threadIdx.x] = (threadIdx.x < n) ? z[j0 + threadIdx.x] : 0.0;
   __syncthreads();
   if (threadIdx.x < 32) {
@@ -237,7 +286,7 @@ __global__ void __launch_bounds__(TRSV_THREADS) trsv_bwd_step_kernel(const doubl
     double y0 = as[lane], y1 = as[lane + 32];
     for (int k = NB - 1; k >= 0; --k) {
       const double num = __shfl_sync(0xffffffffu, (k < 32) ? y0 : y1, k & 31);
-      const double ak = num / Ls[k][k];
+      const double ak = num * rd[k];
       if (lane == (k & 31)) { if (k < 32) y0 = ak; else y1 = ak; }
       if (lane < k) y0 = fma(-Ls[k][lane], ak, y0);
       if (lane + 32 < k) y1 = fma(-Ls[k][lane + 32], ak, y1);
@@ -251,14 +300,18 @@ __global__ void __launch_bounds__(TRSV_THREADS) trsv_bwd_step_kernel(const doubl
        c += (long long)gridDim.x * TRSV_THREADS) {
     const double* lc = L + (long long)j0 * ld + c;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int i = 0;
-    for (; i + 3 < n; i += 4) {
-      s0 = fma(lc[(long long)i * ld], as[i], s0);
-      s1 = fma(lc[(long long)(i + 1) * ld], as[i + 1], s1);
-      s2 = fma(lc[(long long)(i + 2) * ld], as[i + 2], s2);
-      s3 = fma(lc[(long long)(i + 3) * ld], as[i + 3], s3);
+    for (int i0 = 0; i0 < NB; i0 += 16) {
+      double t[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) t[u] = (i0 + u < n) ? lc[(long long)(i0 + u) * ld] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 16; u += 4) {
+        s0 = fma(t[u], as[i0 + u], s0);
+        s1 = fma(t[u + 1], as[i0 + u + 1], s1);
+        s2 = fma(t[u + 2], as[i0 + u + 2], s2);
+        s3 = fma(t[u + 3], as[i0 + u + 3], s3);
+      }
     }
-    for (; i < n; ++i) s0 = fma(lc[(long long)i * ld], as[i], s0);
     z[c] -= (s0 + s1) + (s2 + s3);
   }
 }

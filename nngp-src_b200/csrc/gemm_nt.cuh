@@ -69,7 +69,7 @@ __device__ __forceinline__ double arccos_step(double k, double q1, double q2, do
 }
 
 template <int EPI>
-__global__ void __maxnreg__(112)
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmParams p) {
   const int tile_n = blockIdx.x;

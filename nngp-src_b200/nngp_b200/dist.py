@@ -1,0 +1,98 @@
+"""Row-sharded prediction over 1/2/4/8 GPUs, one process per GPU.
+
+The reference has no multi-device path at all (``nt.batch(device_count=0)``, train.py:166-168); the only
+stage that shards is prediction: test rows are independent given the fitted state {X, L, alpha, lambda}.
+So the fit runs on ONE rank, its state is broadcast once (``torch.distributed`` -- NCCL over NVLink 5 /
+NVSwitch on GPUs, gloo in the CPU tests), and every rank predicts a contiguous row range with no further
+inter-GPU traffic; an all-gather of (mean, var) -- 16 bytes per query -- is optional.  There is no data-path
+collective to fuse with a kernel here: the broadcast happens once per fit.
+
+``engine`` is anything with the ``_lib.Handle`` interface (dims / get_state / set_state / predict); the CPU
+tests inject an oracle-backed fake so the plumbing is covered without a GPU.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_bounds(total: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous row range [lo, hi) of ``rank``: [r*T/G, (r+1)*T/G)."""
+    return rank * total // world, (rank + 1) * total // world
+
+
+def _dist():
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized():
+        raise RuntimeError("nngp_b200.dist: torch.distributed is not initialised")
+    return dist
+
+
+def _comm_device(group=None):
+    import torch
+    dist = _dist()
+    backend = dist.get_backend(group)
+    if "nccl" in str(backend):
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def broadcast_fit(engine, src: int = 0, group=None):
+    """Rank ``src`` holds a fitted engine; on return every rank's engine holds the same state.
+
+    Traffic: 8*(N*N + N*D + N) bytes per receiving rank, once per fit.  Returns (N, D, lambda)."""
+    import torch
+    dist = _dist()
+    rank = dist.get_rank(group)
+    dev = _comm_device(group)
+    hdr = torch.zeros(3, dtype=torch.float64, device=dev)
+    if rank == src:
+        n, d, lam = engine.dims()
+        hdr[0], hdr[1], hdr[2] = n, d, lam
+    dist.broadcast(hdr, src=src, group=group)
+    n, d, lam = int(hdr[0].item()), int(hdr[1].item()), float(hdr[2].item())
+    x = torch.empty((n, d), dtype=torch.float64, device=dev)
+    l = torch.empty((n, n), dtype=torch.float64, device=dev)
+    alpha = torch.empty(n, dtype=torch.float64, device=dev)
+    if rank == src:
+        engine.get_state(out={"x": x, "l": l, "alpha": alpha})
+    for t in (x, l, alpha):
+        dist.broadcast(t, src=src, group=group)
+    if rank != src:
+        engine.set_state(x, l, alpha, lam)
+    if dev.type == "cuda":
+        torch.cuda.synchronize(dev)
+    del x, l, alpha
+    return n, d, lam
+
+
+def sharded_predict(engine, x_test, want_var: bool = True, gather: bool = True, group=None):
+    """Every rank passes the SAME x_test [T, D]; rank r predicts rows shard_bounds(T, G, r).
+
+    gather=True: all ranks return full-length (mean[T], var[T]) (var None when want_var is False);
+    gather=False: each rank returns only its own rows.  A row's result is bitwise independent of G
+    (fixed-order reductions; tests/test_gpu_parity.py::test_row_blocking_and_sharding_are_bitwise_invariant)."""
+    import torch
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    total = x_test.shape[0]
+    lo, hi = shard_bounds(total, world, rank)
+    if hi > lo:
+        mean, var = engine.predict(x_test[lo:hi], want_var=want_var)
+    else:
+        mean, var = np.empty(0), (np.empty(0) if want_var else None)
+    if not gather:
+        return mean, var
+    dev = _comm_device(group)
+    width = max(shard_bounds(total, world, r)[1] - shard_bounds(total, world, r)[0] for r in range(world))
+    cols = 2 if want_var else 1
+    mine = torch.zeros((width, cols), dtype=torch.float64, device=dev)
+    mine[: hi - lo, 0] = torch.as_tensor(np.asarray(mean), dtype=torch.float64).to(dev)
+    if want_var:
+        mine[: hi - lo, 1] = torch.as_tensor(np.asarray(var), dtype=torch.float64).to(dev)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    full = np.empty((total, cols))
+    for r, p in enumerate(parts):
+        a, b = shard_bounds(total, world, r)
+        full[a:b] = p[: b - a].cpu().numpy()
+    return full[:, 0].copy(), (full[:, 1].copy() if want_var else None)

@@ -18,6 +18,12 @@ def set_device(index: int) -> None:
     _device = int(index)
 
 
+def set_stats_level(level: int) -> None:
+    """0 none, 1 per-stage CUDA events (default), 2 per-kernel-class events (bench roofline accounting)."""
+    global _stats_level
+    _stats_level = int(level)
+
+
 def get_device() -> int:
     return _device
 
