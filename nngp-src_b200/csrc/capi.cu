@@ -19,6 +19,7 @@
 #include "../../include/nngp_b200.h"
 #include "dense_kernels.cuh"
 #include "gemm_nt.cuh"
+#include "trsm_fused.cuh"
 
 using namespace nngp;
 
@@ -64,7 +65,7 @@ struct nngp_handle {
   DevBuf lam_d;   // double[1]
 
   // predict workspace
-  DevBuf xt, qt, kss, blk, mean_d, var_d;
+  DevBuf xt, qt, kss, blk, mean_d, var_d, ssq, sync_ints;
   // nngp_kernel workspace
   DevBuf ka, kb, kqa, kqb, kout;
 
@@ -328,6 +329,40 @@ int run_trsm_rlt(nngp_handle* h, double* B, int64_t ldb, int64_t rows, const dou
   return NNGP_OK;
 }
 
+// Same solve as run_trsm_rlt plus the variance, as ONE persistent kernel (trsm_fused.cuh).
+int run_trsm_fused(nngp_handle* h, double* B, int64_t ldb, int64_t rows, const double* L, int64_t ldl, int64_t N,
+                   const double* kss, double* var) {
+  TrsmFusedParams p{};
+  p.B = B; p.ldb = ldb; p.rows = (int)rows; p.L = L; p.ldl = ldl; p.N = (int)N;
+  p.row_tiles = (int)((rows + GEMM_BM - 1) / GEMM_BM);
+  p.col_blocks = (int)((N + NB - 1) / NB);
+  CKR(ensure(h, h->sync_ints, (size_t)(p.row_tiles + 1) * sizeof(int)));
+  CKR(ensure(h, h->ssq, (size_t)rows * sizeof(double)));
+  CK(cudaMemsetAsync(h->sync_ints.p, 0, (size_t)(p.row_tiles + 1) * sizeof(int), h->stream));
+  p.counter = h->sync_ints.as<int>();
+  p.progress = h->sync_ints.as<int>() + 1;
+  p.ssq = h->ssq.as<double>(); p.kss = kss; p.var = var;
+  CUtensorMap tmB, tmL;
+  CKR(get_tmap(h, B, rows, N, ldb, GEMM_BM, &tmB));
+  CKR(get_tmap(h, L, N, N, ldl, GEMM_BN, &tmL));
+  const long long total = (long long)p.row_tiles * p.col_blocks;
+  const int grid = (int)std::min<long long>(total, 2LL * h->sm_count);
+  cudaEvent_t ev;
+  class_begin(h, EV_GEMM, &ev);
+  trsm_fused_kernel<<<grid, GEMM_THREADS, TF_SMEM_BYTES, h->stream>>>(tmB, tmL, p);
+  class_end(h, EV_GEMM, ev);
+  CK(cudaGetLastError());
+  h->st.kernel_launches++;
+  h->st.gemm_launches++;
+  h->st.gemm_flops += (double)rows * (double)N * (double)N;  // N^2 flop per test row
+  return NNGP_OK;
+}
+
+bool use_fused_trsm() {
+  static int v = [] { const char* e = getenv("NNGP_PREDICT_TRSM"); return (e && !strcmp(e, "steps")) ? 0 : 1; }();
+  return v != 0;
+}
+
 // v <- L^-T L^-1 v  (two blocked substitutions, each reads L exactly once); tmp: N doubles of scratch
 int run_cho_solve_vec(nngp_handle* h, const double* L, int64_t ld, int64_t N, double* v, double* tmp) {
   const int warps_per_cta = TRSV_THREADS / 32;
@@ -462,6 +497,7 @@ int nngp_create(const nngp_config* cfg, nngp_handle** out) {
   cudaError_t e1 = cudaFuncSetAttribute(gemm_nt_kernel<EPI_GRAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
   cudaError_t e2 = cudaFuncSetAttribute(gemm_nt_kernel<EPI_SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
   cudaError_t e3 = cudaFuncSetAttribute(trsm_rows_64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM_BYTES);
+  if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(trsm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM_BYTES);
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
     fail(h, NNGP_ECUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s",
          cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
@@ -480,7 +516,7 @@ void nngp_destroy(nngp_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->X, &h->q, &h->L, &h->alpha, &h->scratch_y, &h->flags, &h->lam_d, &h->xt, &h->qt, &h->kss,
-                    &h->blk, &h->mean_d, &h->var_d, &h->ka, &h->kb, &h->kqa, &h->kqb, &h->kout})
+                    &h->blk, &h->mean_d, &h->var_d, &h->ssq, &h->sync_ints, &h->ka, &h->kb, &h->kqa, &h->kqb, &h->kout})
     release(*b);
   for (auto& r : h->pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : h->ev_pool) cudaEventDestroy(e);
@@ -645,14 +681,21 @@ int nngp_predict(nngp_handle* h, const double* x_test, int64_t T, double* mean_o
     timers.back().stop();
 
     if (var_out) {
-      timers.emplace_back(h, &h->st.pred_trsm_ms);
-      CKR(run_trsm_rlt(h, blk, ldl, rows, h->L.as<double>(), ldl, N));
-      timers.back().stop();
-      timers.emplace_back(h, &h->st.pred_var_ms);
       q_final_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, h->stream>>>(h->qt.as<double>(), (int)rows, h->cfg.depth - 1, sw2, sb2, h->kss.as<double>());
-      var_rows_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, h->stream>>>(blk, ldl, (int)rows, (int)N, h->kss.as<double>(), h->var_d.as<double>() + t0);
-      h->st.kernel_launches += 2;
-      timers.back().stop();
+      h->st.kernel_launches++;
+      if (use_fused_trsm()) {
+        timers.emplace_back(h, &h->st.pred_trsm_ms);   // solve + variance in one persistent kernel
+        CKR(run_trsm_fused(h, blk, ldl, rows, h->L.as<double>(), ldl, N, h->kss.as<double>(), h->var_d.as<double>() + t0));
+        timers.back().stop();
+      } else {
+        timers.emplace_back(h, &h->st.pred_trsm_ms);
+        CKR(run_trsm_rlt(h, blk, ldl, rows, h->L.as<double>(), ldl, N));
+        timers.back().stop();
+        timers.emplace_back(h, &h->st.pred_var_ms);
+        var_rows_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, h->stream>>>(blk, ldl, (int)rows, (int)N, h->kss.as<double>(), h->var_d.as<double>() + t0);
+        h->st.kernel_launches++;
+        timers.back().stop();
+      }
     }
   }
   timers.emplace_back(h, &h->st.d2h_ms);

@@ -68,6 +68,57 @@ __device__ __forceinline__ double arccos_step(double k, double q1, double q2, do
   return sw2 * r + sb2;
 }
 
+
+// Consumer side of the operand ring: wait for a stage, run its 4 x (4 x 4) DMMAs on this warp's
+// 32 x 32 tile, release the stage.  `stage` / `phase` persist across calls (persistent kernels).
+template <int STAGES>
+__device__ __forceinline__ void mma_mainloop(double (&acc)[4][4][2], uint32_t ringA_u32, uint32_t ringB_u32,
+                                             uint64_t* full_bar, uint64_t* empty_bar, int& stage, uint32_t& phase,
+                                             int ktiles, int wm, int wn, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  // swizzled byte offset of (row with r&7 == g, k = 4*k4 + t) inside a stage, minus 128*row
+  uint32_t koff[4];
+#pragma unroll
+  for (int k4 = 0; k4 < 4; ++k4) koff[k4] = ((uint32_t)((2 * k4 + (t >> 1)) ^ g) << 4) | ((uint32_t)(t & 1) << 3);
+  const uint32_t a_warp = ringA_u32 + (uint32_t)(wm * 32 + g) * 128u;
+  const uint32_t b_warp = ringB_u32 + (uint32_t)(wn * 32 + g) * 128u;
+  for (int kt = 0; kt < ktiles; ++kt) {
+    mbar_wait(&full_bar[stage], phase);
+    const uint32_t a_st = a_warp + stage * GEMM_A_STAGE_BYTES;
+    const uint32_t b_st = b_warp + stage * GEMM_B_STAGE_BYTES;
+#pragma unroll
+    for (int k4 = 0; k4 < 4; ++k4) {
+      double a[4], b[4];
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) a[mi] = lds_f64(a_st + mi * 1024 + koff[k4]);
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) b[ni] = lds_f64(b_st + ni * 1024 + koff[k4]);
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) dmma_884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[stage]);
+    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+  }
+}
+
+// Producer side: one elected lane streams `ktiles` A/B stages through the ring.
+template <int STAGES>
+__device__ __forceinline__ void tma_producer(const CUtensorMap* tmA, const CUtensorMap* tmB, uint8_t* ringA,
+                                             uint8_t* ringB, uint64_t* full_bar, uint64_t* empty_bar, int& stage,
+                                             uint32_t& phase, int ktiles, int a_col0, int a_row, int b_col0,
+                                             int b_row) {
+  for (int kt = 0; kt < ktiles; ++kt) {
+    mbar_wait(&empty_bar[stage], phase ^ 1u);  // first pass over the ring falls through
+    mbar_arrive_expect_tx(&full_bar[stage], GEMM_STAGE_TX_BYTES);
+    tma_load_2d(ringA + stage * GEMM_A_STAGE_BYTES, tmA, a_col0 + kt * GEMM_BK, a_row, &full_bar[stage]);
+    tma_load_2d(ringB + stage * GEMM_B_STAGE_BYTES, tmB, b_col0 + kt * GEMM_BK, b_row, &full_bar[stage]);
+    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+  }
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -110,13 +161,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int brow = p.b_row0 + tile_n * GEMM_BN;
       int stage = 0;
       uint32_t phase = 0;
-      for (int kt = 0; kt < ktiles; ++kt) {
-        mbar_wait(&empty_bar[stage], phase ^ 1u);  // first pass over the ring falls through
-        mbar_arrive_expect_tx(&full_bar[stage], GEMM_STAGE_TX_BYTES);
-        tma_load_2d(ringA + stage * GEMM_A_STAGE_BYTES, &tmA, p.a_col0 + kt * GEMM_BK, arow, &full_bar[stage]);
-        tma_load_2d(ringB + stage * GEMM_B_STAGE_BYTES, &tmB, p.b_col0 + kt * GEMM_BK, brow, &full_bar[stage]);
-        if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1u; }
-      }
+      tma_producer<GEMM_STAGES>(&tmA, &tmB, ringA, ringB, full_bar, empty_bar, stage, phase, ktiles, p.a_col0, arow,
+                                p.b_col0, brow);
     }
     return;
   }
@@ -161,36 +207,10 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
   }
 
-  // swizzled byte offset of (row with r&7 == g, k = 4*k4 + t) inside a stage, minus 128*row
-  uint32_t koff[4];
-#pragma unroll
-  for (int k4 = 0; k4 < 4; ++k4) koff[k4] = ((uint32_t)((2 * k4 + (t >> 1)) ^ g) << 4) | ((uint32_t)(t & 1) << 3);
-
-  const uint32_t a_warp = smem_u32(ringA) + (uint32_t)(wm * 32 + g) * 128u;
-  const uint32_t b_warp = smem_u32(ringB) + (uint32_t)(wn * 32 + g) * 128u;
-
   int stage = 0;
   uint32_t phase = 0;
-  for (int kt = 0; kt < ktiles; ++kt) {
-    mbar_wait(&full_bar[stage], phase);
-    const uint32_t a_st = a_warp + stage * GEMM_A_STAGE_BYTES;
-    const uint32_t b_st = b_warp + stage * GEMM_B_STAGE_BYTES;
-#pragma unroll
-    for (int k4 = 0; k4 < 4; ++k4) {
-      double a[4], b[4];
-#pragma unroll
-      for (int mi = 0; mi < 4; ++mi) a[mi] = lds_f64(a_st + mi * 1024 + koff[k4]);
-#pragma unroll
-      for (int ni = 0; ni < 4; ++ni) b[ni] = lds_f64(b_st + ni * 1024 + koff[k4]);
-#pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni) dmma_884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_bar[stage]);
-    if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1u; }
-  }
+  mma_mainloop<GEMM_STAGES>(acc, smem_u32(ringA), smem_u32(ringB), full_bar, empty_bar, stage, phase, ktiles, wm, wn,
+                            lane);
 
   // ===== epilogue (registers -> global) =====
   if constexpr (EPI == EPI_SUB) {

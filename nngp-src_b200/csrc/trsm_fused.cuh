@@ -1,0 +1,222 @@
+// trsm_fused.cuh -- the prediction-side triangular solve as ONE persistent kernel (K10 + K11):
+//
+//     V = K_* L^-T   (row-major block buffer B, rows x N, overwritten in place)
+//     var[i] = K(x_i,x_i) - sum_j V[i][j]^2
+//
+// Work item (r, J) = row tile r (128 test rows) x column block J (64 columns):
+//     acc  = B[r, J] - V[r, 0:64J] * L[J, 0:64J]^T     TMA + DMMA main loop (mma_mainloop)
+//     V[r, J] = acc * L_JJ^-T                           one thread per row, forward substitution in smem
+//     ssq[row] += |V[row, J]|^2                         (var written with the last column block)
+// Items are claimed in J-major order from a global counter, so a CTA that needs V[r, 0:64J] finds the
+// item (r, J-1) already claimed by a running CTA: it acquire-spins on progress[r] (no deadlock, no
+// co-residency assumption).  Row tiles never interact, the per-row reduction order is fixed, so the
+// result of a row is bitwise independent of the grid, of the block it sits in and of the GPU count.
+// Compared with one GEMM launch + one substitution launch per column block this removes the per-launch
+// tail (1.73 waves of 296 CTAs -> 13.5 % idle), 2 N/64 launches, and one full re-read of V for the variance.
+#pragma once
+#include "dense_kernels.cuh"
+#include "gemm_nt.cuh"
+
+namespace nngp {
+
+constexpr int TF_STAGES = 3;
+constexpr int TF_RING_BYTES = TF_STAGES * (GEMM_A_STAGE_BYTES + GEMM_B_STAGE_BYTES);  // 72 KiB (>= staging tile)
+constexpr int TF_LS_BYTES = NB * (NB + 1) * 8;
+constexpr int TF_STAGE_TILE_BYTES = GEMM_BM * (NB + 1) * 8;  // 128 x 65 doubles
+static_assert(TF_STAGE_TILE_BYTES <= TF_RING_BYTES, "staging tile must fit in the operand ring");
+constexpr int TF_SMEM_BYTES = TF_RING_BYTES + TF_LS_BYTES + NB * 8 + 2 * TF_STAGES * 8 + 16 + 1024;
+
+struct TrsmFusedParams {
+  double* B;            // rows x N block buffer: K_* on entry, V on exit
+  long long ldb;
+  int rows;
+  const double* L;      // N x N lower factor
+  long long ldl;
+  int N;
+  int row_tiles, col_blocks;
+  int* counter;         // zeroed before launch
+  int* progress;        // [row_tiles], zeroed before launch
+  double* ssq;          // [rows] running sum of squares (not required to be zeroed)
+  const double* kss;    // [rows] K(x,x)
+  double* var;          // [rows] output
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_consumers() {
+  asm volatile("bar.sync 1, %0;" ::"n"(GEMM_CONSUMER_WARPS * 32) : "memory");
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmL,
+                  const TrsmFusedParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+  uint8_t* ring = smem_raw + pad;
+  uint8_t* ringA = ring;
+  uint8_t* ringB = ring + TF_STAGES * GEMM_A_STAGE_BYTES;
+  double(*Bs)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(ring);  // staging tile aliases the ring
+  double(*Ls)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(ring + TF_RING_BYTES);
+  double* rdiag = reinterpret_cast<double*>(ring + TF_RING_BYTES + TF_LS_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(rdiag + NB);
+  uint64_t* empty_bar = full_bar + TF_STAGES;
+  int* s_item = reinterpret_cast<int*>(empty_bar + TF_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < TF_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], GEMM_CONSUMER_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == GEMM_CONSUMER_WARPS && lane == 0) {
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmL);
+  }
+
+  const int total = p.row_tiles * p.col_blocks;
+  int stage = 0;        // ring position: advances identically in the producer and in every consumer
+  uint32_t phase = 0;
+
+  for (;;) {
+    if (threadIdx.x == 0) *s_item = atomicAdd(p.counter, 1);
+    __syncthreads();  // publishes the item; also: nobody still uses the ring / staging tile of the last item
+    const int item = *s_item;
+    if (item >= total) break;
+    const int J = item / p.row_tiles;
+    const int r = item - J * p.row_tiles;
+    const int ktiles = J * (NB / GEMM_BK);
+    const int col0 = J * NB;
+    const int nb = min(NB, p.N - col0);
+    const int row0 = r * GEMM_BM;
+
+    if (warp == GEMM_CONSUMER_WARPS) {
+      // ===== TMA producer =====
+      if (lane == 0) {
+        if (J > 0) {
+          while (ld_acquire_gpu(p.progress + r) < J) __nanosleep(64);
+          fence_proxy_async_all();  // V written through the generic proxy by other CTAs -> read by TMA
+        }
+        tma_producer<TF_STAGES>(&tmB, &tmL, ringA, ringB, full_bar, empty_bar, stage, phase, ktiles, 0, row0, 0, col0);
+      } else {
+        for (int kt = 0; kt < ktiles; ++kt)
+          if (++stage == TF_STAGES) { stage = 0; phase ^= 1u; }
+      }
+      stage = __shfl_sync(0xffffffffu, stage, 0);
+      phase = __shfl_sync(0xffffffffu, phase, 0);
+      __syncthreads();  // end-of-item rendezvous with the consumers' (E) barrier below
+      continue;
+    }
+
+    // ===== consumers =====
+    const int ctid = threadIdx.x;  // 0..255
+    const int wm = warp >> 1, wn = warp & 1;
+    const int g = lane >> 2, t = lane & 3;
+    double acc[4][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+      const int lr = wm * 32 + mi * 8 + g;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int lc = wn * 32 + ni * 8 + 2 * t;
+        double v0 = 0.0, v1 = 0.0;
+        if (row0 + lr < p.rows) {
+          const double* src = p.B + (long long)(row0 + lr) * p.ldb + col0 + lc;
+          if (lc + 1 < nb) {
+            const double2 v = *reinterpret_cast<const double2*>(src);
+            v0 = v.x; v1 = v.y;
+          } else if (lc < nb) {
+            v0 = src[0];
+          }
+        }
+        acc[mi][ni][0] = -v0;
+        acc[mi][ni][1] = -v1;
+      }
+    }
+    {  // diagonal block L_JJ -> Ls (identity padded), 8 loads in flight per thread
+      const double* Ljj = p.L + (long long)col0 * p.ldl + col0;
+      const int c = ctid & 63, rsub = ctid >> 6;
+      for (int r0 = 0; r0 < NB; r0 += 32) {
+        double tv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int rr = r0 + 4 * u + rsub;
+          tv[u] = (rr < nb && c <= rr) ? Ljj[(long long)rr * p.ldl + c] : ((rr == c) ? 1.0 : 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) Ls[r0 + 4 * u + rsub][c] = tv[u];
+      }
+    }
+
+    mma_mainloop<TF_STAGES>(acc, smem_u32(ringA), smem_u32(ringB), full_bar, empty_bar, stage, phase, ktiles, wm, wn,
+                            lane);
+
+    bar_sync_consumers();  // every consumer has left the ring; Ls is complete
+    if (ctid < NB) rdiag[ctid] = 1.0 / Ls[ctid][ctid];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+      const int lr = wm * 32 + mi * 8 + g;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int lc = wn * 32 + ni * 8 + 2 * t;
+        Bs[lr][lc] = -acc[mi][ni][0];
+        Bs[lr][lc + 1] = -acc[mi][ni][1];
+      }
+    }
+    bar_sync_consumers();
+    if (ctid < GEMM_BM) {
+      double* xr = Bs[ctid];
+      double ss = 0.0;
+      for (int j = 0; j < nb; ++j) {
+        double s0 = xr[j], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        const double* lj = Ls[j];
+        int k = 0;
+        for (; k + 3 < j; k += 4) {
+          s0 = fma(-xr[k], lj[k], s0);
+          s1 = fma(-xr[k + 1], lj[k + 1], s1);
+          s2 = fma(-xr[k + 2], lj[k + 2], s2);
+          s3 = fma(-xr[k + 3], lj[k + 3], s3);
+        }
+        for (; k < j; ++k) s0 = fma(-xr[k], lj[k], s0);
+        const double x = ((s0 + s1) + (s2 + s3)) * rdiag[j];
+        xr[j] = x;
+        ss = fma(x, x, ss);
+      }
+      const int grow = row0 + ctid;
+      if (grow < p.rows) {
+        const double tot = ((J > 0) ? __ldcg(p.ssq + grow) : 0.0) + ss;
+        if (J + 1 == p.col_blocks) p.var[grow] = p.kss[grow] - tot;
+        else __stcg(p.ssq + grow, tot);
+      }
+    }
+    bar_sync_consumers();
+    {
+      const int c = ctid & 63, rsub = ctid >> 6;
+      if (c < nb) {
+#pragma unroll 4
+        for (int r0 = 0; r0 < GEMM_BM; r0 += 4) {
+          const int lr = r0 + rsub;
+          if (row0 + lr < p.rows) p.B[(long long)(row0 + lr) * p.ldb + col0 + c] = Bs[lr][c];
+        }
+      }
+    }
+    fence_proxy_async_all();
+    __threadfence();
+    bar_sync_consumers();
+    if (ctid == 0) st_release_gpu(p.progress + r, J + 1);
+    __syncthreads();  // (E) end-of-item rendezvous with the producer warp
+  }
+}
+
+}  // namespace nngp
