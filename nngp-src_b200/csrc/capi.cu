@@ -346,7 +346,9 @@ int run_trsm_fused(nngp_handle* h, double* B, int64_t ldb, int64_t rows, const d
   CKR(get_tmap(h, B, rows, N, ldb, GEMM_BM, &tmB));
   CKR(get_tmap(h, L, N, N, ldl, GEMM_BN, &tmL));
   const long long total = (long long)p.row_tiles * p.col_blocks;
-  const int grid = (int)std::min<long long>(total, 2LL * h->sm_count);
+  int grid = (int)std::min<long long>(total, 2LL * h->sm_count);
+  if (p.row_tiles < grid) grid = p.row_tiles;  // fewer row tiles than CTA slots: one CTA per row tile
+  p.static_sched = (p.row_tiles % grid == 0) ? 1 : 0;
   cudaEvent_t ev;
   class_begin(h, EV_GEMM, &ev);
   trsm_fused_kernel<<<grid, GEMM_THREADS, TF_SMEM_BYTES, h->stream>>>(tmB, tmL, p);

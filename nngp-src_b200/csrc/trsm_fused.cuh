@@ -34,7 +34,9 @@ struct TrsmFusedParams {
   long long ldl;
   int N;
   int row_tiles, col_blocks;
-  int* counter;         // zeroed before launch
+  int* counter;         // zeroed before launch (dynamic schedule only)
+  int static_sched;     // 1: CTA c takes items c, c+G, c+2G, ... (used when row_tiles % G == 0: every
+                        //    dependency is then the CTA's own previous item -> no cross-CTA waiting)
   int* progress;        // [row_tiles], zeroed before launch
   double* ssq;          // [rows] running sum of squares (not required to be zeroed)
   const double* kss;    // [rows] K(x,x)
@@ -89,8 +91,10 @@ trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
   int stage = 0;        // ring position: advances identically in the producer and in every consumer
   uint32_t phase = 0;
 
+  int next_static = blockIdx.x;
   for (;;) {
-    if (threadIdx.x == 0) *s_item = atomicAdd(p.counter, 1);
+    if (threadIdx.x == 0) *s_item = p.static_sched ? next_static : atomicAdd(p.counter, 1);
+    next_static += gridDim.x;
     __syncthreads();  // publishes the item; also: nobody still uses the ring / staging tile of the last item
     const int item = *s_item;
     if (item >= total) break;
