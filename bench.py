@@ -263,7 +263,7 @@ def run_b200(args):
     traffic = json.loads(ncu_file.read_text()).get("dram_bytes_per_launch") if ncu_file.exists() else None
     flops_per_query = float(n) * n + 2.0 * n * d + 4.0 * n
     roofline = {
-        "bound": "tensor", "kernel": "gemm_nt_kernel<EPI_SUB> (TMA + DMMA.8x8x4 FP64 GEMM update of the triangular solve)",
+        "bound": "tensor", "kernel": "trsm_fused_kernel (persistent TMA + DMMA.8x8x4 FP64 triangular solve V = K_* L^-T with fused variance)",
         "achieved": achieved, "peak": peak_dmma, "unit": "TFLOP/s", "frac": achieved / peak_dmma,
         "traffic": traffic,
         "peak_source": "FP64 tensor (DMMA) issue-rate microbenchmark measured in this run (burst); MEASURED_PEAKS.json "

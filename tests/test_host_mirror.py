@@ -1,0 +1,145 @@
+"""CPU: the Python mirror of the neural-tangents surface (host logic only -- no arithmetic here).
+The engine is replaced by an oracle-backed fake through runtime.new_handle, so laziness, caching, shapes,
+error conventions and the lazy covariance are checked without a GPU."""
+import numpy as np
+import pytest
+
+import nngp_oracle as oracle
+from nngp_b200 import batch, predict, runtime, stax
+from nngp_b200.estimator import Estimator
+
+
+class FakeHandle:
+    created = 0
+    fits = 0
+
+    def __init__(self, spec, diag_reg, absolute):
+        FakeHandle.created += 1
+        self.spec, self.diag_reg, self.absolute, self.fit_ = spec, diag_reg, absolute, None
+
+    def kernel(self, x1, x2=None):
+        return oracle.kernel_fn(x1, x2, self.spec.depth, self.spec.sigma_w, self.spec.sigma_b)
+
+    def fit(self, x, y):
+        FakeHandle.fits += 1
+        self.fit_ = oracle.Fit(x, y, self.spec.depth, self.spec.sigma_w, self.spec.sigma_b, self.diag_reg, self.absolute)
+
+    def predict(self, x, want_var=True):
+        return self.fit_.predict(x, want_var)
+
+
+@pytest.fixture()
+def fake_engine(monkeypatch):
+    FakeHandle.created = FakeHandle.fits = 0
+    monkeypatch.setattr(runtime, "new_handle",
+                        lambda spec, diag_reg=0.0, diag_reg_absolute=False: FakeHandle(spec, diag_reg, diag_reg_absolute))
+    return FakeHandle
+
+
+def test_serial_collapses_to_kernel_spec():
+    init_fn, apply_fn, kernel_fn = stax.serial(stax.Dense(512), stax.Relu(), stax.Dense(1))      # train.py:161-164
+    assert kernel_fn.spec == stax.KernelSpec(depth=2, sigma_w=1.0, sigma_b=0.0)
+    _, _, k3 = stax.serial(stax.Dense(512, W_std=1.5, b_std=0.05), stax.Relu(), stax.Dense(512, W_std=1.5, b_std=0.05),
+                           stax.Relu(), stax.Dense(1, W_std=1.5, b_std=0.05))                      # active_train.py:44-49
+    assert k3.spec == stax.KernelSpec(depth=3, sigma_w=1.5, sigma_b=0.05)
+    assert batch.batch(kernel_fn, device_count=0, batch_size=0) is kernel_fn                        # train.py:166-168
+    with pytest.raises(NotImplementedError):
+        init_fn(None, (1, 2))
+    for bad in ([stax.Dense(1), stax.Dense(1)], [stax.Relu(), stax.Dense(1)], [stax.Dense(1), stax.Relu()],
+                [stax.Dense(1, W_std=2.0), stax.Relu(), stax.Dense(1)]):
+        with pytest.raises(NotImplementedError):
+            stax.serial(*bad)
+    with pytest.raises(NotImplementedError):
+        stax.Conv(3, (3, 3))
+    with pytest.raises(NotImplementedError):
+        stax.Dense(1, parameterization="standard")
+
+
+def test_kernel_fn_get_semantics(fake_engine):
+    _, _, kernel_fn = stax.serial(stax.Dense(512), stax.Relu(), stax.Dense(1))
+    x = np.random.default_rng(0).uniform(0, 10, (5, 4))
+    assert np.allclose(kernel_fn(x, None, "nngp"), oracle.kernel_fn(x))
+    assert kernel_fn(x, x[:2], get="nngp").shape == (5, 2)
+    with pytest.raises(NotImplementedError):
+        kernel_fn(x, None, "ntk")
+    with pytest.raises(ValueError):
+        kernel_fn(x[0], None, "nngp")
+
+
+def test_predict_fn_is_lazy_cached_and_shaped_like_neural_tangents(fake_engine):
+    rng = np.random.default_rng(1)
+    x, y, xt = rng.uniform(0, 10, (30, 6)), rng.uniform(0, 8, (30, 1)), rng.uniform(0, 10, (7, 6))
+    _, _, kernel_fn = stax.serial(stax.Dense(512), stax.Relu(), stax.Dense(1))
+    predict_fn = predict.gradient_descent_mse_ensemble(kernel_fn, x, y, diag_reg=1e-3)             # train.py:171-172
+    assert fake_engine.fits == 0                                  # construction does no math (BASELINE.md note)
+    pred_mean, pred_cov = predict_fn(x_test=xt, get="nngp", compute_cov=True)                      # train.py:157-158
+    assert fake_engine.fits == 1
+    predict_fn(x_test=xt, get="nngp", compute_cov=True)
+    assert fake_engine.fits == 1                                  # cached
+    assert pred_mean.shape == (7, 1) and pred_cov.shape == (7, 7)
+    ref = oracle.Fit(x, y)
+    rm, rv = ref.predict(xt)
+    pred_std = np.sqrt(np.diag(pred_cov))                                                           # train.py:180
+    assert np.allclose(pred_mean.ravel(), rm) and np.allclose(pred_std, np.sqrt(rv))
+    assert np.allclose(pred_cov.diagonal(), rv) and np.isclose(np.trace(pred_cov), rv.sum())
+    with pytest.raises(NotImplementedError):
+        np.asarray(pred_cov)                                      # the T x T matrix does not exist
+    m_only = predict_fn(x_test=xt, get="nngp", compute_cov=False)
+    assert m_only.shape == (7, 1)
+    on_train = predict_fn(get="nngp")                             # x_test=None -> training inputs
+    assert on_train.shape == (30, 1)
+    # a new closure is a new fit (ActiveLearner.py:69,76 relies on it)
+    predict.gradient_descent_mse_ensemble(kernel_fn, x, y, diag_reg=1e-3)(x_test=xt, get="nngp")
+    assert fake_engine.fits == 2
+    for kw in ({"t": 1.0}, {"get": "ntk"}, {"foo": 1}):
+        with pytest.raises(NotImplementedError):
+            predict_fn(x_test=xt, **kw)
+    y1 = y.ravel()
+    assert predict.gradient_descent_mse_ensemble(kernel_fn, x, y1, diag_reg=1e-3)(x_test=xt, get="nngp").shape == (7,)
+    with pytest.raises(ValueError):
+        predict.gradient_descent_mse_ensemble(kernel_fn, x, y[:-1], diag_reg=1e-3)
+    with pytest.raises(NotImplementedError):
+        predict.gradient_descent_mse_ensemble(kernel_fn, x, np.zeros((30, 2)), diag_reg=1e-3)
+
+
+def test_estimator_mirror(fake_engine):
+    class Enc:
+        def parse_line_without_card_then_encode(self, line):
+            return np.array([float(v) for v in line.split(",")])
+    rng = np.random.default_rng(2)
+    x, y = rng.uniform(0, 10, (25, 4)), rng.uniform(0, 8, (25, 1))
+    est = Estimator("schema", "data", "queries", X_train=x, Y_train=y, nngp_encoder=Enc(), verbose=False)
+    assert fake_engine.fits == 0
+    est.load_model()                                                                                # estimator.py:37-40
+    assert fake_engine.fits == 1
+    lines = ["1,2,3,4", "4,3,2,1", "0,0,5,5"]
+    mean, std = est.predict(lines)                                                                  # estimator.py:42-61
+    rm, rv = oracle.Fit(x, y).predict(np.array([[1, 2, 3, 4], [4, 3, 2, 1], [0, 0, 5, 5.0]]))
+    assert mean.shape == (3,) and std.shape == (3,)
+    assert np.allclose(mean, rm) and np.allclose(std, np.sqrt(rv))
+    loaded = Estimator("s", "d", "q", 64, False, 100.0, 1.0, loader=lambda *a: (x, y, Enc()), verbose=False)
+    assert loaded.X_train.shape == (25, 4)
+    with pytest.raises(ValueError):
+        Estimator("s", "d", "q", verbose=False)
+
+
+def test_compat_shims_resolve_to_the_mirror():
+    import importlib
+    import sys
+    from pathlib import Path
+    compat = str(Path(__file__).resolve().parents[1] / "nngp-src_b200" / "compat")
+    sys.path.insert(0, compat)
+    try:
+        nt = importlib.import_module("neural_tangents")
+        jnp = importlib.import_module("jax.numpy")
+        from jax.config import config
+        from jax.lib import xla_bridge
+        config.update("jax_enable_x64", True)
+        assert nt.stax is stax and nt.predict is predict and nt.batch is batch.batch
+        assert xla_bridge.get_backend().platform == "cpu"
+        cov = predict.LazyCovariance(np.array([4.0, 9.0]))
+        assert np.allclose(jnp.sqrt(jnp.diag(cov)), [2.0, 3.0])
+    finally:
+        sys.path.remove(compat)
+        for m in [k for k in sys.modules if k == "jax" or k.startswith("jax.") or k == "neural_tangents"]:
+            del sys.modules[m]
