@@ -123,6 +123,28 @@ def test_estimator_mirror(fake_engine):
         Estimator("s", "d", "q", verbose=False)
 
 
+def test_active_learner_mirror_matches_oracle_selection(fake_engine):
+    """Config C4 logic (active/ActiveLearner.py:43-77): deterministic top-k branch vs the oracle's rule."""
+    from nngp_b200.active import ActiveLearner
+    from nngp_b200 import synth
+    xtr, ytr, xpool, ypool = synth.make_problem(60, 90, 8)
+    xval, yval = synth.encodings(30, 8, 5), None
+    yval = synth.labels(xval)
+    _, _, kernel_fn = stax.serial(stax.Dense(512), stax.Relu(), stax.Dense(1))
+    al = ActiveLearner(budget=20, active_iters=2, verbose=False)
+    pf = al.train(kernel_fn, xtr, ytr[:, None])
+    idx = al.active_test(pf, xpool)
+    ref = oracle.Fit(xtr, ytr)
+    rm, rv = ref.predict(xpool)
+    assert list(idx) == list(oracle.active_select(rm[:, None], np.sqrt(rv), 20))
+    fits0 = fake_engine.fits
+    pf2, x_end, y_end = al.active_train(kernel_fn, xtr, ytr[:, None], xpool, ypool[:, None], xval, yval[:, None])
+    assert x_end.shape == (60 + 2 * 20, 8) and y_end.shape == (100, 1)
+    assert fake_engine.fits - fits0 == 3 and len(al.history) == 3      # refit from scratch every iteration
+    x2, y2, xp2, yp2 = al.merge_data(idx, xtr, ytr[:, None], xpool, ypool[:, None])
+    assert x2.shape[0] == 80 and xp2.shape[0] == 70 and not set(map(tuple, xp2)) & set(map(tuple, xpool[idx]))
+
+
 def test_compat_shims_resolve_to_the_mirror():
     import importlib
     import sys
