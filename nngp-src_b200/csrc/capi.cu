@@ -52,7 +52,9 @@ struct nngp_handle {
   nngp_config cfg;
   int device = 0;
   int sm_count = 148;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;        // main stream (all stage timing events live here)
+  cudaStream_t panel_stream = nullptr;  // high-priority stream: Cholesky panel look-ahead
+  cudaStream_t cur = nullptr;           // stream the launch helpers currently target
   PFN_encodeTiled encode = nullptr;
   std::string err;
 
@@ -158,13 +160,13 @@ struct StageTimer {  // level >= 1: accumulates into *dst at flush time
 };
 void class_begin(nngp_handle* h, int cls, cudaEvent_t* a) {
   *a = nullptr;
-  if (h->cfg.stats_level >= 2) { *a = get_event(h); cudaEventRecord(*a, h->stream); }
+  if (h->cfg.stats_level >= 2) { *a = get_event(h); cudaEventRecord(*a, h->cur); }
   (void)cls;
 }
 void class_end(nngp_handle* h, int cls, cudaEvent_t a) {
   if (a) {
     cudaEvent_t b = get_event(h);
-    cudaEventRecord(b, h->stream);
+    cudaEventRecord(b, h->cur);
     h->pending.push_back({a, b, cls});
   }
 }
@@ -225,7 +227,7 @@ int launch_gemm(nngp_handle* h, const MatView& A, int a_row0, int a_col0, const 
   cudaEvent_t ev;
   const int cls = (EPI == EPI_GRAM) ? EV_GRAM : EV_GEMM;
   class_begin(h, cls, &ev);
-  gemm_nt_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(tmA, tmB, p);
+  gemm_nt_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->cur>>>(tmA, tmB, p);
   class_end(h, cls, ev);
   CK(cudaGetLastError());
   h->st.kernel_launches++;
@@ -285,30 +287,71 @@ int chol_outer_width() {
   return w;
 }
 
-int run_potrf(nngp_handle* h, double* A, int64_t ld, int64_t N) {
+// Factor the w-wide panel starting at column j0 (rows j0..N): left-looking over its 64-wide sub-panels.
+int potrf_panel(nngp_handle* h, double* A, int64_t ld, int64_t N, int64_t j0, int64_t w) {
   int* info = h->flags.as<int>();
+  MatView Av{A, N, N, ld};
+  for (int64_t s0 = j0; s0 < j0 + w; s0 += NB) {
+    const int64_t nb = std::min<int64_t>(NB, N - s0);
+    if (s0 > j0)  // A[s0:N, s0:s0+nb] -= A[s0:N, j0:s0] * A[s0:s0+nb, j0:s0]^T
+      CKR(run_gemm_sub(h, Av, s0, j0, Av, s0, j0, N - s0, nb, s0 - j0, A + s0 * ld + s0, ld, 0));
+    potf2_64_kernel<<<1, 256, 0, h->cur>>>(A + s0 * ld + s0, ld, (int)nb, (int)s0, info);
+    h->st.kernel_launches++;
+    const int64_t below = N - s0 - nb;
+    if (below > 0) {
+      const int grid = (int)((below + TRSM_ROWS - 1) / TRSM_ROWS);
+      trsm_rows_64_kernel<<<grid, TRSM_ROWS, TRSM_SMEM_BYTES, h->cur>>>(A + (s0 + nb) * ld + s0, ld, (int)below,
+                                                                       A + s0 * ld + s0, ld, (int)nb);
+      h->st.kernel_launches++;
+    }
+  }
+  return NNGP_OK;
+}
+
+// Look-ahead schedule: the trailing update of outer step j is split into (A) the columns of the NEXT
+// panel and (B) the rest; as soon as (A) is done the next panel is factored on a high-priority stream
+// while (B) keeps the tensor pipes busy on the main stream.
+int run_potrf(nngp_handle* h, double* A, int64_t ld, int64_t N) {
   const int W = chol_outer_width();
   MatView Av{A, N, N, ld};
-  for (int64_t j0 = 0; j0 < N; j0 += W) {
-    const int64_t w = std::min<int64_t>(W, N - j0);
-    for (int64_t s0 = j0; s0 < j0 + w; s0 += NB) {
-      const int64_t nb = std::min<int64_t>(NB, N - s0);
-      if (s0 > j0)  // A[s0:N, s0:s0+nb] -= A[s0:N, j0:s0] * A[s0:s0+nb, j0:s0]^T
-        CKR(run_gemm_sub(h, Av, s0, j0, Av, s0, j0, N - s0, nb, s0 - j0, A + s0 * ld + s0, ld, 0));
-      potf2_64_kernel<<<1, 256, 0, h->stream>>>(A + s0 * ld + s0, ld, (int)nb, (int)s0, info);
-      h->st.kernel_launches++;
-      const int64_t below = N - s0 - nb;
-      if (below > 0) {
-        const int grid = (int)((below + TRSM_ROWS - 1) / TRSM_ROWS);
-        trsm_rows_64_kernel<<<grid, TRSM_ROWS, TRSM_SMEM_BYTES, h->stream>>>(A + (s0 + nb) * ld + s0, ld, (int)below,
-                                                                            A + s0 * ld + s0, ld, (int)nb);
-        h->st.kernel_launches++;
-      }
-    }
-    const int64_t t0 = j0 + w;
-    if (t0 < N)  // trailing: A[t0:N, t0:N] (lower) -= A[t0:N, j0:t0] * A[t0:N, j0:t0]^T
-      CKR(run_gemm_sub(h, Av, t0, j0, Av, t0, j0, N - t0, N - t0, w, A + t0 * ld + t0, ld, 1));
+  const bool lookahead = h->panel_stream != nullptr && N > 2 * W;
+  cudaEvent_t ev_cols = get_event(h), ev_panel = get_event(h);
+  int rc = NNGP_OK;
+  if (lookahead) {  // the panel stream starts after everything queued on the main stream so far
+    cudaEventRecord(ev_cols, h->stream);
+    cudaStreamWaitEvent(h->panel_stream, ev_cols, 0);
   }
+  for (int64_t j0 = 0; j0 < N && rc == NNGP_OK; j0 += W) {
+    const int64_t w = std::min<int64_t>(W, N - j0);
+    const int64_t t0 = j0 + w;
+    h->cur = lookahead ? h->panel_stream : h->stream;
+    rc = potrf_panel(h, A, ld, N, j0, w);
+    if (rc != NNGP_OK || t0 >= N) break;
+    if (lookahead) {
+      cudaEventRecord(ev_panel, h->panel_stream);
+      cudaStreamWaitEvent(h->stream, ev_panel, 0);
+    }
+    h->cur = h->stream;
+    const int64_t w2 = std::min<int64_t>(W, N - t0);
+    const int64_t t1 = t0 + w2;
+    // (A) next panel's columns: A[t0:N, t0:t1] (lower tiles) -= A[t0:N, j0:t0] * A[t0:t1, j0:t0]^T
+    rc = run_gemm_sub(h, Av, t0, j0, Av, t0, j0, N - t0, w2, w, A + t0 * ld + t0, ld, 1);
+    if (rc != NNGP_OK) break;
+    if (lookahead) {
+      cudaEventRecord(ev_cols, h->stream);
+      cudaStreamWaitEvent(h->panel_stream, ev_cols, 0);
+    }
+    // (B) the rest of the trailing matrix: A[t1:N, t1:N] (lower) -= A[t1:N, j0:t0] * A[t1:N, j0:t0]^T
+    if (t1 < N) rc = run_gemm_sub(h, Av, t1, j0, Av, t1, j0, N - t1, N - t1, w, A + t1 * ld + t1, ld, 1);
+  }
+  if (lookahead) {  // join: the main stream continues only after the last panel
+    cudaEventRecord(ev_panel, h->panel_stream);
+    cudaStreamWaitEvent(h->stream, ev_panel, 0);
+  }
+  h->cur = h->stream;
+  h->ev_pool.push_back(ev_cols);
+  h->ev_pool.push_back(ev_panel);
+  CKR(rc);
   CK(cudaGetLastError());
   return NNGP_OK;
 }
@@ -484,9 +527,16 @@ int nngp_create(const nngp_config* cfg, nngp_handle** out) {
   h = nh;
   auto bail = [&](int code) { std::string m = h->err; nngp_destroy(h); g_create_error = m; return code; };
   if (cudaSetDevice(dev) != cudaSuccess) { fail(h, NNGP_ECUDA, "cudaSetDevice(%d) failed", dev); return bail(NNGP_ECUDA); }
-  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&h->panel_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
     fail(h, NNGP_ECUDA, "cudaStreamCreate failed");
     return bail(NNGP_ECUDA);
+  }
+  h->cur = h->stream;
+  if (const char* e = getenv("NNGP_CHOL_LOOKAHEAD")) {
+    if (!strcmp(e, "0")) { cudaStreamDestroy(h->panel_stream); h->panel_stream = nullptr; }
   }
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -522,6 +572,7 @@ void nngp_destroy(nngp_handle* h) {
     release(*b);
   for (auto& r : h->pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : h->ev_pool) cudaEventDestroy(e);
+  if (h->panel_stream) cudaStreamDestroy(h->panel_stream);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }

@@ -75,12 +75,11 @@ __global__ void diag_reg_kernel(double* __restrict__ K, long long ld, int N, dou
 
 // In-place lower Cholesky of the n x n (n <= 64) block at A (row-major, ld).  One CTA, 256 threads as a
 // 16 x 16 grid, each thread owning a 4 x 4 register sub-block (right-looking, two barriers per column;
-// the pivot column is scaled by the reciprocal pivot as LAPACK dpotf2 does).
+// the pivot column is scaled by the reciprocal pivot, as LAPACK dpotf2 does, obtained with one rsqrt).
 // On a non-positive pivot: *info = global pivot index + 1 (first failure wins), block left as is.
 __global__ void __launch_bounds__(256) potf2_64_kernel(double* __restrict__ A, long long ld, int n, int pivot0,
                                                        int* __restrict__ info) {
   __shared__ double colj[NB];
-  __shared__ double diag_s;
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   double v[4][4];
@@ -94,44 +93,44 @@ __global__ void __launch_bounds__(256) potf2_64_kernel(double* __restrict__ A, l
   bool bad = false;
   for (int j = 0; j < n; ++j) {
     const int jb = j >> 2, ja = j & 3;
-    if (ty == jb && tx == jb) {
-      double d = 0.0;
+    if (tx == jb) {  // owners of column j publish the (unscaled) column; the diagonal owner also the pivot
 #pragma unroll
-      for (int a = 0; a < 4; ++a) if (a == ja) d = v[a][a];
-      diag_s = d;
+      for (int a = 0; a < 4; ++a) {
+        double cur = 0.0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) if (b == ja) cur = v[a][b];
+        colj[ty * 4 + a] = cur;
+      }
     }
     __syncthreads();
-    const double d = diag_s;
+    const double d = colj[j];
     if (!(d > 0.0)) {  // also catches NaN; d is CTA-uniform => uniform exit
       if (tid == 0) atomicCAS(info, 0, pivot0 + j + 1);
       bad = true;
       break;
     }
-    if (tx == jb) {  // owners of column j: scale and publish
-      const double piv = sqrt(d);
-      const double rinv = 1.0 / piv;
+    // every thread derives the pivot itself (one rsqrt chain, no second round trip through smem)
+    const double rinv = rsqrt(d);
+    const double piv = d * rinv;
+    double lr[4], lc[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) lr[a] = (ty * 4 + a > j) ? colj[ty * 4 + a] * rinv : 0.0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) lc[b] = (tx * 4 + b > j) ? colj[tx * 4 + b] * rinv : 0.0;
+    if (tx == jb) {
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
         const int r = ty * 4 + a;
-        double cur = 0.0;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) if (b == ja) cur = v[a][b];
-        const double l = (r > j) ? cur * rinv : ((r == j) ? piv : cur);
-#pragma unroll
-        for (int b = 0; b < 4; ++b) if (b == ja) v[a][b] = l;
-        colj[r] = (r > j) ? l : 0.0;
+        for (int b = 0; b < 4; ++b)
+          if (b == ja) v[a][b] = (r > j) ? lr[a] : ((r == j) ? piv : v[a][b]);
       }
     }
-    __syncthreads();
-    double lr[4], lc[4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a) lr[a] = colj[ty * 4 + a];
-#pragma unroll
-    for (int b = 0; b < 4; ++b) lc[b] = (tx * 4 + b > j) ? colj[tx * 4 + b] : 0.0;
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int b = 0; b < 4; ++b) v[a][b] = fma(-lr[a], lc[b], v[a][b]);
+    __syncthreads();  // colj is rewritten by the next column's owners
   }
   if (bad) return;
 #pragma unroll
@@ -144,17 +143,33 @@ __global__ void __launch_bounds__(256) potf2_64_kernel(double* __restrict__ A, l
 }
 
 // X * Ljj^T = B in place, for `rows` rows of B (row-major, ldb) and the n x n (n <= 64) lower block
-// Ljj (row-major, ldl).  128 rows per CTA, one thread per row, forward substitution along the row
-// (reciprocal diagonal, as optimised BLAS dtrsm does).  Global loads are batched 8 deep per thread.
+// Ljj (row-major, ldl).  128 rows per CTA, one thread per row.  The row lives in 64 registers and is
+// solved right-looking (x_j = b_j / l_jj ; b_k -= x_j l_kj for k > j): 63-j independent FMAs per step, so
+// the substitution is issue-bound instead of latency-bound.  Global traffic is staged through smem so
+// that it stays coalesced; loads are batched 8 deep per thread.
 constexpr int TRSM_ROWS = 128;
-constexpr int TRSM_SMEM_BYTES = (TRSM_ROWS * (NB + 1) + NB * (NB + 1) + NB) * 8;
+constexpr int TRSM_SMEM_BYTES = (TRSM_ROWS * (NB + 1) + NB * (NB + 2) + NB) * 8;
+
+// solve one row held in x[0..63] against Lt (Lt[j][k] = L[k][j], row pitch NB+2 doubles) and rdiag
+__device__ __forceinline__ void solve_row_regs(double (&x)[NB], const double* __restrict__ Lt,
+                                               const double* __restrict__ rdiag) {
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    x[j] *= rdiag[j];
+    const double xj = x[j];
+    const double* lt = Lt + j * (NB + 2);
+#pragma unroll
+    for (int k = j + 1; k < NB; ++k) x[k] = fma(-xj, lt[k], x[k]);
+  }
+}
+
 __global__ void __launch_bounds__(TRSM_ROWS) trsm_rows_64_kernel(double* __restrict__ B, long long ldb, int rows,
                                                                 const double* __restrict__ Ljj, long long ldl,
                                                                 int n) {
   extern __shared__ double sm[];
   double(*Bs)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm);
-  double(*Ls)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm + TRSM_ROWS * (NB + 1));
-  double* rdiag = sm + TRSM_ROWS * (NB + 1) + NB * (NB + 1);
+  double* Lt = sm + TRSM_ROWS * (NB + 1);            // [NB][NB+2], transposed diagonal block
+  double* rdiag = Lt + NB * (NB + 2);
   const int tid = threadIdx.x;
   const int row0 = blockIdx.x * TRSM_ROWS;
   const int c = tid & 63, rsub = tid >> 6;  // thread covers column c of rows rsub, rsub+2, ...
@@ -166,7 +181,7 @@ __global__ void __launch_bounds__(TRSM_ROWS) trsm_rows_64_kernel(double* __restr
       t[u] = (r < n && c <= r) ? Ljj[(long long)r * ldl + c] : ((r == c) ? 1.0 : 0.0);
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) Ls[r0 + 2 * u + rsub][c] = t[u];
+    for (int u = 0; u < 8; ++u) Lt[c * (NB + 2) + r0 + 2 * u + rsub] = t[u];   // Lt[c][r] = L[r][c]
   }
   for (int r0 = 0; r0 < TRSM_ROWS; r0 += 16) {
     double t[8];
@@ -179,21 +194,15 @@ __global__ void __launch_bounds__(TRSM_ROWS) trsm_rows_64_kernel(double* __restr
     for (int u = 0; u < 8; ++u) Bs[r0 + 2 * u + rsub][c] = t[u];
   }
   __syncthreads();
-  if (tid < NB) rdiag[tid] = 1.0 / Ls[tid][tid];
+  if (tid < NB) rdiag[tid] = 1.0 / Lt[tid * (NB + 2) + tid];
   __syncthreads();
-  double* xr = Bs[tid];
-  for (int j = 0; j < n; ++j) {
-    double s0 = xr[j], s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    const double* lj = Ls[j];
-    int k = 0;
-    for (; k + 3 < j; k += 4) {
-      s0 = fma(-xr[k], lj[k], s0);
-      s1 = fma(-xr[k + 1], lj[k + 1], s1);
-      s2 = fma(-xr[k + 2], lj[k + 2], s2);
-      s3 = fma(-xr[k + 3], lj[k + 3], s3);
-    }
-    for (; k < j; ++k) s0 = fma(-xr[k], lj[k], s0);
-    xr[j] = ((s0 + s1) + (s2 + s3)) * rdiag[j];
+  {
+    double x[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) x[j] = Bs[tid][j];
+    solve_row_regs(x, Lt, rdiag);
+#pragma unroll
+    for (int j = 0; j < NB; ++j) Bs[tid][j] = x[j];
   }
   __syncthreads();
   for (int r0 = 0; r0 < TRSM_ROWS; r0 += 2) {
