@@ -62,7 +62,7 @@ struct nngp_handle {
   bool fitted = false;
   int64_t N = 0, D = 0, ldx = 0, ldl = 0;
   double lambda = 0.0;
-  DevBuf X, q, L, alpha, scratch_y;
+  DevBuf X, q, L, alpha;
   DevBuf flags;   // int[2]: {potrf info, non-finite input}
   DevBuf lam_d;   // double[1]
 
@@ -277,27 +277,30 @@ int run_gemm_sub(nngp_handle* h, const MatView& A, int64_t a_row0, int64_t a_col
 // Right-looking over W-wide outer panels (trailing SYRK with K = W on the DMMA core), left-looking
 // over the 64-wide sub-panels inside a panel (potf2 on the diagonal block, one-thread-per-row
 // forward substitution for the block column below it).
-int chol_outer_width() {
-  static int w = [] {
+// Outer panel width: 256 keeps the panel chain short for small N; for N >= 16384 the trailing SYRK
+// dominates and K = 512 runs closer to the DMMA peak (measured at N = 32768: 394 / 378 / 371 ms for
+// W = 256 / 384 / 512; at N = 8192: 13.8 / 14.5 / 15.2 ms).  NNGP_CHOL_W overrides.
+int chol_outer_width(int64_t N) {
+  static int forced = [] {
     const char* e = getenv("NNGP_CHOL_W");
-    int v = e ? atoi(e) : 256;
-    if (v < NB) v = NB;
-    return (v / NB) * NB;
+    int v = e ? atoi(e) : 0;
+    return v >= NB ? (v / NB) * NB : 0;
   }();
-  return w;
+  if (forced) return forced;
+  return N >= 16384 ? 512 : 256;
 }
 
-// Factor the w-wide panel starting at column j0 (rows j0..N): left-looking over its 64-wide sub-panels.
-int potrf_panel(nngp_handle* h, double* A, int64_t ld, int64_t N, int64_t j0, int64_t w) {
+// `R` = N + extra rows riding along below the matrix (see run_potrf).
+int potrf_panel(nngp_handle* h, double* A, int64_t ld, int64_t N, int64_t R, int64_t j0, int64_t w) {
   int* info = h->flags.as<int>();
-  MatView Av{A, N, N, ld};
+  MatView Av{A, R, N, ld};
   for (int64_t s0 = j0; s0 < j0 + w; s0 += NB) {
     const int64_t nb = std::min<int64_t>(NB, N - s0);
     if (s0 > j0)  // A[s0:N, s0:s0+nb] -= A[s0:N, j0:s0] * A[s0:s0+nb, j0:s0]^T
-      CKR(run_gemm_sub(h, Av, s0, j0, Av, s0, j0, N - s0, nb, s0 - j0, A + s0 * ld + s0, ld, 0));
+      CKR(run_gemm_sub(h, Av, s0, j0, Av, s0, j0, R - s0, nb, s0 - j0, A + s0 * ld + s0, ld, 0));
     potf2_64_kernel<<<1, 256, 0, h->cur>>>(A + s0 * ld + s0, ld, (int)nb, (int)s0, info);
     h->st.kernel_launches++;
-    const int64_t below = N - s0 - nb;
+    const int64_t below = R - s0 - nb;
     if (below > 0) {
       const int grid = (int)((below + TRSM_ROWS - 1) / TRSM_ROWS);
       trsm_rows_64_kernel<<<grid, TRSM_ROWS, TRSM_SMEM_BYTES, h->cur>>>(A + (s0 + nb) * ld + s0, ld, (int)below,
@@ -311,9 +314,13 @@ int potrf_panel(nngp_handle* h, double* A, int64_t ld, int64_t N, int64_t j0, in
 // Look-ahead schedule: the trailing update of outer step j is split into (A) the columns of the NEXT
 // panel and (B) the rest; as soon as (A) is done the next panel is factored on a high-priority stream
 // while (B) keeps the tensor pipes busy on the main stream.
-int run_potrf(nngp_handle* h, double* A, int64_t ld, int64_t N) {
-  const int W = chol_outer_width();
-  MatView Av{A, N, N, ld};
+// `extra` rows stored below the matrix (rows N..N+extra-1, N columns each) are carried through every
+// panel solve and trailing update: on exit they hold  E L^-T.  The fit puts y^T there, so the forward
+// substitution z = L^-1 y of the alpha solve costs nothing extra (one more row in GEMMs already running).
+int run_potrf(nngp_handle* h, double* A, int64_t ld, int64_t N, int64_t extra = 0) {
+  const int W = chol_outer_width(N);
+  const int64_t R = N + extra;
+  MatView Av{A, R, N, ld};
   const bool lookahead = h->panel_stream != nullptr && N > 2 * W;
   cudaEvent_t ev_cols = get_event(h), ev_panel = get_event(h);
   int rc = NNGP_OK;
@@ -325,7 +332,7 @@ int run_potrf(nngp_handle* h, double* A, int64_t ld, int64_t N) {
     const int64_t w = std::min<int64_t>(W, N - j0);
     const int64_t t0 = j0 + w;
     h->cur = lookahead ? h->panel_stream : h->stream;
-    rc = potrf_panel(h, A, ld, N, j0, w);
+    rc = potrf_panel(h, A, ld, N, R, j0, w);
     if (rc != NNGP_OK || t0 >= N) break;
     if (lookahead) {
       cudaEventRecord(ev_panel, h->panel_stream);
@@ -335,14 +342,14 @@ int run_potrf(nngp_handle* h, double* A, int64_t ld, int64_t N) {
     const int64_t w2 = std::min<int64_t>(W, N - t0);
     const int64_t t1 = t0 + w2;
     // (A) next panel's columns: A[t0:N, t0:t1] (lower tiles) -= A[t0:N, j0:t0] * A[t0:t1, j0:t0]^T
-    rc = run_gemm_sub(h, Av, t0, j0, Av, t0, j0, N - t0, w2, w, A + t0 * ld + t0, ld, 1);
+    rc = run_gemm_sub(h, Av, t0, j0, Av, t0, j0, R - t0, w2, w, A + t0 * ld + t0, ld, 1);
     if (rc != NNGP_OK) break;
     if (lookahead) {
       cudaEventRecord(ev_cols, h->stream);
       cudaStreamWaitEvent(h->panel_stream, ev_cols, 0);
     }
     // (B) the rest of the trailing matrix: A[t1:N, t1:N] (lower) -= A[t1:N, j0:t0] * A[t1:N, j0:t0]^T
-    if (t1 < N) rc = run_gemm_sub(h, Av, t1, j0, Av, t1, j0, N - t1, N - t1, w, A + t1 * ld + t1, ld, 1);
+    if (t1 < N) rc = run_gemm_sub(h, Av, t1, j0, Av, t1, j0, R - t1, N - t1, w, A + t1 * ld + t1, ld, 1);
   }
   if (lookahead) {  // join: the main stream continues only after the last panel
     cudaEventRecord(ev_panel, h->panel_stream);
@@ -408,22 +415,14 @@ bool use_fused_trsm() {
   return v != 0;
 }
 
-// v <- L^-T L^-1 v  (two blocked substitutions, each reads L exactly once); tmp: N doubles of scratch
-int run_cho_solve_vec(nngp_handle* h, const double* L, int64_t ld, int64_t N, double* v, double* tmp) {
-  const int warps_per_cta = TRSV_THREADS / 32;
-  for (int64_t j0 = 0; j0 < N; j0 += NB) {
-    const int64_t nb = std::min<int64_t>(NB, N - j0);
-    const int64_t rem = N - j0 - nb;
-    int grid = (int)std::min<int64_t>(std::max<int64_t>(1, (rem + warps_per_cta - 1) / warps_per_cta), 4 * h->sm_count);
-    trsv_fwd_step_kernel<<<grid, TRSV_THREADS, 0, h->stream>>>(L, ld, (int)N, (int)j0, (int)nb, v, tmp);
-    h->st.kernel_launches++;
-  }
+// out <- L^-T z  (blocked backward substitution; z is destroyed; reads L exactly once)
+int run_trsv_bwd(nngp_handle* h, const double* L, int64_t ld, int64_t N, double* z, double* out) {
   const int64_t nblk = (N + NB - 1) / NB;
   for (int64_t jb = nblk - 1; jb >= 0; --jb) {
     const int64_t j0 = jb * NB;
     const int64_t nb = std::min<int64_t>(NB, N - j0);
     int grid = (int)std::min<int64_t>(std::max<int64_t>(1, (j0 + TRSV_THREADS - 1) / TRSV_THREADS), 4 * h->sm_count);
-    trsv_bwd_step_kernel<<<grid, TRSV_THREADS, 0, h->stream>>>(L, ld, (int)j0, (int)nb, tmp, v);
+    trsv_bwd_step_kernel<<<grid, TRSV_THREADS, 0, h->stream>>>(L, ld, (int)j0, (int)nb, z, out);
     h->st.kernel_launches++;
   }
   CK(cudaGetLastError());
@@ -469,9 +468,8 @@ int alloc_state(nngp_handle* h, int64_t N, int64_t D) {
   h->ldl = round_up(N, 16);
   CKR(ensure(h, h->X, (size_t)N * h->ldx * sizeof(double)));
   CKR(ensure(h, h->q, (size_t)N * sizeof(double)));
-  CKR(ensure(h, h->L, (size_t)N * h->ldl * sizeof(double)));
+  CKR(ensure(h, h->L, (size_t)(N + 1) * h->ldl * sizeof(double)));  // +1 row: y^T rides through the factorisation
   CKR(ensure(h, h->alpha, (size_t)h->ldl * sizeof(double)));
-  CKR(ensure(h, h->scratch_y, (size_t)h->ldl * sizeof(double)));
   return NNGP_OK;
 }
 
@@ -567,7 +565,7 @@ void nngp_destroy(nngp_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  for (DevBuf* b : {&h->X, &h->q, &h->L, &h->alpha, &h->scratch_y, &h->flags, &h->lam_d, &h->xt, &h->qt, &h->kss,
+  for (DevBuf* b : {&h->X, &h->q, &h->L, &h->alpha, &h->flags, &h->lam_d, &h->xt, &h->qt, &h->kss,
                     &h->blk, &h->mean_d, &h->var_d, &h->ssq, &h->sync_ints, &h->ka, &h->kb, &h->kqa, &h->kqb, &h->kout})
     release(*b);
   for (auto& r : h->pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -663,11 +661,13 @@ int nngp_fit(nngp_handle* h, const double* x_train, const double* y_train, int64
   t_gram.stop();
 
   StageTimer t_chol(h, &h->st.fit_chol_ms);
-  CKR(run_potrf(h, L, h->ldl, N));
+  // y^T goes into row N of the factor buffer: the factorisation turns it into z^T = (L^-1 y)^T
+  CK(cudaMemcpyAsync(L + N * h->ldl, alpha, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  CKR(run_potrf(h, L, h->ldl, N, 1));
   t_chol.stop();
 
   StageTimer t_solve(h, &h->st.fit_solve_ms);
-  CKR(run_cho_solve_vec(h, L, h->ldl, N, alpha, h->scratch_y.as<double>()));
+  CKR(run_trsv_bwd(h, L, h->ldl, N, L + N * h->ldl, alpha));  // alpha = L^-T z
   t_solve.stop();
   t_total.stop();
 
@@ -821,9 +821,10 @@ int nngp_diag_dmma_peak(nngp_handle* h, double* tflops_out) {
   const int iters = 4096;
   const int ctas = h->sm_count * 4;
   cudaEvent_t a = get_event(h), b = get_event(h);
-  dmma_peak_kernel<<<ctas, 256, 0, h->stream>>>(64, h->lam_d.as<double>());  // warm-up
+  for (int w = 0; w < 8; ++w)  // ~35 ms of warm-up so the SM clock is at its loaded value
+    dmma_peak_kernel<<<ctas, 256, 0, h->stream>>>(iters, h->lam_d.as<double>());
   double best = 0.0;
-  for (int rep = 0; rep < 5; ++rep) {
+  for (int rep = 0; rep < 8; ++rep) {
     cudaEventRecord(a, h->stream);
     dmma_peak_kernel<<<ctas, 256, 0, h->stream>>>(iters, h->lam_d.as<double>());
     cudaEventRecord(b, h->stream);
@@ -833,7 +834,7 @@ int nngp_diag_dmma_peak(nngp_handle* h, double* tflops_out) {
     const double flops = (double)ctas * 8 /*warps*/ * (double)iters * 16 * 512.0;
     best = std::max(best, flops / (ms * 1e-3) / 1e12);
   }
-  h->st.kernel_launches += 6;
+  h->st.kernel_launches += 16;
   h->ev_pool.push_back(a); h->ev_pool.push_back(b);
   *tflops_out = best;
   return NNGP_OK;

@@ -3,7 +3,8 @@
 //   diag_reg                      lambda = diag_reg * trace(K)/N ; K += lambda I (K4)
 //   potf2_64                      64x64 diagonal-block Cholesky in shared memory  (K5 panel)
 //   trsm_rows_64                  X L_JJ^T = B, one thread per row                (K5 panel, K10)
-//   trsv_fwd_step / trsv_bwd_step blocked forward / backward substitution         (K6)
+//   trsv_bwd_step                 blocked backward substitution (the forward one rides through
+//                                 the Cholesky as an extra row of the factor buffer)              (K6)
 //   gemv_rows                     mean = K_* alpha, one warp per test row          (K8)
 //   var_rows                      var = K(x,x) - ||V_row||^2, one warp per row     (K10/K11)
 // All reductions have a fixed order: results are bitwise reproducible and independent of how
@@ -230,56 +231,10 @@ __device__ __forceinline__ void load_diag_block(const double* __restrict__ Ljj, 
   if (threadIdx.x < NB) rd[threadIdx.x] = 1.0 / Ls[threadIdx.x][threadIdx.x];
 }
 
-// Forward step of L z = y for diagonal block [j0, j0+n): every CTA solves the 64x64 diagonal system
-// redundantly in its warp 0 (bitwise identical), CTA 0 publishes z_J into zout (a different buffer:
-// other CTAs may still be reading y_J), and all CTAs apply
-// y[r] -= L[r, j0:j0+n] . z_J to their rows r >= j0+n (one warp per row, coalesced 512 B reads).
 constexpr int TRSV_THREADS = 256;
-__global__ void __launch_bounds__(TRSV_THREADS) trsv_fwd_step_kernel(const double* __restrict__ L, long long ld,
-                                                                    int N, int j0, int n,
-                                                                    double* __restrict__ y,
-                                                                    double* __restrict__ zout) {
-  __shared__ double Ls[NB][NB + 1];
-  __shared__ double zs[NB];
-  __shared__ double rd[NB];
-  load_diag_block(L + (long long)j0 * ld + j0, ld, n, Ls, rd);
-  if (threadIdx.x < NB) zs[threadIdx.x] = (threadIdx.x < n) ? y[j0 + threadIdx.x] : 0.0;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    double y0 = zs[lane], y1 = zs[lane + 32];  // lane owns entries lane, lane+32
-    for (int k = 0; k < NB; ++k) {
-      const double num = __shfl_sync(0xffffffffu, (k < 32) ? y0 : y1, k & 31);
-      const double zk = num * rd[k];
-      if (lane == (k & 31)) { if (k < 32) y0 = zk; else y1 = zk; }
-      if (lane > k) y0 = fma(-Ls[lane][k], zk, y0);
-      if (lane + 32 > k) y1 = fma(-Ls[lane + 32][k], zk, y1);
-    }
-    zs[lane] = y0;
-    zs[lane + 32] = y1;
-  }
-  __syncthreads();
-  if (blockIdx.x == 0 && threadIdx.x < n) zout[j0 + threadIdx.x] = zs[threadIdx.x];
-  const int lane = threadIdx.x & 31;
-  const int warps_per_cta = TRSV_THREADS / 32;
-  const double z0 = zs[2 * lane], z1 = zs[2 * lane + 1];
-  for (long long r = (long long)j0 + n + blockIdx.x * warps_per_cta + (threadIdx.x >> 5); r < N;
-       r += (long long)gridDim.x * warps_per_cta) {
-    const double* lr = L + r * ld + j0;
-    double s = 0.0;
-    if (2 * lane + 1 < n) {
-      const double2 v = *reinterpret_cast<const double2*>(lr + 2 * lane);
-      s = fma(v.x, z0, v.y * z1);
-    } else if (2 * lane < n) {
-      s = lr[2 * lane] * z0;
-    }
-    s = warp_sum(s);
-    if (lane == 0) y[r] -= s;
-  }
-}
 
 // Backward step of L^T a = z for diagonal block [j0, j0+n): every CTA solves Ljj^T a_J = z_J
-// redundantly, CTA 0 publishes a_J into aout (not z: see above), and all CTAs apply z[c] -= sum_i L[j0+i][c] a_i to the
+// redundantly, CTA 0 publishes a_J into aout (not into z, which other CTAs may still be reading), and all CTAs apply z[c] -= sum_i L[j0+i][c] a_i to the
 // columns c < j0 (one thread per column, coalesced row reads).
 __global__ void __launch_bounds__(TRSV_THREADS) trsv_bwd_step_kernel(const double* __restrict__ L, long long ld,
                                                                     int j0, int n, double* __restrict__ z,
