@@ -336,6 +336,20 @@ def run_b200(args):
 
 if __name__ == "__main__":
     a = parse_args()
+    # stdout carries exactly ONE line (rank 0's JSON): library banners (e.g. "NCCL version ...") that are
+    # written to fd 1 during the run are diverted to stderr, and fd 1 is restored for the final print.
+    sys.stdout.flush()
+    _saved_fd = os.dup(1)
+    os.dup2(2, 1)
+    _real_print = print
+
+    def print(*args, **kw):  # noqa: A001
+        sys.stdout.flush()
+        os.dup2(_saved_fd, 1)
+        _real_print(*args, **kw)
+        sys.stdout.flush()
+        os.dup2(2, 1)
+
     if a.impl == "reference":
         run_reference(a)
     else:

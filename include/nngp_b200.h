@@ -144,6 +144,12 @@ NNGP_API int nngp_get_state(nngp_handle* h, double* x_out, double* l_out, double
 NNGP_API int nngp_set_state(nngp_handle* h, const double* x, const double* l, const double* alpha, int64_t N,
                    int64_t D, double lambda);
 
+/* Gaussian log marginal likelihood of the fitted model (model selection over depth / W_std / b_std /
+ * diag_reg -- the reference's abandoned hyper-parameter path, train.py:86-103, active/active_train.py:44-49):
+ *   -1/2 y^T (K + lambda I)^-1 y - sum_i log L_ii - N/2 log(2 pi).
+ * Both sums are by-products of nngp_fit (z = L^-1 y rides through the factorisation). */
+NNGP_API int nngp_log_marginal_likelihood(nngp_handle* h, double* lml_out);
+
 NNGP_API int nngp_stats(nngp_handle* h, nngp_stats_t* out);
 NNGP_API int nngp_stats_reset(nngp_handle* h);
 
@@ -157,6 +163,30 @@ NNGP_API int nngp_diag_gemm_probe(nngp_handle* h, int64_t M, int64_t N, int64_t 
 NNGP_API int nngp_diag_potrf(nngp_handle* h, double* a, int64_t N);
 
 NNGP_API int nngp_abi_version(void);
+
+/*
+ * Batch query-line encoder (host C++, multi-threaded) -- scope row f-1.
+ * Replaces the per-line Python loop of Estimator.predict (estimator.py:43-50, "TODO :: parallel encoding")
+ * and produces bit-identical float64 rows to NNGPEncoder.parse_line_without_card_then_encode /
+ * parse_line (neuroestimator/estimator/encoder.py:207-250) and, for single-table workloads, to
+ * GeneralQuerySampler.parse_line + transform_to_1d_array (QuerySampler.py:157-221).
+ * schema_text, one item per line:
+ *     chunk_size <1..64>
+ *     table <name>
+ *     col <name> num <min> <denominator>         (numerical: [ (v-min)/denominator*1000 ] x {upper, lower})
+ *     col <name> cat <number of categories>      (categorical: ceil(n/chunk_size) factorised words)
+ *     join <t1_id> <t2_id> <col_name>            (in the order of NNGPEncoder.all_join_triples)
+ * format: 0 = "t1,t2@preds1@preds2@joins" (neuroestimator/README.md:35-48), 1 = the same + "@card",
+ *         2 = single table "preds@card" (Queries/forest_data).  Lines are '\n'-separated in `blob`.
+ * x_out: n_lines x nngp_encoder_dim(); card_out (formats 1, 2) may be NULL.  n_threads <= 0: all cores.
+ */
+typedef struct nngp_encoder nngp_encoder;
+NNGP_API int nngp_encoder_create(const char* schema_text, nngp_encoder** out);
+NNGP_API void nngp_encoder_destroy(nngp_encoder* enc);
+NNGP_API int nngp_encoder_dim(const nngp_encoder* enc);
+NNGP_API const char* nngp_encoder_last_error(const nngp_encoder* enc);
+NNGP_API int nngp_encode_lines(nngp_encoder* enc, const char* blob, int64_t blob_len, int64_t n_lines,
+                               int32_t format, double* x_out, double* card_out_or_null, int32_t n_threads);
 
 #ifdef __cplusplus
 }

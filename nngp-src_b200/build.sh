@@ -6,5 +6,5 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 out="$here/libnngp_b200.so"
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
   -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -shared -cudart static \
-  "$@" -o "$out" "$here/csrc/capi.cu"
+  "$@" -o "$out" "$here/csrc/capi.cu" "$here/csrc/encoder.cc"
 echo "built $out"

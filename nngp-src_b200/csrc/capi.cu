@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -62,9 +63,11 @@ struct nngp_handle {
   bool fitted = false;
   int64_t N = 0, D = 0, ldx = 0, ldl = 0;
   double lambda = 0.0;
+  double lml_terms[2] = {0.0, 0.0};  // {sum log diag(L), y^T (K+lambda I)^-1 y}; valid after nngp_fit
+  bool have_lml = false;
   DevBuf X, q, L, alpha;
   DevBuf flags;   // int[2]: {potrf info, non-finite input}
-  DevBuf lam_d;   // double[1]
+  DevBuf lam_d;   // double[4]: {lambda, sum log diag L, z^T z, spare}
 
   // predict workspace
   DevBuf xt, qt, kss, blk, mean_d, var_d, ssq, sync_ints;
@@ -460,7 +463,7 @@ int bind_device(nngp_handle* h) {
   return NNGP_OK;
 }
 
-void drop_fit(nngp_handle* h) { h->fitted = false; }
+void drop_fit(nngp_handle* h) { h->fitted = false; h->have_lml = false; }
 
 int alloc_state(nngp_handle* h, int64_t N, int64_t D) {
   h->N = N; h->D = D;
@@ -553,7 +556,7 @@ int nngp_create(const nngp_config* cfg, nngp_handle** out) {
          cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
     return bail(NNGP_ECUDA);
   }
-  if (ensure(h, h->flags, 2 * sizeof(int)) != NNGP_OK || ensure(h, h->lam_d, sizeof(double)) != NNGP_OK)
+  if (ensure(h, h->flags, 2 * sizeof(int)) != NNGP_OK || ensure(h, h->lam_d, 4 * sizeof(double)) != NNGP_OK)
     return bail(NNGP_ENOMEM);
   cudaMemsetAsync(h->flags.p, 0, 2 * sizeof(int), h->stream);
   cudaStreamSynchronize(h->stream);
@@ -667,6 +670,8 @@ int nngp_fit(nngp_handle* h, const double* x_train, const double* y_train, int64
   t_chol.stop();
 
   StageTimer t_solve(h, &h->st.fit_solve_ms);
+  lml_terms_kernel<<<1, 1024, 0, h->stream>>>(L, h->ldl, (int)N, L + N * h->ldl, h->lam_d.as<double>() + 1);
+  h->st.kernel_launches++;
   CKR(run_trsv_bwd(h, L, h->ldl, N, L + N * h->ldl, alpha));  // alpha = L^-T z
   t_solve.stop();
   t_total.stop();
@@ -674,6 +679,7 @@ int nngp_fit(nngp_handle* h, const double* x_train, const double* y_train, int64
   int flags[2];
   CK(cudaMemcpyAsync(flags, h->flags.p, sizeof flags, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(&h->lambda, h->lam_d.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->lml_terms, h->lam_d.as<double>() + 1, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   t_total.collect(); t_h2d.collect(); t_gram.collect(); t_chol.collect(); t_solve.collect();
   flush_class_events(h);
@@ -682,6 +688,7 @@ int nngp_fit(nngp_handle* h, const double* x_train, const double* y_train, int64
     return fail(h, NNGP_ENOTPD, "nngp_fit: K + lambda*I is not positive definite (pivot %d of %lld, lambda=%.6g)",
                 flags[0] - 1, (long long)N, h->lambda);
   h->fitted = true;
+  h->have_lml = true;
   return NNGP_OK;
 }
 
@@ -775,6 +782,15 @@ int nngp_get_dims(nngp_handle* h, int64_t* N, int64_t* D, double* lambda_out) {
   if (N) *N = h->N;
   if (D) *D = h->D;
   if (lambda_out) *lambda_out = h->lambda;
+  return NNGP_OK;
+}
+
+int nngp_log_marginal_likelihood(nngp_handle* h, double* lml_out) {
+  if (!h || !lml_out) return NNGP_EINVAL;
+  if (!h->fitted || !h->have_lml)
+    return fail(h, NNGP_ESTATE, "nngp_log_marginal_likelihood: needs a model fitted by nngp_fit on this handle");
+  const double two_pi = 6.283185307179586476925;
+  *lml_out = -0.5 * h->lml_terms[1] - h->lml_terms[0] - 0.5 * (double)h->N * log(two_pi);
   return NNGP_OK;
 }
 

@@ -338,6 +338,30 @@ __global__ void var_rows_kernel(const double* __restrict__ V, long long ldv, int
   if (lane == 0) var[warp] = kss[warp] - s;
 }
 
+// Single CTA (1024 threads), fixed-order reductions for the log marginal likelihood:
+//   out[0] = sum_i log L[i][i]     out[1] = sum_i z[i]^2  (= y^T (K + lambda I)^-1 y with z = L^-1 y)
+__global__ void lml_terms_kernel(const double* __restrict__ L, long long ld, int N, const double* __restrict__ z,
+                                 double* __restrict__ out) {
+  __shared__ double red[2][32];
+  double s0 = 0.0, s1 = 0.0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    s0 += log(L[(long long)i * ld + i]);
+    const double v = z[i];
+    s1 = fma(v, v, s1);
+  }
+  s0 = warp_sum(s0);
+  s1 = warp_sum(s1);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s0; red[1][threadIdx.x >> 5] = s1; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double a = (threadIdx.x < (blockDim.x >> 5)) ? red[0][threadIdx.x] : 0.0;
+    double b = (threadIdx.x < (blockDim.x >> 5)) ? red[1][threadIdx.x] : 0.0;
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (threadIdx.x == 0) { out[0] = a; out[1] = b; }
+  }
+}
+
 // zero the strict upper triangle of an N x N row-major matrix (state export)
 __global__ void zero_upper_kernel(double* __restrict__ A, long long ld, int N) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -63,11 +63,17 @@ EXPORTS = {
     "nngp_get_dims": (C.c_int, [_P, C.POINTER(_I64), C.POINTER(_I64), _DP]),
     "nngp_get_state": (C.c_int, [_P, _P, _P, _P]),
     "nngp_set_state": (C.c_int, [_P, _P, _P, _P, _I64, _I64, C.c_double]),
+    "nngp_log_marginal_likelihood": (C.c_int, [_P, _DP]),
     "nngp_stats": (C.c_int, [_P, C.POINTER(NngpStats)]),
     "nngp_stats_reset": (C.c_int, [_P]),
     "nngp_diag_dmma_peak": (C.c_int, [_P, _DP]),
     "nngp_diag_gemm_probe": (C.c_int, [_P, _I64, _I64, _I64, C.c_int32, _DP]),
     "nngp_diag_potrf": (C.c_int, [_P, _P, _I64]),
+    "nngp_encoder_create": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
+    "nngp_encoder_destroy": (None, [_P]),
+    "nngp_encoder_dim": (C.c_int, [_P]),
+    "nngp_encoder_last_error": (C.c_char_p, [_P]),
+    "nngp_encode_lines": (C.c_int, [_P, C.c_char_p, _I64, _I64, C.c_int32, _P, _P, C.c_int32]),
 }
 
 _lib = None
@@ -218,6 +224,27 @@ class Handle:
         ap, _ka = _ptr(alpha)
         N, D = kx.shape
         self._ck(self._lib.nngp_set_state(self._h, xp, lp, ap, N, D, float(lam)))
+
+    def log_marginal_likelihood(self) -> float:
+        v = C.c_double()
+        self._ck(self._lib.nngp_log_marginal_likelihood(self._h, C.byref(v)))
+        return v.value
+
+    def save(self, path) -> None:
+        """Fitted state + hyper-parameters -> .npz (the reference has no model file: it refits on every start,
+        neuroestimator/README.md:28-29; its ``load_model`` is a warm-up, estimator.py:37-40)."""
+        st = self.get_state()
+        np.savez(path, x=st["x"], l=st["l"], alpha=st["alpha"], lam=st["lambda"], depth=self.cfg.depth,
+                 sigma_w=self.cfg.sigma_w, sigma_b=self.cfg.sigma_b, diag_reg=self.cfg.diag_reg,
+                 diag_reg_absolute=self.cfg.diag_reg_absolute)
+
+    @classmethod
+    def load(cls, path, **kw) -> "Handle":
+        z = np.load(path)
+        h = cls(depth=int(z["depth"]), sigma_w=float(z["sigma_w"]), sigma_b=float(z["sigma_b"]),
+                diag_reg=float(z["diag_reg"]), diag_reg_absolute=bool(z["diag_reg_absolute"]), **kw)
+        h.set_state(z["x"], z["l"], z["alpha"], float(z["lam"]))
+        return h
 
     def stats(self) -> dict:
         s = NngpStats()

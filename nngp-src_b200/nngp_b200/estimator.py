@@ -48,8 +48,11 @@ class Estimator(object):
         start = datetime.datetime.now()
         if self.nngp_encoder is None:
             raise ValueError("Estimator.predict needs nngp_encoder.parse_line_without_card_then_encode")
-        X_test = np.asarray([self.nngp_encoder.parse_line_without_card_then_encode(line) for line in query_lines],
-                            dtype=np.float64)                                                     # estimator.py:46-50
+        if hasattr(self.nngp_encoder, "encode"):        # nngp_b200.encoder.BatchEncoder: all lines in one C++ call
+            X_test = self.nngp_encoder.encode(query_lines)
+        else:                                           # the reference's per-line loop, estimator.py:46-50
+            X_test = np.asarray([self.nngp_encoder.parse_line_without_card_then_encode(line) for line in query_lines],
+                                dtype=np.float64)
         pred_mean, pred_cov = self._nngp_prediction(X_test)
         duration = (datetime.datetime.now() - start).total_seconds()
         self._say("prediction time={} seconds".format(duration))

@@ -98,6 +98,11 @@ class Fit:
         self.c = sla.cholesky(k, lower=True, overwrite_a=True, check_finite=False)  # [nt: cho_factor]
         self.alpha = sla.cho_solve((self.c, True), self.y, check_finite=False)      # [nt: cho_solve]
 
+    def log_marginal_likelihood(self):
+        """-1/2 y^T (K+lam I)^-1 y - sum log C_ii - N/2 log 2 pi  (standard GP evidence; cf. train.py:86-103)."""
+        n = self.y.shape[0]
+        return float(-0.5 * self.y @ self.alpha - np.sum(np.log(np.diag(self.c))) - 0.5 * n * np.log(2 * np.pi))
+
     def predict(self, x_test, want_var=True, chunk=4096):
         """mean = K_* alpha ; var_i = K(x_i,x_i) - ||C^-1 K_*[i,:]^T||^2 (Appendix A.3, diagonal only)."""
         x_test = np.asarray(x_test, dtype=np.float64)

@@ -202,6 +202,26 @@ def test_state_roundtrip_and_device_pointers(lib, synth):
     assert np.array_equal(md.cpu().numpy(), mean) and np.array_equal(vd.cpu().numpy(), var)
 
 
+def test_log_marginal_likelihood_and_model_file(lib, synth, tmp_path):
+    xtr, ytr, xte, _ = synth.make_problem(900, 200, 24)
+    best = None
+    for depth, sw, sb in [(2, 1.0, 0.0), (3, 1.0, 0.0), (2, 1.5, 0.05)]:
+        h = lib.Handle(depth=depth, sigma_w=sw, sigma_b=sb)
+        h.fit(xtr, ytr)
+        ref = oracle.Fit(xtr, ytr, depth, sw, sb)
+        lml, rl = h.log_marginal_likelihood(), ref.log_marginal_likelihood()
+        assert abs(lml - rl) < 1e-9 * abs(rl)
+        best = max(best or (lml, depth), (lml, depth))
+    assert best is not None
+    h.save(tmp_path / "model.npz")
+    mean, var = h.predict(xte)
+    h2 = lib.Handle.load(tmp_path / "model.npz")
+    m2, v2 = h2.predict(xte)
+    assert np.array_equal(mean, m2) and np.array_equal(var, v2)
+    with pytest.raises(lib.NngpError):
+        h2.log_marginal_likelihood()          # an imported state carries no evidence terms
+
+
 def test_error_conventions(lib, synth):
     h = lib.Handle()
     xtr, ytr, xte, _ = synth.make_problem(64, 8, 8)
