@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define NNGP_B200_ABI_VERSION 1
+#define NNGP_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define NNGP_API __attribute__((visibility("default")))
@@ -54,6 +54,10 @@ typedef enum nngp_status {
  *   nt.predict.gradient_descent_mse_ensemble(..., diag_reg=1e-3)    train.py:171-172,
  *                                        estimator.py:34-35, active/ActiveLearner.py:27-28
  * depth = number of Dense layers (reference: 2) = depth-1 ReLU arc-cosine steps.
+ * kernel_type selects what predict_fn's `get=` selects in the reference (train.py:157-158,254):
+ *   'nngp': K, posterior of the NNGP;   'ntk': Theta, t=infinity NTK ensemble posterior
+ *   mean = Theta_* A^-1 y,  var_i = K_ii + w_i^T K_dd w_i - 2 w_i^T k_i,  w_i = A^-1 theta_i,
+ *   A = Theta_dd + diag_reg*trace(Theta_dd)/N I   [nt 0.6.1 predict.gp_inference, get='ntk'].
  */
 typedef struct nngp_config {
   int32_t depth;              /* >= 1                                                 */
@@ -64,6 +68,7 @@ typedef struct nngp_config {
   int32_t device;             /* CUDA ordinal; -1 = current device                    */
   int64_t max_block_bytes;    /* cap of the test-row block buffer; 0 = default 16 GiB */
   int32_t stats_level;        /* 0 none, 1 per-stage events, 2 per-kernel-class events*/
+  int32_t kernel_type;        /* 0 = 'nngp' (reference default), 1 = 'ntk' (train.py:254)  */
 } nngp_config;
 
 /* Per-stage device timings (CUDA events on the handle's stream) and work counters,

@@ -71,6 +71,8 @@ struct nngp_handle {
 
   // predict workspace
   DevBuf xt, qt, kss, blk, mean_d, var_d, ssq, sync_ints;
+  // NTK mode: M = L^-1 K_dd L^-T (N x N), scratch for building it, second row block, cross / partial terms
+  DevBuf Mmat, Kdd, blk2, cross, partial;
   // nngp_kernel workspace
   DevBuf ka, kb, kqa, kqb, kout;
 
@@ -228,7 +230,7 @@ int launch_gemm(nngp_handle* h, const MatView& A, int a_row0, int a_col0, const 
   dim3 grid((p.N + GEMM_BN - 1) / GEMM_BN, (p.M + GEMM_BM - 1) / GEMM_BM, 1);
   if (grid.y > 65535) return fail(h, NNGP_EINVAL, "internal: GEMM row range too large (%d rows)", p.M);
   cudaEvent_t ev;
-  const int cls = (EPI == EPI_GRAM) ? EV_GRAM : EV_GEMM;
+  const int cls = (EPI == EPI_GRAM) ? EV_GRAM : EV_GEMM;  // ROWDOT counts as a GEMM-class launch
   class_begin(h, cls, &ev);
   gemm_nt_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->cur>>>(tmA, tmB, p);
   class_end(h, cls, ev);
@@ -248,9 +250,12 @@ int launch_gemm(nngp_handle* h, const MatView& A, int a_row0, int a_col0, const 
 }
 
 // K(A rows, B rows) -> out (M x N, ld ldo).  A: M x D (lda), B: N x D (ldb); qa/qb layer-0 diagonals.
+// In NTK mode (cfg.kernel_type == 1) `out` receives Theta and `out2` (optional) the NNGP kernel K.
 int run_gram(nngp_handle* h, const double* A, int64_t lda, int64_t M, const double* qa, const double* B, int64_t ldb,
-             int64_t N, const double* qb, int64_t D, double* out, int64_t ldo, int lower) {
+             int64_t N, const double* qb, int64_t D, double* out, int64_t ldo, int lower, double* out2 = nullptr) {
   GemmParams p{};
+  p.ntk = h->cfg.kernel_type == 1 ? 1 : 0;
+  p.C2 = out2;
   p.M = (int)M; p.N = (int)N;
   p.ktiles = (int)((D + GEMM_BK - 1) / GEMM_BK);
   p.C = out; p.ldc = ldo; p.lower = lower;
@@ -274,6 +279,16 @@ int run_gemm_sub(nngp_handle* h, const MatView& A, int64_t a_row0, int64_t a_col
   p.M = (int)M; p.N = (int)N; p.ktiles = (int)(K / GEMM_BK);
   p.C = C; p.ldc = ldc; p.lower = lower;
   return launch_gemm<EPI_SUB>(h, A, (int)a_row0, (int)a_col0, B, (int)b_row0, (int)b_col0, p);
+}
+
+// partial[tile_n][r] = sum_{c in tile_n} (V M^T)[r][c] * V[r][c]   (V: rows x N at `V`, ldv; M: N x N, ldm == ldv)
+int run_gemm_rowdot(nngp_handle* h, const double* V, int64_t ldv, int64_t rows, const double* Mm, int64_t N,
+                    double* partial) {
+  GemmParams p{};
+  p.M = (int)rows; p.N = (int)N; p.ktiles = (int)((N + GEMM_BK - 1) / GEMM_BK);
+  p.ldc = ldv; p.W = V; p.partial = partial;
+  MatView a{V, rows, N, ldv}, b{Mm, N, N, ldv};
+  return launch_gemm<EPI_ROWDOT>(h, a, 0, 0, b, 0, 0, p);
 }
 
 // ---- blocked Cholesky (lower, in place, row-major) ----------------------------------------------
@@ -494,6 +509,7 @@ void nngp_default_config(nngp_config* cfg) {
   cfg->device = -1;
   cfg->max_block_bytes = 0;
   cfg->stats_level = 1;
+  cfg->kernel_type = 0;
 }
 
 const char* nngp_last_error(const nngp_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -503,6 +519,8 @@ int nngp_create(const nngp_config* cfg, nngp_handle** out) {
   if (!cfg || !out) return fail(h, NNGP_EINVAL, "nngp_create: null argument");
   *out = nullptr;
   if (cfg->depth < 1) return fail(h, NNGP_EINVAL, "nngp_create: depth must be >= 1 (got %d)", cfg->depth);
+  if (cfg->kernel_type != 0 && cfg->kernel_type != 1)
+    return fail(h, NNGP_EINVAL, "nngp_create: kernel_type must be 0 (nngp) or 1 (ntk)");
   if (!(cfg->sigma_w > 0.0) || !(cfg->sigma_b >= 0.0) || !(cfg->diag_reg >= 0.0))
     return fail(h, NNGP_EINVAL, "nngp_create: need sigma_w > 0, sigma_b >= 0, diag_reg >= 0");
   int ndev = 0;
@@ -549,6 +567,7 @@ int nngp_create(const nngp_config* cfg, nngp_handle** out) {
   h->encode = reinterpret_cast<PFN_encodeTiled>(fn);
   cudaError_t e1 = cudaFuncSetAttribute(gemm_nt_kernel<EPI_GRAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
   cudaError_t e2 = cudaFuncSetAttribute(gemm_nt_kernel<EPI_SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+  if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(gemm_nt_kernel<EPI_ROWDOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
   cudaError_t e3 = cudaFuncSetAttribute(trsm_rows_64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM_BYTES);
   if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(trsm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM_BYTES);
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
@@ -569,7 +588,7 @@ void nngp_destroy(nngp_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->X, &h->q, &h->L, &h->alpha, &h->flags, &h->lam_d, &h->xt, &h->qt, &h->kss,
-                    &h->blk, &h->mean_d, &h->var_d, &h->ssq, &h->sync_ints, &h->ka, &h->kb, &h->kqa, &h->kqb, &h->kout})
+                    &h->blk, &h->mean_d, &h->var_d, &h->ssq, &h->sync_ints, &h->Mmat, &h->Kdd, &h->blk2, &h->cross, &h->partial, &h->ka, &h->kb, &h->kqa, &h->kqb, &h->kout})
     release(*b);
   for (auto& r : h->pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : h->ev_pool) cudaEventDestroy(e);
@@ -658,7 +677,14 @@ int nngp_fit(nngp_handle* h, const double* x_train, const double* y_train, int64
   StageTimer t_gram(h, &h->st.fit_gram_ms);
   row_sqnorm_kernel<<<(unsigned)((N * 32 + 255) / 256), 256, 0, h->stream>>>(X, h->ldx, (int)N, (int)D, sw2, sb2, q);
   h->st.kernel_launches++;
-  CKR(run_gram(h, X, h->ldx, N, q, X, h->ldx, N, q, D, L, h->ldl, 1));
+  const bool ntk = h->cfg.kernel_type == 1;
+  if (!ntk) {
+    CKR(run_gram(h, X, h->ldx, N, q, X, h->ldx, N, q, D, L, h->ldl, 1));
+  } else {  // NTK: Theta_dd (to be factored) -> L, the full symmetric K_dd -> Kdd (for M = L^-1 K_dd L^-T)
+    CKR(ensure(h, h->Kdd, (size_t)N * h->ldl * sizeof(double)));
+    CKR(ensure(h, h->Mmat, (size_t)N * h->ldl * sizeof(double)));
+    CKR(run_gram(h, X, h->ldx, N, q, X, h->ldx, N, q, D, L, h->ldl, 0, h->Kdd.as<double>()));
+  }
   diag_reg_kernel<<<1, 1024, 0, h->stream>>>(L, h->ldl, (int)N, h->cfg.diag_reg, h->cfg.diag_reg_absolute, h->lam_d.as<double>());
   h->st.kernel_launches++;
   t_gram.stop();
@@ -673,6 +699,15 @@ int nngp_fit(nngp_handle* h, const double* x_train, const double* y_train, int64
   lml_terms_kernel<<<1, 1024, 0, h->stream>>>(L, h->ldl, (int)N, L + N * h->ldl, h->lam_d.as<double>() + 1);
   h->st.kernel_launches++;
   CKR(run_trsv_bwd(h, L, h->ldl, N, L + N * h->ldl, alpha));  // alpha = L^-T z
+  if (ntk) {  // M = L^-1 K_dd L^-T : two row-wise solves around a transpose (M is symmetric)
+    double* Kd = h->Kdd.as<double>();
+    double* Mm = h->Mmat.as<double>();
+    CKR(run_trsm_fused(h, Kd, h->ldl, N, L, h->ldl, N, nullptr, nullptr));   // Kd <- K_dd L^-T
+    dim3 tg((unsigned)((N + 31) / 32), (unsigned)((N + 31) / 32));
+    transpose_kernel<<<tg, dim3(32, 8), 0, h->stream>>>(Kd, Mm, h->ldl, (int)N);
+    h->st.kernel_launches++;
+    CKR(run_trsm_fused(h, Mm, h->ldl, N, L, h->ldl, N, nullptr, nullptr));   // Mm <- (L^-1 K_dd L^-T)^T = M
+  }
   t_solve.stop();
   t_total.stop();
 
@@ -703,7 +738,8 @@ int nngp_predict(nngp_handle* h, const double* x_test, int64_t T, double* mean_o
 
   // Row-block size: a whole number of full DMMA waves (2 CTAs/SM x 128 rows) that fits the buffer cap.
   const int64_t wave_rows = 2LL * h->sm_count * GEMM_BM;
-  int64_t cap_rows = h->cfg.max_block_bytes / (ldl * 8);
+  const bool ntk = h->cfg.kernel_type == 1;
+  int64_t cap_rows = h->cfg.max_block_bytes / (ldl * 8) / (ntk && var_out ? 2 : 1);  // NTK variance needs two row blocks
   if (cap_rows >= wave_rows) cap_rows = cap_rows / wave_rows * wave_rows;
   cap_rows = std::max<int64_t>(cap_rows, GEMM_BM);
   cap_rows = std::min<int64_t>(cap_rows, 65535LL * GEMM_BM);
@@ -713,6 +749,12 @@ int nngp_predict(nngp_handle* h, const double* x_test, int64_t T, double* mean_o
   CKR(ensure(h, h->qt, (size_t)TB * 8));
   CKR(ensure(h, h->kss, (size_t)TB * 8));
   CKR(ensure(h, h->blk, (size_t)TB * ldl * 8));
+  const int col_tiles = (int)((N + GEMM_BN - 1) / GEMM_BN);
+  if (ntk && var_out) {
+    CKR(ensure(h, h->blk2, (size_t)TB * ldl * 8));
+    CKR(ensure(h, h->cross, (size_t)TB * 8));
+    CKR(ensure(h, h->partial, (size_t)TB * col_tiles * 8));
+  }
   CKR(ensure(h, h->mean_d, (size_t)T * 8));
   if (var_out) CKR(ensure(h, h->var_d, (size_t)T * 8));
   CK(cudaMemsetAsync(h->flags.p, 0, 2 * sizeof(int), h->stream));
@@ -721,7 +763,7 @@ int nngp_predict(nngp_handle* h, const double* x_test, int64_t T, double* mean_o
   double* blk = h->blk.as<double>();
   StageTimer t_total(h, &h->st.pred_total_ms);
   std::vector<StageTimer> timers;
-  timers.reserve(8 * ((T + TB - 1) / TB) + 8);
+  timers.reserve(10 * ((T + TB - 1) / TB) + 8);
   for (int64_t t0 = 0; t0 < T; t0 += TB) {
     const int64_t rows = std::min<int64_t>(TB, T - t0);
     timers.emplace_back(h, &h->st.h2d_ms);
@@ -732,7 +774,8 @@ int nngp_predict(nngp_handle* h, const double* x_test, int64_t T, double* mean_o
     timers.emplace_back(h, &h->st.pred_gram_ms);
     row_sqnorm_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, h->stream>>>(xt, ldx, (int)rows, (int)D, sw2, sb2, h->qt.as<double>());
     h->st.kernel_launches++;
-    CKR(run_gram(h, xt, ldx, rows, h->qt.as<double>(), h->X.as<double>(), ldx, N, h->q.as<double>(), D, blk, ldl, 0));
+    CKR(run_gram(h, xt, ldx, rows, h->qt.as<double>(), h->X.as<double>(), ldx, N, h->q.as<double>(), D, blk, ldl, 0,
+                 (ntk && var_out) ? h->blk2.as<double>() : nullptr));
     timers.back().stop();
 
     timers.emplace_back(h, &h->st.pred_mean_ms);
@@ -743,7 +786,20 @@ int nngp_predict(nngp_handle* h, const double* x_test, int64_t T, double* mean_o
     if (var_out) {
       q_final_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, h->stream>>>(h->qt.as<double>(), (int)rows, h->cfg.depth - 1, sw2, sb2, h->kss.as<double>());
       h->st.kernel_launches++;
-      if (use_fused_trsm()) {
+      if (ntk) {
+        // var_i = K_ii + v_i^T M v_i - 2 v_i . u_i,  v_i = L^-1 theta_i, u_i = L^-1 k_i, M = L^-1 K_dd L^-T
+        double* blk2 = h->blk2.as<double>();
+        timers.emplace_back(h, &h->st.pred_trsm_ms);
+        CKR(run_trsm_fused(h, blk, ldl, rows, h->L.as<double>(), ldl, N, nullptr, nullptr));    // V
+        CKR(run_trsm_fused(h, blk2, ldl, rows, h->L.as<double>(), ldl, N, nullptr, nullptr));   // U
+        timers.back().stop();
+        timers.emplace_back(h, &h->st.pred_var_ms);
+        rowdot_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, h->stream>>>(blk, blk2, ldl, (int)rows, (int)N, h->cross.as<double>());
+        CKR(run_gemm_rowdot(h, blk, ldl, rows, h->Mmat.as<double>(), N, h->partial.as<double>()));
+        ntk_var_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, h->stream>>>(h->kss.as<double>(), h->partial.as<double>(), col_tiles, (int)rows, h->cross.as<double>(), h->var_d.as<double>() + t0);
+        h->st.kernel_launches += 2;
+        timers.back().stop();
+      } else if (use_fused_trsm()) {
         timers.emplace_back(h, &h->st.pred_trsm_ms);   // solve + variance in one persistent kernel
         CKR(run_trsm_fused(h, blk, ldl, rows, h->L.as<double>(), ldl, N, h->kss.as<double>(), h->var_d.as<double>() + t0));
         timers.back().stop();
@@ -797,6 +853,8 @@ int nngp_log_marginal_likelihood(nngp_handle* h, double* lml_out) {
 int nngp_get_state(nngp_handle* h, double* x_out, double* l_out, double* alpha_out) {
   if (!h) return NNGP_EINVAL;
   if (!h->fitted) return fail(h, NNGP_ESTATE, "nngp_get_state: no fitted model");
+  if (h->cfg.kernel_type == 1 && l_out)
+    return fail(h, NNGP_ESTATE, "nngp_get_state: exporting the factor is not supported in 'ntk' mode (the state also holds M)");
   CKR(bind_device(h));
   if (x_out) CKR(download(h, h->X.as<double>(), h->N, h->D, h->ldx, x_out));
   if (l_out) {
@@ -814,6 +872,7 @@ int nngp_set_state(nngp_handle* h, const double* x, const double* l, const doubl
                    double lambda) {
   if (!h) return NNGP_EINVAL;
   if (!x || !l || !alpha || N <= 0 || D <= 0) return fail(h, NNGP_EINVAL, "nngp_set_state: bad argument");
+  if (h->cfg.kernel_type == 1) return fail(h, NNGP_ESTATE, "nngp_set_state: not supported in 'ntk' mode");
   CKR(bind_device(h));
   drop_fit(h);
   CKR(alloc_state(h, N, D));

@@ -362,6 +362,55 @@ __global__ void lml_terms_kernel(const double* __restrict__ L, long long ld, int
   }
 }
 
+// out[r] = sum_j A[r][j] * B[r][j]; one warp per row (NTK cross term  w_i^T k_i = v_i . u_i).
+__global__ void rowdot_kernel(const double* __restrict__ A, const double* __restrict__ B, long long ld, int rows, int N,
+                              double* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const double* a = A + (long long)warp * ld;
+  const double* b = B + (long long)warp * ld;
+  double s0 = 0.0, s1 = 0.0;
+  int j = 2 * lane;
+  for (; j + 65 < N; j += 128) {
+    const double2 a0 = *reinterpret_cast<const double2*>(a + j), b0 = *reinterpret_cast<const double2*>(b + j);
+    const double2 a1 = *reinterpret_cast<const double2*>(a + j + 64), b1 = *reinterpret_cast<const double2*>(b + j + 64);
+    s0 = fma(a0.x, b0.x, s0); s0 = fma(a0.y, b0.y, s0);
+    s1 = fma(a1.x, b1.x, s1); s1 = fma(a1.y, b1.y, s1);
+  }
+  for (; j < N; j += 64) {
+    s0 = fma(a[j], b[j], s0);
+    if (j + 1 < N) s0 = fma(a[j + 1], b[j + 1], s0);
+  }
+  const double s = warp_sum(s0 + s1);
+  if (lane == 0) out[warp] = s;
+}
+
+// NTK posterior variance: var[r] = kss[r] + sum_t partial[t][r] - 2 cross[r]   (tiles summed in index order)
+__global__ void ntk_var_kernel(const double* __restrict__ kss, const double* __restrict__ partial, int tiles, int rows,
+                               const double* __restrict__ cross, double* __restrict__ var) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  double q = 0.0;
+  for (int t = 0; t < tiles; ++t) q += partial[(long long)t * rows + r];
+  var[r] = kss[r] + q - 2.0 * cross[r];
+}
+
+// out = in^T for an n x n row-major matrix (both with leading dimension ld); 32 x 32 smem tiles.
+__global__ void transpose_kernel(const double* __restrict__ in, double* __restrict__ out, long long ld, int n) {
+  __shared__ double tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = by + i, c = bx + threadIdx.x;
+    if (r < n && c < n) tile[i][threadIdx.x] = in[(long long)r * ld + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = bx + i, c = by + threadIdx.x;
+    if (r < n && c < n) out[(long long)r * ld + c] = tile[threadIdx.x][i];
+  }
+}
+
 // zero the strict upper triangle of an N x N row-major matrix (state export)
 __global__ void zero_upper_kernel(double* __restrict__ A, long long ld, int N) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;

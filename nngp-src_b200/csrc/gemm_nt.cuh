@@ -35,7 +35,7 @@ constexpr int GEMM_STAGE_TX_BYTES = GEMM_A_STAGE_BYTES + GEMM_B_STAGE_BYTES;
 constexpr int GEMM_SMEM_BYTES =
     GEMM_STAGES * (GEMM_A_STAGE_BYTES + GEMM_B_STAGE_BYTES) + 2 * GEMM_STAGES * 8 + 1024;
 
-enum GemmEpilogue : int { EPI_GRAM = 0, EPI_SUB = 1 };
+enum GemmEpilogue : int { EPI_GRAM = 0, EPI_SUB = 1, EPI_ROWDOT = 2 };
 
 struct GemmParams {
   int M, N;            // valid output extent (rows of the A range, rows of the B range)
@@ -51,6 +51,11 @@ struct GemmParams {
   double scale;        // sigma_w^2 / D
   double sw2, sb2;     // sigma_w^2, sigma_b^2
   int steps;           // depth-1 arc-cosine steps
+  int ntk;             // 1: C receives the NTK Theta, C2 (if not null) the NNGP kernel K
+  double* C2;
+  // EPI_ROWDOT only: partial[tile_n * M + r] = sum_{c in tile} acc[r][c] * W[r][c]
+  const double* W;     // M x N, leading dimension ldc (reuses ldc)
+  double* partial;
 };
 
 // One ReLU arc-cosine step followed by the next Dense layer's affine map
@@ -71,6 +76,20 @@ __device__ __forceinline__ double arccos_step(double k, double q1, double q2, do
 
 // Consumer side of the operand ring: wait for a stage, run its 4 x (4 x 4) DMMAs on this warp's
 // 32 x 32 tile, release the stage.  `stage` / `phase` persist across calls (persistent kernels).
+// Same step, also advancing the NTK:  ntk' = k' + sw2 * (ntk * kdot),  kdot = 1/2 - theta/(2 pi)
+// ([nt: Relu `ntk *= dot_sigma`, Dense `ntk = nngp + W_std^2 * ntk`]).
+__device__ __forceinline__ void arccos_step_ntk(double& k, double& ntk, double q1, double q2, double sw2, double sb2) {
+  const double inv_2pi = 0.15915494309189533577;
+  const double half_pi = 1.57079632679489661923;
+  double s2 = q1 * q2 - k * k;
+  double s = sqrt(fmax(s2, 0.0));
+  double theta = (s == 0.0 && k == 0.0) ? half_pi : atan2(s, k);
+  double dot_sigma = 0.5 - inv_2pi * theta;
+  double r = inv_2pi * s + dot_sigma * k;
+  k = sw2 * r + sb2;
+  ntk = k + sw2 * (ntk * dot_sigma);
+}
+
 template <int STAGES>
 __device__ __forceinline__ void mma_mainloop(double (&acc)[4][4][2], uint32_t ringA_u32, uint32_t ringB_u32,
                                              uint64_t* full_bar, uint64_t* empty_bar, int& stage, uint32_t& phase,
@@ -229,6 +248,44 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+  } else if constexpr (EPI == EPI_ROWDOT) {
+    // quad[r] contribution of this 64-column tile: sum_c acc[r][c] * W[r][c]  (fixed order => deterministic)
+    double part[4];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+      const int r = row_base + 8 * mi;
+      double sacc = 0.0;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int c = col_base + 8 * ni;
+        double w0 = 0.0, w1 = 0.0;
+        if (r < p.M) {
+          const double* src = p.W + (long long)r * p.ldc + c;
+          if (c + 1 < p.N) {
+            const double2 v = *reinterpret_cast<const double2*>(src);
+            w0 = v.x; w1 = v.y;
+          } else if (c < p.N) {
+            w0 = src[0];
+          }
+        }
+        sacc = fma(acc[mi][ni][0], w0, sacc);
+        sacc = fma(acc[mi][ni][1], w1, sacc);
+      }
+      sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+      sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+      part[mi] = sacc;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(GEMM_CONSUMER_WARPS * 32) : "memory");  // every consumer left the ring
+    double* red = reinterpret_cast<double*>(ringA);                              // [2][128]
+    if (t == 0) {
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) red[wn * GEMM_BM + wm * 32 + mi * 8 + g] = part[mi];
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(GEMM_CONSUMER_WARPS * 32) : "memory");
+    if (threadIdx.x < GEMM_BM) {
+      const int r = tile_m * GEMM_BM + threadIdx.x;
+      if (r < p.M) p.partial[(long long)tile_n * p.M + r] = red[threadIdx.x] + red[GEMM_BM + threadIdx.x];
+    }
   } else {
     double q2v[4][2];
 #pragma unroll
@@ -248,14 +305,31 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         double k0 = p.scale * acc[mi][ni][0] + p.sb2;
         double k1 = p.scale * acc[mi][ni][1] + p.sb2;
         double qa = q1r, qb0 = q2v[ni][0], qb1 = q2v[ni][1];
-        for (int s = 0; s < p.steps; ++s) {
-          k0 = arccos_step(k0, qa, qb0, p.sw2, p.sb2);
-          k1 = arccos_step(k1, qa, qb1, p.sw2, p.sb2);
-          qa = p.sw2 * (0.5 * qa) + p.sb2;
-          qb0 = p.sw2 * (0.5 * qb0) + p.sb2;
-          qb1 = p.sw2 * (0.5 * qb1) + p.sb2;
-        }
         double* dst = p.C + (long long)r * p.ldc + c;
+        if (!p.ntk) {
+          for (int s = 0; s < p.steps; ++s) {
+            k0 = arccos_step(k0, qa, qb0, p.sw2, p.sb2);
+            k1 = arccos_step(k1, qa, qb1, p.sw2, p.sb2);
+            qa = p.sw2 * (0.5 * qa) + p.sb2;
+            qb0 = p.sw2 * (0.5 * qb0) + p.sb2;
+            qb1 = p.sw2 * (0.5 * qb1) + p.sb2;
+          }
+        } else {
+          double n0 = k0, n1 = k1;
+          for (int s = 0; s < p.steps; ++s) {
+            arccos_step_ntk(k0, n0, qa, qb0, p.sw2, p.sb2);
+            arccos_step_ntk(k1, n1, qa, qb1, p.sw2, p.sb2);
+            qa = p.sw2 * (0.5 * qa) + p.sb2;
+            qb0 = p.sw2 * (0.5 * qb0) + p.sb2;
+            qb1 = p.sw2 * (0.5 * qb1) + p.sb2;
+          }
+          if (p.C2) {
+            double* dst2 = p.C2 + (long long)r * p.ldc + c;
+            if (c + 1 < p.N) *reinterpret_cast<double2*>(dst2) = make_double2(k0, k1);
+            else if (c < p.N) dst2[0] = k0;
+          }
+          k0 = n0; k1 = n1;
+        }
         if (c + 1 < p.N) {
           *reinterpret_cast<double2*>(dst) = make_double2(k0, k1);
         } else if (c < p.N) {

@@ -40,7 +40,7 @@ struct TrsmFusedParams {
   int* progress;        // [row_tiles], zeroed before launch
   double* ssq;          // [rows] running sum of squares (not required to be zeroed)
   const double* kss;    // [rows] K(x,x)
-  double* var;          // [rows] output
+  double* var;          // [rows] output; nullptr: plain solve, no variance bookkeeping
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
@@ -198,7 +198,7 @@ trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
         ss = fma(x, x, ss);
       }
       const int grow = row0 + ctid;
-      if (grow < p.rows) {
+      if (p.var != nullptr && grow < p.rows) {
         const double tot = ((J > 0) ? __ldcg(p.ssq + grow) : 0.0) + ss;
         if (J + 1 == p.col_blocks) p.var[grow] = p.kss[grow] - tot;
         else __stcg(p.ssq + grow, tot);

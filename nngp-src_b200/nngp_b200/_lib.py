@@ -28,6 +28,7 @@ class NngpConfig(C.Structure):
         ("device", C.c_int32),
         ("max_block_bytes", C.c_int64),
         ("stats_level", C.c_int32),
+        ("kernel_type", C.c_int32),
     ]
 
 
@@ -134,13 +135,16 @@ class Handle:
     """RAII wrapper of ``nngp_handle*`` (one GPU, not re-entrant)."""
 
     def __init__(self, depth=2, sigma_w=1.0, sigma_b=0.0, diag_reg=1e-3, diag_reg_absolute=False,
-                 device=-1, max_block_bytes=0, stats_level=1):
+                 device=-1, max_block_bytes=0, stats_level=1, kernel_type="nngp"):
         self._lib = load()
         cfg = NngpConfig()
         self._lib.nngp_default_config(C.byref(cfg))
         cfg.depth, cfg.sigma_w, cfg.sigma_b = int(depth), float(sigma_w), float(sigma_b)
         cfg.diag_reg, cfg.diag_reg_absolute = float(diag_reg), int(bool(diag_reg_absolute))
         cfg.device, cfg.max_block_bytes, cfg.stats_level = int(device), int(max_block_bytes), int(stats_level)
+        if kernel_type not in ("nngp", "ntk"):
+            raise NotImplementedError(f"kernel_type {kernel_type!r}: only 'nngp' and 'ntk' exist")
+        cfg.kernel_type = 1 if kernel_type == "ntk" else 0
         self.cfg = cfg
         h = C.c_void_p()
         rc = self._lib.nngp_create(C.byref(cfg), C.byref(h))

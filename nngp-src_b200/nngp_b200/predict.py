@@ -1,4 +1,4 @@
-"""Mirror of ``neural_tangents.predict.gradient_descent_mse_ensemble`` for ``get='nngp'``.
+"""Mirror of ``neural_tangents.predict.gradient_descent_mse_ensemble`` for ``get='nngp'`` / ``get='ntk'``.
 
 Reference call sites: train.py:171-172 + 157-158, neuroestimator/estimator/estimator.py:34-35 + 66-67,
 active/ActiveLearner.py:27-28 + 35-36,44-45.  Semantics kept ([nt 0.6.1] predict.gp_inference):
@@ -71,25 +71,26 @@ def gradient_descent_mse_ensemble(kernel_fn, x_train, y_train, learning_rate=1.0
         raise NotImplementedError("only a single regression output (y_train of shape [N] or [N,1]) is supported")
     if y_shape[0] != x_train.shape[0]:
         raise ValueError(f"x_train has {x_train.shape[0]} rows but y_train has {y_shape[0]}")
-    state = {"handle": None}
+    state = {}                                 # one cached fit per `get`, like nt's lru_cache'd predict_inf
 
-    def _fitted():
-        if state["handle"] is None:
-            h = runtime.new_handle(kernel_fn.spec, diag_reg=diag_reg, diag_reg_absolute=diag_reg_absolute_scale)
+    def _fitted(get="nngp"):
+        if get not in state:
+            h = runtime.new_handle(kernel_fn.spec, diag_reg=diag_reg, diag_reg_absolute=diag_reg_absolute_scale,
+                                   kernel_type=get)
             h.fit(x_train, y_arr)          # raises ValueError / LinAlgError through the C-ABI error codes
-            state["handle"] = h
-        return state["handle"]
+            state[get] = h
+        return state[get]
 
     def predict_fn(t=None, x_test=None, get=None, compute_cov=False, **kwargs):
         if t is not None:
             raise NotImplementedError("predict_fn(t=...): only the infinite-time (t=None) posterior is implemented")
         if kwargs:
             raise NotImplementedError(f"predict_fn: unsupported arguments {sorted(kwargs)}")
-        if get is None or get == "nngp":
-            pass
-        else:
-            raise NotImplementedError(f"predict_fn(get={get!r}): only 'nngp' is implemented")
-        h = _fitted()
+        if get is None:
+            get = "nngp"
+        if get not in ("nngp", "ntk"):
+            raise NotImplementedError(f"predict_fn(get={get!r}): 'nngp' and 'ntk' are implemented (one at a time)")
+        h = _fitted(get)
         xt = x_train if x_test is None else runtime.as_matrix(x_test, "x_test")
         mean, var = h.predict(xt, want_var=bool(compute_cov))
         mean = mean.reshape(-1, 1) if len(y_shape) == 2 else mean

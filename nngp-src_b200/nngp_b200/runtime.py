@@ -28,10 +28,10 @@ def get_device() -> int:
     return _device
 
 
-def new_handle(spec, diag_reg=0.0, diag_reg_absolute=False) -> "_lib.Handle":
+def new_handle(spec, diag_reg=0.0, diag_reg_absolute=False, kernel_type="nngp") -> "_lib.Handle":
     return _lib.Handle(depth=spec.depth, sigma_w=spec.sigma_w, sigma_b=spec.sigma_b, diag_reg=diag_reg,
                        diag_reg_absolute=diag_reg_absolute, device=_device, max_block_bytes=_max_block_bytes,
-                       stats_level=_stats_level)
+                       stats_level=_stats_level, kernel_type=kernel_type)
 
 
 def as_matrix(x, name="x"):

@@ -63,28 +63,27 @@ for _n in ("Conv", "Erf", "Gelu", "ABRelu", "LeakyRelu", "Abs", "Flatten", "AvgP
 
 
 class KernelFn:
-    """``kernel_fn(x1, x2=None, get='nngp')`` -> ndarray[M, N]  (reference: train.py:216, via predict_fn)."""
+    """``kernel_fn(x1, x2=None, get='nngp' | 'ntk')`` -> ndarray[M, N]  (reference: train.py:216, via predict_fn)."""
 
     def __init__(self, spec: KernelSpec):
         self.spec = spec
-        self._handle = None
+        self._handles = {}
 
-    def _engine(self):
-        if self._handle is None:
-            self._handle = runtime.new_handle(self.spec)
-        return self._handle
+    def _engine(self, get="nngp"):
+        if get not in self._handles:
+            self._handles[get] = runtime.new_handle(self.spec, kernel_type=get)
+        return self._handles[get]
 
     def __call__(self, x1, x2=None, get=None, **kwargs):
         if kwargs:
             raise NotImplementedError(f"kernel_fn: unsupported arguments {sorted(kwargs)}")
         if get is None:
             get = "nngp"
-        if get != "nngp":
-            raise NotImplementedError(f"kernel_fn(get={get!r}): only 'nngp' is implemented "
-                                      "('ntk' is the next scope row, see DESIGN.md)")
+        if get not in ("nngp", "ntk"):
+            raise NotImplementedError(f"kernel_fn(get={get!r}): 'nngp' and 'ntk' are implemented (one at a time)")
         x1 = runtime.as_matrix(x1, "x1")
         x2 = None if x2 is None else runtime.as_matrix(x2, "x2")
-        return self._engine().kernel(x1, x2)
+        return self._engine(get).kernel(x1, x2)
 
     def __repr__(self):
         return f"KernelFn({self.spec})"

@@ -52,13 +52,15 @@ def final_diag(q0: np.ndarray, depth: int = 2, sigma_w: float = 1.0, sigma_b: fl
 
 
 def kernel_fn(x1: np.ndarray, x2: np.ndarray | None = None, depth: int = 2, sigma_w: float = 1.0,
-              sigma_b: float = 0.0, chunk: int = 2048) -> np.ndarray:
-    """NNGP kernel K(x1, x2) of a depth-`depth` Dense/ReLU network.
+              sigma_b: float = 0.0, chunk: int = 2048, get: str = "nngp"):
+    """NNGP kernel K(x1, x2) -- or, with get='ntk', the NTK Theta(x1, x2) -- of a depth-`depth` Dense/ReLU
+    network.
 
-    k0 = sigma_w^2 x1.x2^T / D + sigma_b^2, then depth-1 times
-      s = sqrt(max(q1 q2 - k^2, 0)); theta = arctan2(s, k) (pi/2 where s == k == 0)
-      k <- sigma_w^2 ( s/(2 pi) + (1/2 - theta/(2 pi)) k ) + sigma_b^2 ;  q <- sigma_w^2 q/2 + sigma_b^2
-    Row-chunked so the elementwise temporaries stay bounded.
+    k0 = sigma_w^2 x1.x2^T / D + sigma_b^2, theta_ntk0 = k0, then depth-1 times
+      s = sqrt(max(q1 q2 - k^2, 0)); theta = arctan2(s, k) (pi/2 where s == k == 0); kdot = 1/2 - theta/(2 pi)
+      k <- sigma_w^2 ( s/(2 pi) + kdot k ) + sigma_b^2 ;  q <- sigma_w^2 q/2 + sigma_b^2
+      ntk <- k + sigma_w^2 (ntk kdot)                      [nt: Relu `ntk *= dot_sigma`, Dense `ntk = nngp + W_std^2 ntk`]
+    get: 'nngp' | 'ntk' | 'both' (returns (K, Theta)).  Row-chunked so the temporaries stay bounded.
     """
     x1 = np.asarray(x1, dtype=np.float64)
     x2 = x1 if x2 is None else np.asarray(x2, dtype=np.float64)
@@ -66,21 +68,40 @@ def kernel_fn(x1: np.ndarray, x2: np.ndarray | None = None, depth: int = 2, sigm
     sw2, sb2 = sigma_w**2, sigma_b**2
     q1_all, q2 = layer0_diag(x1, sigma_w, sigma_b), layer0_diag(x2, sigma_w, sigma_b)
     out = np.empty((x1.shape[0], x2.shape[0]), dtype=np.float64)
+    out_ntk = np.empty_like(out) if get in ("ntk", "both") else None
     factor = 1.0 / TWO_PI
     for r0 in range(0, x1.shape[0], chunk):
         r1 = min(r0 + chunk, x1.shape[0])
         k = sw2 * ((x1[r0:r1] @ x2.T) / D) + sb2
+        ntk = k.copy() if out_ntk is not None else None
         q1, q2l = q1_all[r0:r1].copy(), q2.copy()
         for _ in range(depth - 1):
             prod = q1[:, None] * q2l[None, :]
             s = np.sqrt(np.maximum(prod - k * k, 0.0))
             theta = np.arctan2(s, k)
             theta[(s == 0.0) & (k == 0.0)] = np.pi / 2
-            k = sw2 * (factor * s + (0.5 - factor * theta) * k) + sb2
+            dot_sigma = 0.5 - factor * theta
+            k = sw2 * (factor * s + dot_sigma * k) + sb2
+            if ntk is not None:
+                ntk = k + sw2 * (ntk * dot_sigma)
             q1 = sw2 * (0.5 * q1) + sb2
             q2l = sw2 * (0.5 * q2l) + sb2
         out[r0:r1] = k
-    return out
+        if out_ntk is not None:
+            out_ntk[r0:r1] = ntk
+    if get == "nngp":
+        return out
+    return out_ntk if get == "ntk" else (out, out_ntk)
+
+
+def final_diag_ntk(q0: np.ndarray, depth: int = 2, sigma_w: float = 1.0, sigma_b: float = 0.0) -> np.ndarray:
+    """Theta(x,x): theta = 0 on the diagonal so kdot = 1/2."""
+    q = np.array(q0, dtype=np.float64, copy=True)
+    ntk = q.copy()
+    for _ in range(depth - 1):
+        q = sigma_w**2 * (0.5 * q) + sigma_b**2
+        ntk = q + sigma_w**2 * (0.5 * ntk)
+    return ntk
 
 
 class Fit:
@@ -142,3 +163,42 @@ def q_error_stats(pred_log2, true_log2):
     qe = 2.0 ** np.abs(np.asarray(pred_log2).reshape(-1) - np.asarray(true_log2).reshape(-1))
     return {"median": float(np.median(qe)), "mean": float(np.mean(qe)), "p95": float(np.quantile(qe, 0.95)),
             "max": float(np.max(qe))}
+
+
+class FitNTK:
+    """predict_fn(get='ntk') of nt.predict.gradient_descent_mse_ensemble at t = infinity (SURVEY.md Appendix A.5;
+    reference flag: train.py:254 `--kernel_type ntk`, consumed at train.py:157-158,178).
+      lambda = diag_reg * trace(Theta_dd)/N ; A = Theta_dd + lambda I = C C^T ; alpha = A^-1 y
+      mean   = Theta_* alpha
+      cov    = K_** + Theta_* A^-1 K_dd A^-1 Theta_*^T - (Theta_* A^-1 K_*^T + transpose)       (diagonal only)
+    """
+
+    def __init__(self, x, y, depth=2, sigma_w=1.0, sigma_b=0.0, diag_reg=1e-3, diag_reg_absolute=False):
+        self.x = np.asarray(x, dtype=np.float64)
+        self.y = np.asarray(y, dtype=np.float64).reshape(-1)
+        self.depth, self.sigma_w, self.sigma_b = depth, sigma_w, sigma_b
+        n = self.x.shape[0]
+        self.k_dd, th = kernel_fn(self.x, None, depth, sigma_w, sigma_b, get="both")
+        reg = max(diag_reg, 0.0)
+        self.lam = reg if diag_reg_absolute else reg * (np.trace(th) / n)
+        th[np.diag_indices(n)] += self.lam
+        self.c = sla.cholesky(th, lower=True, overwrite_a=True, check_finite=False)
+        self.alpha = sla.cho_solve((self.c, True), self.y, check_finite=False)
+
+    def predict(self, x_test, want_var=True, chunk=2048):
+        x_test = np.asarray(x_test, dtype=np.float64)
+        t = x_test.shape[0]
+        mean = np.empty(t)
+        var = np.empty(t) if want_var else None
+        for r0 in range(0, t, chunk):
+            r1 = min(r0 + chunk, t)
+            ks, ths = kernel_fn(x_test[r0:r1], self.x, self.depth, self.sigma_w, self.sigma_b, get="both")
+            mean[r0:r1] = ths @ self.alpha
+            if want_var:
+                w = sla.cho_solve((self.c, True), ths.T, check_finite=False)          # A^-1 Theta_*^T   (N x rows)
+                kss = final_diag(layer0_diag(x_test[r0:r1], self.sigma_w, self.sigma_b), self.depth, self.sigma_w,
+                                 self.sigma_b)
+                quad = np.einsum("ij,ij->j", w, self.k_dd @ w)
+                cross = np.einsum("ij,ji->j", w, ks)
+                var[r0:r1] = kss + quad - 2.0 * cross
+        return mean, var

@@ -55,6 +55,20 @@ def main():
         out[f"{name}/mean"] = np.array([float(v) for v in r["mean"]])
         out[f"{name}/var"] = np.array([float(v) for v in r["var"]])
         print(name, "lam", lam, "mean[0]", out[f"{name}/mean"][0], "var[0]", out[f"{name}/var"][0])
+    # NTK mode (train.py:254 `--kernel_type ntk`)
+    for name, n, t, d, depth, sw, sb, reg in [("ntk_d2", 32, 10, 16, 2, 1.0, 0.0, 1e-3), ("ntk_d3_sigma", 28, 8, 12, 3, 1.5, 0.05, 1e-3)]:
+        xtr, ytr, xte, _ = synth.make_problem(n, t, d, seed_train=21, seed_test=22)
+        xtr[1] = xtr[0]; xte[0] = xtr[0]; xtr[2] = 0.0
+        r = mpo.fit_predict_ntk(xtr.tolist(), ytr.tolist(), xte.tolist(), depth, sw, sb, reg)
+        out[f"{name}/x_train"], out[f"{name}/y_train"], out[f"{name}/x_test"] = xtr, ytr, xte
+        out[f"{name}/cfg"] = np.array([depth, sw, sb, reg, 0.0])
+        out[f"{name}/Theta_dd"] = f64(r["Theta"])
+        out[f"{name}/Theta_td"] = f64(r["Thetas"])
+        out[f"{name}/lam"] = np.array(float(r["lam"]))
+        out[f"{name}/alpha"] = np.array([float(v) for v in r["alpha"]])
+        out[f"{name}/mean"] = np.array([float(v) for v in r["mean"]])
+        out[f"{name}/var"] = np.array([float(v) for v in r["var"]])
+        print(name, "lam", float(r["lam"]), "mean[0]", out[f"{name}/mean"][0], "var[0]", out[f"{name}/var"][0])
     np.savez_compressed(Path(__file__).with_name("mp_small.npz"), **out)
 
 

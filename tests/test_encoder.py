@@ -78,7 +78,7 @@ def test_estimator_uses_the_batch_encoder(encmod, gold, monkeypatch):
         def predict(self, x, want_var=True):
             return self.f.predict(x, want_var)
 
-    monkeypatch.setattr(runtime, "new_handle", lambda spec, diag_reg=0.0, diag_reg_absolute=False: FakeHandle(spec, diag_reg, diag_reg_absolute))
+    monkeypatch.setattr(runtime, "new_handle", lambda spec, diag_reg=0.0, diag_reg_absolute=False, kernel_type="nngp": FakeHandle(spec, diag_reg, diag_reg_absolute))
     enc = encmod.BatchEncoder(str(gold["schema"]))
     y = np.log2(gold["cards"])[:, None]
     est = Estimator("s", "d", "q", X_train=gold["x_train"], Y_train=y, nngp_encoder=enc, verbose=False)

@@ -202,6 +202,53 @@ def test_state_roundtrip_and_device_pointers(lib, synth):
     assert np.array_equal(md.cpu().numpy(), mean) and np.array_equal(vd.cpu().numpy(), var)
 
 
+# ---------------------------------------------------------------------------------------------- NTK mode (row f-2)
+@pytest.mark.parametrize("depth,sw,sb", [(2, 1.0, 0.0), (3, 1.5, 0.05)])
+def test_ntk_kernel_entries(lib, synth, depth, sw, sb):
+    x1, x2 = synth.encodings(400, 24, 3), synth.encodings(300, 24, 4)
+    h = lib.Handle(depth=depth, sigma_w=sw, sigma_b=sb, kernel_type="ntk")
+    # no duplicate rows here: Theta is first-order sensitive to theta at theta = 0 (see tests/test_oracle.py)
+    assert relmax(h.kernel(x1, x2), oracle.kernel_fn(x1, x2, depth, sw, sb, get="ntk")) < 1e-12
+    th = h.kernel(x1)
+    ref = oracle.kernel_fn(x1, None, depth, sw, sb, get="ntk")
+    off = ~np.eye(400, dtype=bool)
+    assert np.max(np.abs(th - ref)[off]) < 1e-12 * np.max(ref)
+    assert np.max(np.abs(np.diag(th) - np.diag(ref))) < 1e-7 * np.max(ref)
+
+
+@pytest.mark.parametrize("case", ["ntk_d2", "ntk_d3_sigma"])
+def test_ntk_against_mpmath_golden(lib, mp_golden, case):
+    g = mp_golden[case]
+    depth, sw, sb, reg, _ = g["cfg"]
+    h = lib.Handle(depth=int(depth), sigma_w=sw, sigma_b=sb, diag_reg=reg, kernel_type="ntk")
+    h.fit(g["x_train"], g["y_train"])
+    assert abs(h.dims()[2] - g["lam"]) < 1e-8 * abs(g["lam"])
+    mean, var = h.predict(g["x_test"])
+    assert np.max(np.abs(mean - g["mean"])) < 1e-7 * np.max(np.abs(g["mean"]))
+    assert np.max(np.abs(var - g["var"])) < 1e-7 * np.max(np.abs(g["var"]))
+
+
+@pytest.mark.parametrize("n,t,d,depth", [(600, 300, 24, 2), (1500, 700, 64, 3)])
+def test_ntk_fit_predict_match_oracle(lib, synth, n, t, d, depth):
+    """train.py --kernel_type ntk: predict_fn(get='ntk', compute_cov=True) -> mean and diag(cov) (Appendix A.5)."""
+    xtr, ytr, xte, _ = synth.make_problem(n, t, d)
+    h = lib.Handle(depth=depth, kernel_type="ntk")
+    h.fit(xtr, ytr)
+    ref = oracle.FitNTK(xtr, ytr, depth)
+    assert abs(h.dims()[2] - ref.lam) < 1e-8 * ref.lam
+    mean, var = h.predict(xte)
+    rm, rv = ref.predict(xte)
+    assert relmax(mean, rm) < 1e-6 and relmax(var, rv) < 1e-6
+    m_only, _ = h.predict(xte, want_var=False)
+    assert np.array_equal(m_only, mean)
+    small = lib.Handle(depth=depth, kernel_type="ntk", max_block_bytes=2 * 128 * ((n + 15) // 16 * 16) * 8)
+    small.fit(xtr, ytr)
+    m2, v2 = small.predict(xte)                      # 128-row blocks: bitwise invariant to the blocking
+    assert np.array_equal(m2, mean) and np.array_equal(v2, var)
+    with pytest.raises(lib.NngpError):
+        h.get_state()                                 # factor export is NNGP-mode only
+
+
 def test_log_marginal_likelihood_and_model_file(lib, synth, tmp_path):
     xtr, ytr, xte, _ = synth.make_problem(900, 200, 24)
     best = None

@@ -13,16 +13,17 @@ class FakeHandle:
     created = 0
     fits = 0
 
-    def __init__(self, spec, diag_reg, absolute):
+    def __init__(self, spec, diag_reg, absolute, kernel_type="nngp"):
         FakeHandle.created += 1
-        self.spec, self.diag_reg, self.absolute, self.fit_ = spec, diag_reg, absolute, None
+        self.spec, self.diag_reg, self.absolute, self.fit_, self.kt = spec, diag_reg, absolute, None, kernel_type
 
     def kernel(self, x1, x2=None):
-        return oracle.kernel_fn(x1, x2, self.spec.depth, self.spec.sigma_w, self.spec.sigma_b)
+        return oracle.kernel_fn(x1, x2, self.spec.depth, self.spec.sigma_w, self.spec.sigma_b, get=self.kt)
 
     def fit(self, x, y):
         FakeHandle.fits += 1
-        self.fit_ = oracle.Fit(x, y, self.spec.depth, self.spec.sigma_w, self.spec.sigma_b, self.diag_reg, self.absolute)
+        cls = oracle.FitNTK if self.kt == "ntk" else oracle.Fit
+        self.fit_ = cls(x, y, self.spec.depth, self.spec.sigma_w, self.spec.sigma_b, self.diag_reg, self.absolute)
 
     def predict(self, x, want_var=True):
         return self.fit_.predict(x, want_var)
@@ -32,7 +33,8 @@ class FakeHandle:
 def fake_engine(monkeypatch):
     FakeHandle.created = FakeHandle.fits = 0
     monkeypatch.setattr(runtime, "new_handle",
-                        lambda spec, diag_reg=0.0, diag_reg_absolute=False: FakeHandle(spec, diag_reg, diag_reg_absolute))
+                        lambda spec, diag_reg=0.0, diag_reg_absolute=False, kernel_type="nngp": FakeHandle(
+                            spec, diag_reg, diag_reg_absolute, kernel_type))
     return FakeHandle
 
 
@@ -60,8 +62,9 @@ def test_kernel_fn_get_semantics(fake_engine):
     x = np.random.default_rng(0).uniform(0, 10, (5, 4))
     assert np.allclose(kernel_fn(x, None, "nngp"), oracle.kernel_fn(x))
     assert kernel_fn(x, x[:2], get="nngp").shape == (5, 2)
+    assert np.allclose(kernel_fn(x, None, "ntk"), oracle.kernel_fn(x, get="ntk"))
     with pytest.raises(NotImplementedError):
-        kernel_fn(x, None, "ntk")
+        kernel_fn(x, None, ("nngp", "ntk"))
     with pytest.raises(ValueError):
         kernel_fn(x[0], None, "nngp")
 
@@ -91,9 +94,15 @@ def test_predict_fn_is_lazy_cached_and_shaped_like_neural_tangents(fake_engine):
     # a new closure is a new fit (ActiveLearner.py:69,76 relies on it)
     predict.gradient_descent_mse_ensemble(kernel_fn, x, y, diag_reg=1e-3)(x_test=xt, get="nngp")
     assert fake_engine.fits == 2
-    for kw in ({"t": 1.0}, {"get": "ntk"}, {"foo": 1}):
+    for kw in ({"t": 1.0}, {"get": ("nngp", "ntk")}, {"foo": 1}):
         with pytest.raises(NotImplementedError):
             predict_fn(x_test=xt, **kw)
+    fits = fake_engine.fits
+    m_ntk, c_ntk = predict_fn(x_test=xt, get="ntk", compute_cov=True)      # train.py:254 --kernel_type ntk
+    predict_fn(x_test=xt, get="ntk", compute_cov=True)
+    assert fake_engine.fits == fits + 1                                    # cached per `get`
+    rn = oracle.FitNTK(x, y)
+    assert np.allclose(m_ntk.ravel(), rn.predict(xt)[0]) and np.allclose(np.diag(c_ntk), rn.predict(xt)[1])
     y1 = y.ravel()
     assert predict.gradient_descent_mse_ensemble(kernel_fn, x, y1, diag_reg=1e-3)(x_test=xt, get="nngp").shape == (7,)
     with pytest.raises(ValueError):

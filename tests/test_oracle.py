@@ -61,6 +61,29 @@ def test_oracle_matches_mpmath_golden(mp_golden, case):
     assert np.max(np.abs(np.diag(cov) - g["var"])) < 1e-8 * np.max(np.abs(g["var"]))
 
 
+@pytest.mark.parametrize("case", ["ntk_d2", "ntk_d3_sigma"])
+def test_ntk_oracle_matches_mpmath_golden(mp_golden, case):
+    g = mp_golden[case]
+    depth, sw, sb, reg, _ = g["cfg"]
+    depth = int(depth)
+    scale = np.max(np.abs(g["Theta_dd"]))
+    # Unlike K (dK/dtheta = 0 at theta = 0), Theta is first-order sensitive to theta through kdot = 1/2 - theta/(2 pi):
+    # for duplicate rows / the diagonal, s = sqrt(q q' - k^2) is sqrt(rounding noise) ~ 1e-8 sqrt(qq') in ANY FP64
+    # evaluation of the nt formula, so entries agree with the 50-digit value to ~1e-9 only there, 1e-14 elsewhere.
+    dth = np.abs(o.kernel_fn(g["x_train"], None, depth, sw, sb, get="ntk") - g["Theta_dd"])
+    assert np.max(dth) < 1e-8 * scale and np.median(dth) < 1e-14 * scale
+    dts = np.abs(o.kernel_fn(g["x_test"], g["x_train"], depth, sw, sb, get="ntk") - g["Theta_td"])
+    assert np.max(dts) < 1e-8 * scale and np.median(dts) < 1e-14 * scale
+    fit = o.FitNTK(g["x_train"], g["y_train"], depth, sw, sb, reg)
+    assert abs(fit.lam - g["lam"]) < 1e-9 * abs(g["lam"])
+    mean, var = fit.predict(g["x_test"])
+    assert np.max(np.abs(mean - g["mean"])) < 1e-8 * np.max(np.abs(g["mean"]))
+    assert np.max(np.abs(var - g["var"])) < 1e-8 * np.max(np.abs(g["var"]))
+    # Theta(x,x) closed form: kdot = 1/2 on the diagonal
+    q0 = o.layer0_diag(g["x_train"], sw, sb)
+    assert np.allclose(np.diag(g["Theta_dd"]), o.final_diag_ntk(q0, depth, sw, sb), rtol=1e-13)   # exact in mpmath
+
+
 def test_finite_width_monte_carlo_conventions():
     """f(x) = v . relu(W x / sqrt(D)) / sqrt(width): covariance -> K; guards /D, W_std=1, no bias."""
     rng = np.random.default_rng(5)
