@@ -6,6 +6,7 @@
 // Work item (r, J) = row tile r (128 test rows) x column block J (64 columns):
 //     acc  = B[r, J] - V[r, 0:64J] * L[J, 0:64J]^T     TMA + DMMA main loop (mma_mainloop)
 //     V[r, J] = acc * L_JJ^-T                           one thread per row, forward substitution in smem
+//                                                       (scratch aliases the drained operand ring)
 //     ssq[row] += |V[row, J]|^2                         (var written with the last column block)
 // Items are claimed in J-major order from a global counter, so a CTA that needs V[r, 0:64J] finds the
 // item (r, J-1) already claimed by a running CTA: it acquire-spins on progress[r] (no deadlock, no
@@ -19,12 +20,14 @@
 
 namespace nngp {
 
-constexpr int TF_STAGES = 3;
-constexpr int TF_RING_BYTES = TF_STAGES * (GEMM_A_STAGE_BYTES + GEMM_B_STAGE_BYTES);  // 72 KiB (>= staging tile)
-constexpr int TF_LS_BYTES = NB * (NB + 1) * 8;
-constexpr int TF_STAGE_TILE_BYTES = GEMM_BM * (NB + 1) * 8;  // 128 x 65 doubles
-static_assert(TF_STAGE_TILE_BYTES <= TF_RING_BYTES, "staging tile must fit in the operand ring");
-constexpr int TF_SMEM_BYTES = TF_RING_BYTES + TF_LS_BYTES + NB * 8 + 2 * TF_STAGES * 8 + 16 + 1024;
+constexpr int TF_STAGES = 4;
+constexpr int TF_RING_BYTES = TF_STAGES * (GEMM_A_STAGE_BYTES + GEMM_B_STAGE_BYTES);  // 96 KiB
+// After the main loop the ring is dead and is reused for the substitution: the 128 x 65 staging tile, the
+// packed lower triangle of L_JJ (row j at j(j+1)/2) and its reciprocal diagonal.
+constexpr int TF_STAGE_TILE_BYTES = GEMM_BM * (NB + 1) * 8;
+constexpr int TF_LP_BYTES = (NB * (NB + 1) / 2) * 8;
+static_assert(TF_STAGE_TILE_BYTES + TF_LP_BYTES + NB * 8 <= TF_RING_BYTES, "substitution scratch must fit in the ring");
+constexpr int TF_SMEM_BYTES = TF_RING_BYTES + 2 * TF_STAGES * 8 + 16 + 1024;
 
 struct TrsmFusedParams {
   double* B;            // rows x N block buffer: K_* on entry, V on exit
@@ -66,9 +69,9 @@ trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
   uint8_t* ringA = ring;
   uint8_t* ringB = ring + TF_STAGES * GEMM_A_STAGE_BYTES;
   double(*Bs)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(ring);  // staging tile aliases the ring
-  double(*Ls)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(ring + TF_RING_BYTES);
-  double* rdiag = reinterpret_cast<double*>(ring + TF_RING_BYTES + TF_LS_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(rdiag + NB);
+  double* Lp = reinterpret_cast<double*>(ring + TF_STAGE_TILE_BYTES);  // packed lower triangle of L_JJ (aliases too)
+  double* rdiag = Lp + NB * (NB + 1) / 2;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + TF_RING_BYTES);
   uint64_t* empty_bar = full_bar + TF_STAGES;
   int* s_item = reinterpret_cast<int*>(empty_bar + TF_STAGES);
 
@@ -148,34 +151,35 @@ trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
         acc[mi][ni][1] = -v1;
       }
     }
-    {  // diagonal block L_JJ -> Ls (identity padded), 8 loads in flight per thread
-      const double* Ljj = p.L + (long long)col0 * p.ldl + col0;
-      const int c = ctid & 63, rsub = ctid >> 6;
-      for (int r0 = 0; r0 < NB; r0 += 32) {
-        double tv[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int rr = r0 + 4 * u + rsub;
-          tv[u] = (rr < nb && c <= rr) ? Ljj[(long long)rr * p.ldl + c] : ((rr == c) ? 1.0 : 0.0);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) Ls[r0 + 4 * u + rsub][c] = tv[u];
-      }
-    }
-
     mma_mainloop<TF_STAGES>(acc, smem_u32(ringA), smem_u32(ringB), full_bar, empty_bar, stage, phase, ktiles, wm, wn,
                             lane);
 
-    bar_sync_consumers();  // every consumer has left the ring; Ls is complete
-    if (ctid < NB) rdiag[ctid] = 1.0 / Ls[ctid][ctid];
+    bar_sync_consumers();  // every consumer has left the ring: it becomes substitution scratch
+    {
+      // diagonal block L_JJ (identity padded) -> registers first, so the global latency overlaps the smem writes
+      const double* Ljj = p.L + (long long)col0 * p.ldl + col0;
+      const int c = ctid & 63, rsub = ctid >> 6;
+      double tv[16];
 #pragma unroll
-    for (int mi = 0; mi < 4; ++mi) {
-      const int lr = wm * 32 + mi * 8 + g;
+      for (int u = 0; u < 16; ++u) {
+        const int rr = 4 * u + rsub;
+        tv[u] = (rr < nb && c <= rr) ? Ljj[(long long)rr * p.ldl + c] : ((rr == c) ? 1.0 : 0.0);
+      }
 #pragma unroll
-      for (int ni = 0; ni < 4; ++ni) {
-        const int lc = wn * 32 + ni * 8 + 2 * t;
-        Bs[lr][lc] = -acc[mi][ni][0];
-        Bs[lr][lc + 1] = -acc[mi][ni][1];
+      for (int mi = 0; mi < 4; ++mi) {
+        const int lr = wm * 32 + mi * 8 + g;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+          const int lc = wn * 32 + ni * 8 + 2 * t;
+          Bs[lr][lc] = -acc[mi][ni][0];
+          Bs[lr][lc + 1] = -acc[mi][ni][1];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int rr = 4 * u + rsub;
+        if (c <= rr) Lp[rr * (rr + 1) / 2 + c] = tv[u];
+        if (c == rr) rdiag[rr] = 1.0 / tv[u];
       }
     }
     bar_sync_consumers();
@@ -184,7 +188,7 @@ trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
       double ss = 0.0;
       for (int j = 0; j < nb; ++j) {
         double s0 = xr[j], s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        const double* lj = Ls[j];
+        const double* lj = Lp + j * (j + 1) / 2;
         int k = 0;
         for (; k + 3 < j; k += 4) {
           s0 = fma(-xr[k], lj[k], s0);
