@@ -428,6 +428,43 @@ int run_trsm_fused(nngp_handle* h, double* B, int64_t ldb, int64_t rows, const d
   return NNGP_OK;
 }
 
+// Small-batch variant of the same solve (identical arithmetic, see solve_row_left_packed): right-looking over the
+// column blocks, so every step exposes (N - j)/64 column tiles of parallelism even when there is a single row
+// tile -- the persistent left-looking kernel would walk the N/64 blocks of a row tile sequentially on one SM.
+// Used when the block has few row tiles (serving a handful of queries, the forest workload).
+int run_trsm_right(nngp_handle* h, double* B, int64_t ldb, int64_t rows, const double* L, int64_t ldl, int64_t N,
+                   const double* kss, double* var) {
+  MatView Bv{B, rows, N, ldb}, Lv{L, N, N, ldl};
+  const int col_blocks = (int)((N + NB - 1) / NB);
+  const int grid = (int)((rows + 127) / 128);
+  if (var) CKR(ensure(h, h->ssq, (size_t)rows * sizeof(double)));
+  for (int J = 0; J < col_blocks; ++J) {
+    const int64_t j0 = (int64_t)J * NB;
+    const int64_t nb = std::min<int64_t>(NB, N - j0);
+    trsm_rows_var_kernel<<<grid, 256, TRSMV_SMEM_BYTES, h->stream>>>(B + j0, ldb, (int)rows, L + j0 * ldl + j0, ldl, (int)nb, J,
+                                                                    col_blocks, h->ssq.as<double>(), kss, var);
+    h->st.kernel_launches++;
+    const int64_t j1 = j0 + nb;
+    if (j1 < N)  // B[:, j1:] -= V[:, J] * L[j1:, J]^T
+      CKR(run_gemm_sub(h, Bv, 0, j0, Lv, j1, j0, rows, N - j1, nb, B + j1, ldb, 0));
+  }
+  CK(cudaGetLastError());
+  return NNGP_OK;
+}
+
+int small_batch_row_tiles() {  // read on every call so tests / A-B runs can flip it inside one process
+  const char* e = getenv("NNGP_SMALL_BATCH_TILES");
+  return e ? atoi(e) : 64;
+}
+
+// V = K_* L^-T (+ variance): persistent fused kernel for large blocks, right-looking steps for small ones.
+int run_predict_solve(nngp_handle* h, double* B, int64_t ldb, int64_t rows, const double* L, int64_t ldl, int64_t N,
+                      const double* kss, double* var) {
+  const int64_t row_tiles = (rows + GEMM_BM - 1) / GEMM_BM;
+  if (row_tiles <= small_batch_row_tiles()) return run_trsm_right(h, B, ldb, rows, L, ldl, N, kss, var);
+  return run_trsm_fused(h, B, ldb, rows, L, ldl, N, kss, var);
+}
+
 bool use_fused_trsm() {
   static int v = [] { const char* e = getenv("NNGP_PREDICT_TRSM"); return (e && !strcmp(e, "steps")) ? 0 : 1; }();
   return v != 0;
@@ -570,6 +607,7 @@ int nngp_create(const nngp_config* cfg, nngp_handle** out) {
   if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(gemm_nt_kernel<EPI_ROWDOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
   cudaError_t e3 = cudaFuncSetAttribute(trsm_rows_64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM_BYTES);
   if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(trsm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM_BYTES);
+  if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(trsm_rows_var_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSMV_SMEM_BYTES);
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
     fail(h, NNGP_ECUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s",
          cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
@@ -702,11 +740,11 @@ int nngp_fit(nngp_handle* h, const double* x_train, const double* y_train, int64
   if (ntk) {  // M = L^-1 K_dd L^-T : two row-wise solves around a transpose (M is symmetric)
     double* Kd = h->Kdd.as<double>();
     double* Mm = h->Mmat.as<double>();
-    CKR(run_trsm_fused(h, Kd, h->ldl, N, L, h->ldl, N, nullptr, nullptr));   // Kd <- K_dd L^-T
+    CKR(run_predict_solve(h, Kd, h->ldl, N, L, h->ldl, N, nullptr, nullptr));   // Kd <- K_dd L^-T
     dim3 tg((unsigned)((N + 31) / 32), (unsigned)((N + 31) / 32));
     transpose_kernel<<<tg, dim3(32, 8), 0, h->stream>>>(Kd, Mm, h->ldl, (int)N);
     h->st.kernel_launches++;
-    CKR(run_trsm_fused(h, Mm, h->ldl, N, L, h->ldl, N, nullptr, nullptr));   // Mm <- (L^-1 K_dd L^-T)^T = M
+    CKR(run_predict_solve(h, Mm, h->ldl, N, L, h->ldl, N, nullptr, nullptr));   // Mm <- (L^-1 K_dd L^-T)^T = M
   }
   t_solve.stop();
   t_total.stop();
@@ -790,8 +828,8 @@ int nngp_predict(nngp_handle* h, const double* x_test, int64_t T, double* mean_o
         // var_i = K_ii + v_i^T M v_i - 2 v_i . u_i,  v_i = L^-1 theta_i, u_i = L^-1 k_i, M = L^-1 K_dd L^-T
         double* blk2 = h->blk2.as<double>();
         timers.emplace_back(h, &h->st.pred_trsm_ms);
-        CKR(run_trsm_fused(h, blk, ldl, rows, h->L.as<double>(), ldl, N, nullptr, nullptr));    // V
-        CKR(run_trsm_fused(h, blk2, ldl, rows, h->L.as<double>(), ldl, N, nullptr, nullptr));   // U
+        CKR(run_predict_solve(h, blk, ldl, rows, h->L.as<double>(), ldl, N, nullptr, nullptr));    // V
+        CKR(run_predict_solve(h, blk2, ldl, rows, h->L.as<double>(), ldl, N, nullptr, nullptr));   // U
         timers.back().stop();
         timers.emplace_back(h, &h->st.pred_var_ms);
         rowdot_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, h->stream>>>(blk, blk2, ldl, (int)rows, (int)N, h->cross.as<double>());
@@ -801,7 +839,7 @@ int nngp_predict(nngp_handle* h, const double* x_test, int64_t T, double* mean_o
         timers.back().stop();
       } else if (use_fused_trsm()) {
         timers.emplace_back(h, &h->st.pred_trsm_ms);   // solve + variance in one persistent kernel
-        CKR(run_trsm_fused(h, blk, ldl, rows, h->L.as<double>(), ldl, N, h->kss.as<double>(), h->var_d.as<double>() + t0));
+        CKR(run_predict_solve(h, blk, ldl, rows, h->L.as<double>(), ldl, N, h->kss.as<double>(), h->var_d.as<double>() + t0));
         timers.back().stop();
       } else {
         timers.emplace_back(h, &h->st.pred_trsm_ms);

@@ -184,23 +184,7 @@ trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
     }
     bar_sync_consumers();
     if (ctid < GEMM_BM) {
-      double* xr = Bs[ctid];
-      double ss = 0.0;
-      for (int j = 0; j < nb; ++j) {
-        double s0 = xr[j], s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        const double* lj = Lp + j * (j + 1) / 2;
-        int k = 0;
-        for (; k + 3 < j; k += 4) {
-          s0 = fma(-xr[k], lj[k], s0);
-          s1 = fma(-xr[k + 1], lj[k + 1], s1);
-          s2 = fma(-xr[k + 2], lj[k + 2], s2);
-          s3 = fma(-xr[k + 3], lj[k + 3], s3);
-        }
-        for (; k < j; ++k) s0 = fma(-xr[k], lj[k], s0);
-        const double x = ((s0 + s1) + (s2 + s3)) * rdiag[j];
-        xr[j] = x;
-        ss = fma(x, x, ss);
-      }
+      const double ss = solve_row_left_packed(Bs[ctid], Lp, rdiag, nb);
       const int grow = row0 + ctid;
       if (p.var != nullptr && grow < p.rows) {
         const double tot = ((J > 0) ? __ldcg(p.ssq + grow) : 0.0) + ss;

@@ -155,6 +155,23 @@ def test_row_blocking_and_sharding_are_bitwise_invariant(lib, synth):
     assert np.array_equal(np.concatenate([p[1] for p in parts]), var)
 
 
+def test_small_batch_and_persistent_solve_paths_agree_bitwise(lib, synth, monkeypatch):
+    """The right-looking small-batch path and the persistent fused kernel share their arithmetic: same bits."""
+    xtr, ytr, xte, _ = synth.make_problem(1100, 700, 20)
+    h = lib.Handle()
+    h.fit(xtr, ytr)
+    monkeypatch.setenv("NNGP_SMALL_BATCH_TILES", "0")          # force the persistent fused kernel
+    m_f, v_f = h.predict(xte)
+    monkeypatch.setenv("NNGP_SMALL_BATCH_TILES", "1000000")    # force the right-looking steps
+    m_s, v_s = h.predict(xte)
+    assert np.array_equal(m_f, m_s) and np.array_equal(v_f, v_s)
+    one_f = h.predict(xte[:1])                                  # single query (the PostgreSQL serving case)
+    assert one_f[0][0] == m_f[0] and one_f[1][0] == v_f[0]
+    ref = oracle.Fit(xtr, ytr)
+    rm, rv = ref.predict(xte)
+    assert relmax(m_s, rm) < 1e-6 and relmax(v_s, rv) < 1e-6
+
+
 def test_full_size_properties_c2(lib, synth):
     """BASELINE config C2 sizes (N=8192, D=128, depth 2): size-independent properties + sampled oracle check."""
     xtr, ytr, xte, _ = synth.make_problem(8192, 8192, 128)
