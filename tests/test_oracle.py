@@ -123,3 +123,41 @@ def test_active_selection_rule():
     std = np.array([0.4, 0.1, 0.9, 0.2])
     assert list(o.active_select(mean, std, 2)) == [0, 2]
     assert sorted(o.active_select(mean, std, 10)) == [0, 1, 2, 3]
+
+
+def test_device_atan2_algorithm_in_numpy():
+    """The Gram epilogue's atan2_pos (csrc/gemm_nt.cuh) restated in numpy with the SAME coefficients (parsed from
+    the source): <= 1 ulp-level agreement with libm and with 40-digit mpmath, incl. the axes and the origin."""
+    import re
+    from pathlib import Path
+    import mpmath as mp
+    src = (Path(__file__).resolve().parents[1] / "nngp-src_b200" / "csrc" / "gemm_nt.cuh").read_text()
+    body = src[src.index("constexpr double C[21] = {"):]
+    body = body[:body.index("};")]
+    coef = [float(v) for v in re.findall(r"-?\d+\.\d+(?:e-?\d+)?", body.split("{", 1)[1])]
+    assert len(coef) == 21 and coef[0] == 1.0
+
+    def atan2_pos(s, k):
+        a = np.abs(k)
+        mx, mn = np.maximum(s, a), np.minimum(s, a)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            t = mn / mx
+        u = t * t
+        p = np.full_like(u, coef[20])
+        for c in coef[19::-1]:
+            p = p * u + c
+        at = t * p
+        th0 = np.where(s > a, np.pi / 2 - at, at)
+        th = np.where(k < 0, np.pi - th0, th0)
+        return np.where(mx == 0, np.pi / 2, th)
+
+    rng = np.random.default_rng(1)
+    s = np.abs(rng.standard_normal(200000)) * 10 ** rng.uniform(-12, 3, 200000)
+    k = rng.standard_normal(200000) * 10 ** rng.uniform(-12, 3, 200000)
+    s[:500] = 0.0; k[500:1000] = 0.0; s[1000] = k[1000] = 0.0; k[1001:1500] = s[1001:1500]
+    ref = np.arctan2(s, k)
+    ref[(s == 0) & (k == 0)] = np.pi / 2
+    assert np.max(np.abs(atan2_pos(s, k) - ref)) <= 4.5e-16
+    mp.mp.dps = 40
+    hi = np.array([float(mp.atan2(mp.mpf(float(a)), mp.mpf(float(b)))) for a, b in zip(s[2000:4000], k[2000:4000])])
+    assert np.max(np.abs(atan2_pos(s[2000:4000], k[2000:4000]) - hi)) <= 4.5e-16
