@@ -314,7 +314,7 @@ int potrf_panel(nngp_handle* h, double* A, int64_t ld, int64_t N, int64_t R, int
   MatView Av{A, R, N, ld};
   for (int64_t s0 = j0; s0 < j0 + w; s0 += NB) {
     const int64_t nb = std::min<int64_t>(NB, N - s0);
-    if (s0 > j0)  // A[s0:N, s0:s0+nb] -= A[s0:N, j0:s0] * A[s0:s0+nb, j0:s0]^T
+    if (s0 > j0)  // A[s0:R, s0:s0+nb] -= A[s0:R, j0:s0] * A[s0:s0+nb, j0:s0]^T
       CKR(run_gemm_sub(h, Av, s0, j0, Av, s0, j0, R - s0, nb, s0 - j0, A + s0 * ld + s0, ld, 0));
     potf2_64_kernel<<<1, 256, 0, h->cur>>>(A + s0 * ld + s0, ld, (int)nb, (int)s0, info);
     h->st.kernel_launches++;
@@ -329,9 +329,14 @@ int potrf_panel(nngp_handle* h, double* A, int64_t ld, int64_t N, int64_t R, int
   return NNGP_OK;
 }
 
-// Look-ahead schedule: the trailing update of outer step j is split into (A) the columns of the NEXT
-// panel and (B) the rest; as soon as (A) is done the next panel is factored on a high-priority stream
-// while (B) keeps the tensor pipes busy on the main stream.
+// Blocked right-looking Cholesky.  The trailing update of outer step j is split into (A) the columns of the NEXT
+// panel and (B) the rest.
+// Optional look-ahead (NNGP_CHOL_LOOKAHEAD=1, OFF by default): as soon as (A) is done the next panel is factored on
+// a high-priority stream while (B) keeps the tensor pipes busy on the main stream (-6 % fit time at N = 32768,
+// -30 % at N = 8192).  It is off by default because overlapping the two streams was observed to corrupt results
+// on this B200 pool (about one fit in ten at N = 8192) although the streams touch disjoint column ranges and the
+// identical two-stream schedule WITHOUT overlap (NNGP_LA_MODE=2) is bit-stable; the findings are written up in
+// DESIGN.md section 5.3 and reproducible with tools/determinism_check.py.
 // `extra` rows stored below the matrix (rows N..N+extra-1, N columns each) are carried through every
 // panel solve and trailing update: on exit they hold  E L^-T.  The fit puts y^T there, so the forward
 // substitution z = L^-1 y of the alpha solve costs nothing extra (one more row in GEMMs already running).
@@ -340,42 +345,39 @@ int run_potrf(nngp_handle* h, double* A, int64_t ld, int64_t N, int64_t extra = 
   const int64_t R = N + extra;
   MatView Av{A, R, N, ld};
   const bool lookahead = h->panel_stream != nullptr && N > 2 * W;
+  static const int la_mode = [] { const char* e = getenv("NNGP_LA_MODE"); return e ? atoi(e) : 1; }();
   cudaEvent_t ev_cols = get_event(h), ev_panel = get_event(h);
+  auto edge = [&](cudaEvent_t e, cudaStream_t from, cudaStream_t to) -> cudaError_t {
+    cudaError_t r = cudaEventRecord(e, from);
+    if (r == cudaSuccess) r = cudaStreamWaitEvent(to, e, 0);
+    return r;
+  };
   int rc = NNGP_OK;
-  if (lookahead) {  // the panel stream starts after everything queued on the main stream so far
-    cudaEventRecord(ev_cols, h->stream);
-    cudaStreamWaitEvent(h->panel_stream, ev_cols, 0);
-  }
-  for (int64_t j0 = 0; j0 < N && rc == NNGP_OK; j0 += W) {
+  cudaError_t ce = cudaSuccess;
+  if (lookahead) ce = edge(ev_cols, h->stream, h->panel_stream);  // panel stream starts after the work queued so far
+  for (int64_t j0 = 0; j0 < N && rc == NNGP_OK && ce == cudaSuccess; j0 += W) {
     const int64_t w = std::min<int64_t>(W, N - j0);
     const int64_t t0 = j0 + w;
     h->cur = lookahead ? h->panel_stream : h->stream;
     rc = potrf_panel(h, A, ld, N, R, j0, w);
     if (rc != NNGP_OK || t0 >= N) break;
-    if (lookahead) {
-      cudaEventRecord(ev_panel, h->panel_stream);
-      cudaStreamWaitEvent(h->stream, ev_panel, 0);
-    }
+    if (lookahead) ce = edge(ev_panel, h->panel_stream, h->stream);
     h->cur = h->stream;
     const int64_t w2 = std::min<int64_t>(W, N - t0);
     const int64_t t1 = t0 + w2;
-    // (A) next panel's columns: A[t0:N, t0:t1] (lower tiles) -= A[t0:N, j0:t0] * A[t0:t1, j0:t0]^T
+    // (A) next panel's columns: A[t0:R, t0:t1] (lower tiles) -= A[t0:R, j0:t0] * A[t0:t1, j0:t0]^T
     rc = run_gemm_sub(h, Av, t0, j0, Av, t0, j0, R - t0, w2, w, A + t0 * ld + t0, ld, 1);
     if (rc != NNGP_OK) break;
-    if (lookahead) {
-      cudaEventRecord(ev_cols, h->stream);
-      cudaStreamWaitEvent(h->panel_stream, ev_cols, 0);
-    }
-    // (B) the rest of the trailing matrix: A[t1:N, t1:N] (lower) -= A[t1:N, j0:t0] * A[t1:N, j0:t0]^T
+    if (lookahead && la_mode != 2 && ce == cudaSuccess) ce = edge(ev_cols, h->stream, h->panel_stream);
+    // (B) the rest of the trailing matrix: A[t1:R, t1:N] (lower) -= A[t1:R, j0:t0] * A[t1:N, j0:t0]^T
     if (t1 < N) rc = run_gemm_sub(h, Av, t1, j0, Av, t1, j0, R - t1, N - t1, w, A + t1 * ld + t1, ld, 1);
+    if (lookahead && la_mode == 2 && ce == cudaSuccess) ce = edge(ev_cols, h->stream, h->panel_stream);  // no overlap
   }
-  if (lookahead) {  // join: the main stream continues only after the last panel
-    cudaEventRecord(ev_panel, h->panel_stream);
-    cudaStreamWaitEvent(h->stream, ev_panel, 0);
-  }
+  if (lookahead && ce == cudaSuccess) ce = edge(ev_panel, h->panel_stream, h->stream);  // join
   h->cur = h->stream;
   h->ev_pool.push_back(ev_cols);
   h->ev_pool.push_back(ev_panel);
+  if (ce != cudaSuccess) rc = fail(h, NNGP_ECUDA, "look-ahead event plumbing failed: %s", cudaGetErrorString(ce));
   CKR(rc);
   CK(cudaGetLastError());
   return NNGP_OK;
@@ -591,8 +593,10 @@ int nngp_create(const nngp_config* cfg, nngp_handle** out) {
     return bail(NNGP_ECUDA);
   }
   h->cur = h->stream;
-  if (const char* e = getenv("NNGP_CHOL_LOOKAHEAD")) {
-    if (!strcmp(e, "0")) { cudaStreamDestroy(h->panel_stream); h->panel_stream = nullptr; }
+  // Look-ahead is opt-in (see run_potrf): without NNGP_CHOL_LOOKAHEAD=1 the panel stream is not kept.
+  {
+    const char* e = getenv("NNGP_CHOL_LOOKAHEAD");
+    if (!(e && !strcmp(e, "1"))) { cudaStreamDestroy(h->panel_stream); h->panel_stream = nullptr; }
   }
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -989,12 +993,18 @@ int nngp_diag_potrf(nngp_handle* h, double* a, int64_t N) {
   if (!h || !a || N <= 0) return NNGP_EINVAL;
   CKR(bind_device(h));
   const int64_t ld = round_up(N, 16);
+  const int64_t extra = getenv("NNGP_DIAG_EXTRA") ? 1 : 0;  // debug: carry a row of ones like nngp_fit carries y^T
   DevBuf A;
-  CKR(ensure(h, A, (size_t)N * ld * 8));
+  CKR(ensure(h, A, (size_t)(N + extra) * ld * 8));
   int rc = NNGP_OK;
   cudaMemsetAsync(h->flags.p, 0, 2 * sizeof(int), h->stream);
   rc = upload_matrix(h, a, N, N, A.as<double>(), ld);
-  if (rc == NNGP_OK) rc = run_potrf(h, A.as<double>(), ld, N);
+  if (rc == NNGP_OK && extra) {
+    std::vector<double> ones(N, 1.0);
+    cudaMemcpyAsync(A.as<double>() + N * ld, ones.data(), N * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    cudaStreamSynchronize(h->stream);
+  }
+  if (rc == NNGP_OK) rc = run_potrf(h, A.as<double>(), ld, N, extra);
   if (rc == NNGP_OK) rc = download(h, A.as<double>(), N, N, ld, a);
   int flags[2] = {0, 0};
   cudaMemcpyAsync(flags, h->flags.p, sizeof flags, cudaMemcpyDeviceToHost, h->stream);

@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) potf2_64_kernel(double* __restrict__ A, l
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       const int r = ty * 4 + a, c = tx * 4 + b;
-      v[a][b] = (r < n && c <= r) ? A[(long long)r * ld + c] : ((r == c) ? 1.0 : 0.0);
+      v[a][b] = (r < n && c <= r) ? __ldcg(A + (long long)r * ld + c) : ((r == c) ? 1.0 : 0.0);
     }
   bool bad = false;
   for (int j = 0; j < n; ++j) {
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(TRSM_ROWS) trsm_rows_64_kernel(double* __restr
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int r = r0 + 2 * u + rsub;
-      t[u] = (r < n && c <= r) ? Ljj[(long long)r * ldl + c] : ((r == c) ? 1.0 : 0.0);
+      t[u] = (r < n && c <= r) ? __ldcg(Ljj + (long long)r * ldl + c) : ((r == c) ? 1.0 : 0.0);
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) Lt[c * (NB + 2) + r0 + 2 * u + rsub] = t[u];   // Lt[c][r] = L[r][c]
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(TRSM_ROWS) trsm_rows_64_kernel(double* __restr
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int r = r0 + 2 * u + rsub;
-      t[u] = (row0 + r < rows && c < n) ? B[(long long)(row0 + r) * ldb + c] : 0.0;
+      t[u] = (row0 + r < rows && c < n) ? __ldcg(B + (long long)(row0 + r) * ldb + c) : 0.0;
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) Bs[r0 + 2 * u + rsub][c] = t[u];

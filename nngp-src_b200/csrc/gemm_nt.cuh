@@ -4,11 +4,13 @@
 //                                                                         K contiguous)
 //
 //   * operands: TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B, box 16 doubles x {128|64} rows)
-//     into a 4-stage shared-memory ring, full/empty mbarriers, one dedicated producer warp;
-//   * math: 8 consumer warps (4 along M x 2 along N), each a 32 x 32 warp tile = 4 x 4
+//     into a 4-stage shared-memory ring with full/empty mbarriers; thread 0 is the producer: it
+//     refills a stage right after all 8 warps have released it (prefetch distance 3 k-tiles);
+//   * math: 8 warps (4 along M x 2 along N), each a 32 x 32 warp tile = 4 x 4
 //     mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4) accumulators, 64 FP64 registers per thread;
-//   * 288 threads, ~97 KB smem -> 2 CTAs per SM, so one CTA's epilogue hides under the
-//     other's main loop;
+//   * 256 threads x <= 128 registers, ~97 KB smem -> 2 CTAs per SM, so one CTA's epilogue hides
+//     under the other's main loop, and no local memory (a 9-warp variant with a dedicated producer
+//     warp was capped at 96 registers and spilled its output pointers to the stack);
 //   * epilogues: (GRAM) the NNGP arc-cosine recursion of SURVEY Appendix A.1 applied in
 //     registers -- intermediate layer kernels never touch HBM -- or (SUB) C -= acc, the
 //     trailing/left-looking update of the blocked Cholesky and triangular solves.
@@ -27,7 +29,7 @@ constexpr int GEMM_BN = 64;
 constexpr int GEMM_BK = 16;
 constexpr int GEMM_STAGES = 4;
 constexpr int GEMM_CONSUMER_WARPS = 8;
-constexpr int GEMM_THREADS = (GEMM_CONSUMER_WARPS + 1) * 32;
+constexpr int GEMM_THREADS = GEMM_CONSUMER_WARPS * 32;  // no dedicated producer warp: thread 0 issues the TMA loads
 constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * GEMM_BK * 8;  // 16 KiB
 constexpr int GEMM_B_STAGE_BYTES = GEMM_BN * GEMM_BK * 8;  //  8 KiB
 constexpr int GEMM_STAGE_TX_BYTES = GEMM_A_STAGE_BYTES + GEMM_B_STAGE_BYTES;
@@ -116,8 +118,6 @@ __device__ __forceinline__ double arccos_step(double k, double q1, double q2, do
 }
 
 
-// Consumer side of the operand ring: wait for a stage, run its 4 x (4 x 4) DMMAs on this warp's
-// 32 x 32 tile, release the stage.  `stage` / `phase` persist across calls (persistent kernels).
 // Same step, also advancing the NTK:  ntk' = k' + sw2 * (ntk * kdot),  kdot = 1/2 - theta/(2 pi)
 // ([nt: Relu `ntk *= dot_sigma`, Dense `ntk = nngp + W_std^2 * ntk`]).
 __device__ __forceinline__ void arccos_step_ntk(double& k, double& ntk, double q1, double q2, double sw2, double sb2) {
@@ -131,8 +131,37 @@ __device__ __forceinline__ void arccos_step_ntk(double& k, double& ntk, double q
   ntk = k + sw2 * (ntk * dot_sigma);
 }
 
+// Operand ring, producer and consumer in one loop.  Every warp: wait for a stage, run its 4 x (4 x 4) DMMAs on
+// the warp's 32 x 32 tile, release the stage.  Thread 0 additionally re-arms the stage it has just finished with
+// k-tile kt + STAGES once all 8 warps have released it.  `stage` / `phase` persist across calls (persistent kernels).
+struct TileSrc {  // where the A / B operand tiles of this output tile come from
+  const CUtensorMap* tmA;
+  const CUtensorMap* tmB;
+  int a_col0, a_row, b_col0, b_row;
+};
+
 template <int STAGES>
-__device__ __forceinline__ void mma_mainloop(double (&acc)[4][4][2], uint32_t ringA_u32, uint32_t ringB_u32,
+__device__ __forceinline__ void ring_issue(const TileSrc& src, uint8_t* ringA, uint8_t* ringB, uint64_t* full_bar,
+                                           int stage, int kt) {
+  mbar_arrive_expect_tx(&full_bar[stage], GEMM_STAGE_TX_BYTES);
+  tma_load_2d(ringA + stage * GEMM_A_STAGE_BYTES, src.tmA, src.a_col0 + kt * GEMM_BK, src.a_row, &full_bar[stage]);
+  tma_load_2d(ringB + stage * GEMM_B_STAGE_BYTES, src.tmB, src.b_col0 + kt * GEMM_BK, src.b_row, &full_bar[stage]);
+}
+
+// Thread 0 only: start the first min(STAGES, ktiles) loads of a tile.  The stages are free: the previous tile's
+// refills stopped at its last k-tile and every warp has passed the barrier that ends a tile.
+template <int STAGES>
+__device__ __forceinline__ void ring_prologue(const TileSrc& src, uint8_t* ringA, uint8_t* ringB, uint64_t* full_bar,
+                                              int stage, int ktiles) {
+  const int n = ktiles < STAGES ? ktiles : STAGES;
+  for (int i = 0; i < n; ++i) {
+    ring_issue<STAGES>(src, ringA, ringB, full_bar, stage, i);
+    if (++stage == STAGES) stage = 0;
+  }
+}
+
+template <int STAGES>
+__device__ __forceinline__ void mma_mainloop(double (&acc)[4][4][2], const TileSrc& src, uint8_t* ringA, uint8_t* ringB,
                                              uint64_t* full_bar, uint64_t* empty_bar, int& stage, uint32_t& phase,
                                              int ktiles, int wm, int wn, int lane) {
   const int g = lane >> 2, t = lane & 3;
@@ -140,8 +169,8 @@ __device__ __forceinline__ void mma_mainloop(double (&acc)[4][4][2], uint32_t ri
   uint32_t koff[4];
 #pragma unroll
   for (int k4 = 0; k4 < 4; ++k4) koff[k4] = ((uint32_t)((2 * k4 + (t >> 1)) ^ g) << 4) | ((uint32_t)(t & 1) << 3);
-  const uint32_t a_warp = ringA_u32 + (uint32_t)(wm * 32 + g) * 128u;
-  const uint32_t b_warp = ringB_u32 + (uint32_t)(wn * 32 + g) * 128u;
+  const uint32_t a_warp = smem_u32(ringA) + (uint32_t)(wm * 32 + g) * 128u;
+  const uint32_t b_warp = smem_u32(ringB) + (uint32_t)(wn * 32 + g) * 128u;
   for (int kt = 0; kt < ktiles; ++kt) {
     mbar_wait(&full_bar[stage], phase);
     const uint32_t a_st = a_warp + stage * GEMM_A_STAGE_BYTES;
@@ -160,27 +189,20 @@ __device__ __forceinline__ void mma_mainloop(double (&acc)[4][4][2], uint32_t ri
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[stage]);
+    if (threadIdx.x == 0 && kt + STAGES < ktiles) {
+      mbar_wait(&empty_bar[stage], phase);  // all 8 warps are done with this stage in this round
+      ring_issue<STAGES>(src, ringA, ringB, full_bar, stage, kt + STAGES);
+    }
+    __syncwarp();
     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
   }
 }
 
-// Producer side: one elected lane streams `ktiles` A/B stages through the ring.
-template <int STAGES>
-__device__ __forceinline__ void tma_producer(const CUtensorMap* tmA, const CUtensorMap* tmB, uint8_t* ringA,
-                                             uint8_t* ringB, uint64_t* full_bar, uint64_t* empty_bar, int& stage,
-                                             uint32_t& phase, int ktiles, int a_col0, int a_row, int b_col0,
-                                             int b_row) {
-  for (int kt = 0; kt < ktiles; ++kt) {
-    mbar_wait(&empty_bar[stage], phase ^ 1u);  // first pass over the ring falls through
-    mbar_arrive_expect_tx(&full_bar[stage], GEMM_STAGE_TX_BYTES);
-    tma_load_2d(ringA + stage * GEMM_A_STAGE_BYTES, tmA, a_col0 + kt * GEMM_BK, a_row, &full_bar[stage]);
-    tma_load_2d(ringB + stage * GEMM_B_STAGE_BYTES, tmB, b_col0 + kt * GEMM_BK, b_row, &full_bar[stage]);
-    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-  }
-}
-
+#ifndef NNGP_GEMM_MINBLOCKS
+#define NNGP_GEMM_MINBLOCKS 2
+#endif
 template <int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 2)
+__global__ void __launch_bounds__(GEMM_THREADS, NNGP_GEMM_MINBLOCKS)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmParams p) {
   const int tile_n = blockIdx.x;
@@ -211,23 +233,16 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
 
   const int ktiles = p.ktiles;
-
-  if (warp == GEMM_CONSUMER_WARPS) {
-    // ===== TMA producer (one elected lane) =====
-    if (lane == 0) {
-      tma_prefetch_desc(&tmA);
-      tma_prefetch_desc(&tmB);
-      const int arow = p.a_row0 + tile_m * GEMM_BM;
-      const int brow = p.b_row0 + tile_n * GEMM_BN;
-      int stage = 0;
-      uint32_t phase = 0;
-      tma_producer<GEMM_STAGES>(&tmA, &tmB, ringA, ringB, full_bar, empty_bar, stage, phase, ktiles, p.a_col0, arow,
-                                p.b_col0, brow);
-    }
-    return;
+  TileSrc src;
+  src.tmA = &tmA; src.tmB = &tmB;
+  src.a_col0 = p.a_col0; src.a_row = p.a_row0 + tile_m * GEMM_BM;
+  src.b_col0 = p.b_col0; src.b_row = p.b_row0 + tile_n * GEMM_BN;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    ring_prologue<GEMM_STAGES>(src, ringA, ringB, full_bar, 0, ktiles);  // overlaps the C / q loads below
   }
 
-  // ===== consumers =====
   const int wm = warp >> 1;  // 0..3 : 32-row slab
   const int wn = warp & 1;   // 0..1 : 32-col slab
   const int g = lane >> 2;   // fragment row / col group
@@ -250,10 +265,10 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (r < p.M) {
           const double* src = p.C + (long long)r * p.ldc + c;
           if (c + 1 < p.N) {
-            const double2 v = *reinterpret_cast<const double2*>(src);
-            v0 = v.x; v1 = v.y;
+            const double2 v = __ldcg(reinterpret_cast<const double2*>(src));  // L2 only: C is produced by other kernels,
+            v0 = v.x; v1 = v.y;                                                 // possibly on another stream
           } else if (c < p.N) {
-            v0 = src[0];
+            v0 = __ldcg(src);
           }
         }
         acc[mi][ni][0] = -v0;
@@ -269,18 +284,21 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   int stage = 0;
   uint32_t phase = 0;
-  mma_mainloop<GEMM_STAGES>(acc, smem_u32(ringA), smem_u32(ringB), full_bar, empty_bar, stage, phase, ktiles, wm, wn,
-                            lane);
+  mma_mainloop<GEMM_STAGES>(acc, src, ringA, ringB, full_bar, empty_bar, stage, phase, ktiles, wm, wn, lane);
 
   // ===== epilogue (registers -> global) =====
+  // The tile coordinates are laundered through an empty asm so that the compiler re-derives the output addresses
+  // here instead of keeping the prologue's pointers alive (in registers or spilled) across the main loop.
+  int row_base_e = row_base, col_base_e = col_base;
+  asm volatile("" : "+r"(row_base_e), "+r"(col_base_e));
   if constexpr (EPI == EPI_SUB) {
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi) {
-      const int r = row_base + 8 * mi;
+      const int r = row_base_e + 8 * mi;
       if (r >= p.M) continue;
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
-        const int c = col_base + 8 * ni;
+        const int c = col_base_e + 8 * ni;
         double* dst = p.C + (long long)r * p.ldc + c;
         if (c + 1 < p.N) {
           *reinterpret_cast<double2*>(dst) = make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
@@ -294,11 +312,11 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     double part[4];
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi) {
-      const int r = row_base + 8 * mi;
+      const int r = row_base_e + 8 * mi;
       double sacc = 0.0;
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
-        const int c = col_base + 8 * ni;
+        const int c = col_base_e + 8 * ni;
         double w0 = 0.0, w1 = 0.0;
         if (r < p.M) {
           const double* src = p.W + (long long)r * p.ldc + c;
@@ -316,36 +334,31 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
       part[mi] = sacc;
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(GEMM_CONSUMER_WARPS * 32) : "memory");  // every consumer left the ring
+    __syncthreads();  // every warp has left the ring
     double* red = reinterpret_cast<double*>(ringA);                              // [2][128]
     if (t == 0) {
 #pragma unroll
       for (int mi = 0; mi < 4; ++mi) red[wn * GEMM_BM + wm * 32 + mi * 8 + g] = part[mi];
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(GEMM_CONSUMER_WARPS * 32) : "memory");
+    __syncthreads();
     if (threadIdx.x < GEMM_BM) {
       const int r = tile_m * GEMM_BM + threadIdx.x;
       if (r < p.M) p.partial[(long long)tile_n * p.M + r] = red[threadIdx.x] + red[GEMM_BM + threadIdx.x];
     }
   } else {
-    double q2v[4][2];
-#pragma unroll
-    for (int ni = 0; ni < 4; ++ni) {
-      const int c = col_base + 8 * ni;
-      q2v[ni][0] = (c < p.N) ? p.q2[c] : 0.0;
-      q2v[ni][1] = (c + 1 < p.N) ? p.q2[c + 1] : 0.0;
-    }
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi) {
-      const int r = row_base + 8 * mi;
+      const int r = row_base_e + 8 * mi;
       if (r >= p.M) continue;
       const double q1r = p.q1[r];
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
-        const int c = col_base + 8 * ni;
+        const int c = col_base_e + 8 * ni;
         double k0 = p.scale * acc[mi][ni][0] + p.sb2;
         double k1 = p.scale * acc[mi][ni][1] + p.sb2;
-        double qa = q1r, qb0 = q2v[ni][0], qb1 = q2v[ni][1];
+        double qa = q1r;
+        double qb0 = (c < p.N) ? __ldg(p.q2 + c) : 0.0;          // re-read per fragment (L1 hit): keeps 16 registers free
+        double qb1 = (c + 1 < p.N) ? __ldg(p.q2 + c + 1) : 0.0;
         double* dst = p.C + (long long)r * p.ldc + c;
         if (!p.ntk) {
           for (int s = 0; s < p.steps; ++s) {

@@ -55,9 +55,6 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-__device__ __forceinline__ void bar_sync_consumers() {
-  asm volatile("bar.sync 1, %0;" ::"n"(GEMM_CONSUMER_WARPS * 32) : "memory");
-}
 
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmL,
@@ -77,28 +74,29 @@ trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
+  const int tid = threadIdx.x;
+  if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < TF_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], GEMM_CONSUMER_WARPS);
     }
     fence_mbar_init();
-  }
-  if (warp == GEMM_CONSUMER_WARPS && lane == 0) {
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmL);
   }
 
   const int total = p.row_tiles * p.col_blocks;
-  int stage = 0;        // ring position: advances identically in the producer and in every consumer
+  int stage = 0;        // ring position: advances identically in every thread
   uint32_t phase = 0;
+  const int wm = warp >> 1, wn = warp & 1;
+  const int g = lane >> 2, t = lane & 3;
 
   int next_static = blockIdx.x;
   for (;;) {
-    if (threadIdx.x == 0) *s_item = p.static_sched ? next_static : atomicAdd(p.counter, 1);
+    if (tid == 0) *s_item = p.static_sched ? next_static : atomicAdd(p.counter, 1);
     next_static += gridDim.x;
-    __syncthreads();  // publishes the item; also: nobody still uses the ring / staging tile of the last item
+    __syncthreads();  // publishes the item; also: nobody still uses the ring / the scratch of the last item
     const int item = *s_item;
     if (item >= total) break;
     const int J = item / p.row_tiles;
@@ -108,28 +106,17 @@ trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
     const int nb = min(NB, p.N - col0);
     const int row0 = r * GEMM_BM;
 
-    if (warp == GEMM_CONSUMER_WARPS) {
-      // ===== TMA producer =====
-      if (lane == 0) {
-        if (J > 0) {
-          while (ld_acquire_gpu(p.progress + r) < J) __nanosleep(64);
-          fence_proxy_async_all();  // V written through the generic proxy by other CTAs -> read by TMA
-        }
-        tma_producer<TF_STAGES>(&tmB, &tmL, ringA, ringB, full_bar, empty_bar, stage, phase, ktiles, 0, row0, 0, col0);
-      } else {
-        for (int kt = 0; kt < ktiles; ++kt)
-          if (++stage == TF_STAGES) { stage = 0; phase ^= 1u; }
+    TileSrc src;
+    src.tmA = &tmB; src.tmB = &tmL;
+    src.a_col0 = 0; src.a_row = row0; src.b_col0 = 0; src.b_row = col0;
+    if (tid == 0) {
+      if (J > 0) {
+        while (ld_acquire_gpu(p.progress + r) < J) __nanosleep(64);
+        fence_proxy_async_all();  // V was written through the generic proxy by other CTAs -> read by TMA
       }
-      stage = __shfl_sync(0xffffffffu, stage, 0);
-      phase = __shfl_sync(0xffffffffu, phase, 0);
-      __syncthreads();  // end-of-item rendezvous with the consumers' (E) barrier below
-      continue;
+      ring_prologue<TF_STAGES>(src, ringA, ringB, full_bar, stage, ktiles);
     }
 
-    // ===== consumers =====
-    const int ctid = threadIdx.x;  // 0..255
-    const int wm = warp >> 1, wn = warp & 1;
-    const int g = lane >> 2, t = lane & 3;
     double acc[4][4][2];
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi) {
@@ -139,31 +126,31 @@ trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
         const int lc = wn * 32 + ni * 8 + 2 * t;
         double v0 = 0.0, v1 = 0.0;
         if (row0 + lr < p.rows) {
-          const double* src = p.B + (long long)(row0 + lr) * p.ldb + col0 + lc;
+          const double* src_c = p.B + (long long)(row0 + lr) * p.ldb + col0 + lc;
           if (lc + 1 < nb) {
-            const double2 v = *reinterpret_cast<const double2*>(src);
+            const double2 v = __ldcg(reinterpret_cast<const double2*>(src_c));
             v0 = v.x; v1 = v.y;
           } else if (lc < nb) {
-            v0 = src[0];
+            v0 = __ldcg(src_c);
           }
         }
         acc[mi][ni][0] = -v0;
         acc[mi][ni][1] = -v1;
       }
     }
-    mma_mainloop<TF_STAGES>(acc, smem_u32(ringA), smem_u32(ringB), full_bar, empty_bar, stage, phase, ktiles, wm, wn,
-                            lane);
 
-    bar_sync_consumers();  // every consumer has left the ring: it becomes substitution scratch
+    mma_mainloop<TF_STAGES>(acc, src, ringA, ringB, full_bar, empty_bar, stage, phase, ktiles, wm, wn, lane);
+
+    __syncthreads();  // every warp has left the ring: it becomes substitution scratch
     {
       // diagonal block L_JJ (identity padded) -> registers first, so the global latency overlaps the smem writes
       const double* Ljj = p.L + (long long)col0 * p.ldl + col0;
-      const int c = ctid & 63, rsub = ctid >> 6;
+      const int c = tid & 63, rsub = tid >> 6;
       double tv[16];
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
         const int rr = 4 * u + rsub;
-        tv[u] = (rr < nb && c <= rr) ? Ljj[(long long)rr * p.ldl + c] : ((rr == c) ? 1.0 : 0.0);
+        tv[u] = (rr < nb && c <= rr) ? __ldcg(Ljj + (long long)rr * p.ldl + c) : ((rr == c) ? 1.0 : 0.0);
       }
 #pragma unroll
       for (int mi = 0; mi < 4; ++mi) {
@@ -182,19 +169,19 @@ trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
         if (c == rr) rdiag[rr] = 1.0 / tv[u];
       }
     }
-    bar_sync_consumers();
-    if (ctid < GEMM_BM) {
-      const double ss = solve_row_left_packed(Bs[ctid], Lp, rdiag, nb);
-      const int grow = row0 + ctid;
+    __syncthreads();
+    if (tid < GEMM_BM) {
+      const double ss = solve_row_left_packed(Bs[tid], Lp, rdiag, nb);
+      const int grow = row0 + tid;
       if (p.var != nullptr && grow < p.rows) {
         const double tot = ((J > 0) ? __ldcg(p.ssq + grow) : 0.0) + ss;
         if (J + 1 == p.col_blocks) p.var[grow] = p.kss[grow] - tot;
         else __stcg(p.ssq + grow, tot);
       }
     }
-    bar_sync_consumers();
+    __syncthreads();
     {
-      const int c = ctid & 63, rsub = ctid >> 6;
+      const int c = tid & 63, rsub = tid >> 6;
       if (c < nb) {
 #pragma unroll 4
         for (int r0 = 0; r0 < GEMM_BM; r0 += 4) {
@@ -205,9 +192,8 @@ trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
     }
     fence_proxy_async_all();
     __threadfence();
-    bar_sync_consumers();
-    if (ctid == 0) st_release_gpu(p.progress + r, J + 1);
-    __syncthreads();  // (E) end-of-item rendezvous with the producer warp
+    __syncthreads();
+    if (tid == 0) st_release_gpu(p.progress + r, J + 1);
   }
 }
 

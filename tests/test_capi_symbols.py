@@ -49,3 +49,19 @@ def test_no_cpu_fallback_without_gpu(lib):
     with pytest.raises(Exception) as ei:
         lib.Handle()
     assert "no CUDA device" in str(ei.value) or "error" in str(ei.value).lower()
+
+
+def test_no_kernel_uses_local_memory(lib):
+    """Every kernel must be spill-free (STACK:0, LOCAL:0) and the DMMA kernels must fit 2 CTAs per SM."""
+    import shutil
+    import subprocess
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    out = subprocess.run([tool, "--dump-resource-usage", str(lib.LIB_PATH)], capture_output=True, text=True).stdout
+    funcs = re.findall(r"Function (\S+):\s*\n?\s*REG:(\d+) STACK:(\d+) SHARED:\d+ LOCAL:(\d+)", out)
+    assert len(funcs) >= 15, out[:400]
+    bad = [(f, st, lo) for f, _r, st, lo in funcs if int(st) or int(lo)]
+    assert not bad, f"kernels using local memory: {bad}"
+    regs = {f: int(r) for f, r, _s, _l in funcs}
+    for f, r in regs.items():
+        if "gemm_nt_kernel" in f or "trsm_fused_kernel" in f:
+            assert r <= 128, (f, r)        # 2 CTAs x 256 threads x 128 registers = one SM's register file

@@ -172,6 +172,22 @@ def test_small_batch_and_persistent_solve_paths_agree_bitwise(lib, synth, monkey
     assert relmax(m_s, rm) < 1e-6 and relmax(v_s, rv) < 1e-6
 
 
+def test_repeated_fits_are_bit_identical(lib, synth):
+    """Race detector of last resort (compute-sanitizer is closed on this pool): the same fit + predict, repeated on
+    three alternating handles, must give identical bits (this is what exposed the look-ahead corruption)."""
+    xtr, ytr, xte, _ = synth.make_problem(4096, 1024, 64)
+    handles = [lib.Handle() for _ in range(3)]
+    ref = None
+    for rep in range(9):
+        h = handles[rep % 3]
+        h.fit(xtr, np.ones_like(ytr))
+        cur = (h.get_state(x=False, l=False)["alpha"],) + tuple(h.predict(xte))
+        if ref is None:
+            ref = cur
+        else:
+            assert all(np.array_equal(a, b) for a, b in zip(cur, ref)), f"fit #{rep} differs from fit #0"
+
+
 def test_full_size_properties_c2(lib, synth):
     """BASELINE config C2 sizes (N=8192, D=128, depth 2): size-independent properties + sampled oracle check."""
     xtr, ytr, xte, _ = synth.make_problem(8192, 8192, 128)
