@@ -302,6 +302,23 @@ def test_log_marginal_likelihood_and_model_file(lib, synth, tmp_path):
         h2.log_marginal_likelihood()          # an imported state carries no evidence terms
 
 
+def test_active_learning_round_selects_the_oracle_rows(lib, synth):
+    """Config C4 on the real engine: one round of active/ActiveLearner.py:43-77 (deterministic top-k branch)."""
+    from nngp_b200 import stax
+    from nngp_b200.active import ActiveLearner
+    xtr, ytr, xpool, ypool = synth.make_problem(400, 900, 16)
+    _, _, kernel_fn = stax.serial(stax.Dense(512), stax.Relu(), stax.Dense(1))
+    al = ActiveLearner(budget=100, active_iters=1, verbose=False)
+    pf = al.train(kernel_fn, xtr, ytr[:, None])
+    idx = al.active_test(pf, xpool)
+    ref = oracle.Fit(xtr, ytr)
+    rm, rv = ref.predict(xpool)
+    want = oracle.active_select(rm[:, None], np.sqrt(rv), 100)
+    assert set(idx.tolist()) == set(want.tolist())
+    pf2, x_end, y_end = al.active_train(kernel_fn, xtr, ytr[:, None], xpool, ypool[:, None], xpool[:50], ypool[:50, None])
+    assert x_end.shape == (500, 16) and len(al.history) == 2
+
+
 def test_error_conventions(lib, synth):
     h = lib.Handle()
     xtr, ytr, xte, _ = synth.make_problem(64, 8, 8)
