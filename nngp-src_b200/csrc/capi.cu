@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -27,6 +28,16 @@ using namespace nngp;
 namespace {
 
 thread_local std::string g_create_error;
+
+// Process-wide serialisation of this library's GPU work.  Handles are independent objects, but kernels of two
+// handles running CONCURRENTLY on one GPU were observed to corrupt each other on this B200 pool: whenever the
+// one-CTA potf2_64_kernel of one stream shared an SM with a DMMA GEMM CTA of another stream, single 8 x 32
+// accumulator fragments of that GEMM came out wrong (tools/concurrency_check.py: 9 of 16 concurrent fits at
+// N = 8192; none when potf2 is kept off the GEMM's SMs, none when either kernel is isolated).
+// The root cause is not understood, so every entry point that launches work takes this lock; calls are synchronous,
+// hence no two calls of this library ever overlap on the device.  One call already saturates the GPU, so nothing
+// is lost in throughput; separate processes (one per GPU) are unaffected.
+std::mutex g_device_work_mutex;
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -655,6 +666,7 @@ int nngp_stats_reset(nngp_handle* h) {
 // -------------------------------------------------------------------------------------------------
 int nngp_kernel(nngp_handle* h, const double* x1, int64_t M, const double* x2, int64_t N2, int64_t D, double* k_out) {
   if (!h) return NNGP_EINVAL;
+  std::lock_guard<std::mutex> device_lock(g_device_work_mutex);
   if (!x1 || !k_out || M <= 0 || D <= 0 || (x2 && N2 <= 0))
     return fail(h, NNGP_EINVAL, "nngp_kernel: bad argument (M=%lld N2=%lld D=%lld)", (long long)M, (long long)N2, (long long)D);
   CKR(bind_device(h));
@@ -696,6 +708,7 @@ int nngp_kernel(nngp_handle* h, const double* x1, int64_t M, const double* x2, i
 // -------------------------------------------------------------------------------------------------
 int nngp_fit(nngp_handle* h, const double* x_train, const double* y_train, int64_t N, int64_t D) {
   if (!h) return NNGP_EINVAL;
+  std::lock_guard<std::mutex> device_lock(g_device_work_mutex);
   if (!x_train || !y_train || N <= 0 || D <= 0)
     return fail(h, NNGP_EINVAL, "nngp_fit: bad argument (N=%lld D=%lld)", (long long)N, (long long)D);
   if (N > 65535LL * GEMM_BM || D > 0x7fffffffLL) return fail(h, NNGP_EINVAL, "nngp_fit: N=%lld too large", (long long)N);
@@ -772,6 +785,7 @@ int nngp_fit(nngp_handle* h, const double* x_train, const double* y_train, int64
 // -------------------------------------------------------------------------------------------------
 int nngp_predict(nngp_handle* h, const double* x_test, int64_t T, double* mean_out, double* var_out) {
   if (!h) return NNGP_EINVAL;
+  std::lock_guard<std::mutex> device_lock(g_device_work_mutex);
   if (!h->fitted) return fail(h, NNGP_ESTATE, "nngp_predict: no fitted model (call nngp_fit or nngp_set_state)");
   if (!x_test || !mean_out || T <= 0) return fail(h, NNGP_EINVAL, "nngp_predict: bad argument (T=%lld)", (long long)T);
   CKR(bind_device(h));
@@ -894,6 +908,7 @@ int nngp_log_marginal_likelihood(nngp_handle* h, double* lml_out) {
 
 int nngp_get_state(nngp_handle* h, double* x_out, double* l_out, double* alpha_out) {
   if (!h) return NNGP_EINVAL;
+  std::lock_guard<std::mutex> device_lock(g_device_work_mutex);
   if (!h->fitted) return fail(h, NNGP_ESTATE, "nngp_get_state: no fitted model");
   if (h->cfg.kernel_type == 1 && l_out)
     return fail(h, NNGP_ESTATE, "nngp_get_state: exporting the factor is not supported in 'ntk' mode (the state also holds M)");
@@ -913,6 +928,7 @@ int nngp_get_state(nngp_handle* h, double* x_out, double* l_out, double* alpha_o
 int nngp_set_state(nngp_handle* h, const double* x, const double* l, const double* alpha, int64_t N, int64_t D,
                    double lambda) {
   if (!h) return NNGP_EINVAL;
+  std::lock_guard<std::mutex> device_lock(g_device_work_mutex);
   if (!x || !l || !alpha || N <= 0 || D <= 0) return fail(h, NNGP_EINVAL, "nngp_set_state: bad argument");
   if (h->cfg.kernel_type == 1) return fail(h, NNGP_ESTATE, "nngp_set_state: not supported in 'ntk' mode");
   CKR(bind_device(h));
@@ -934,6 +950,7 @@ int nngp_set_state(nngp_handle* h, const double* x, const double* l, const doubl
 // -------------------------------------------------------------------------------------------------
 int nngp_diag_dmma_peak(nngp_handle* h, double* tflops_out) {
   if (!h || !tflops_out) return NNGP_EINVAL;
+  std::lock_guard<std::mutex> device_lock(g_device_work_mutex);
   CKR(bind_device(h));
   const int iters = 4096;
   const int ctas = h->sm_count * 4;
@@ -960,6 +977,7 @@ int nngp_diag_dmma_peak(nngp_handle* h, double* tflops_out) {
 int nngp_diag_gemm_probe(nngp_handle* h, int64_t M, int64_t N, int64_t K, int32_t iters, double* ms_out) {
   if (!h || !ms_out || M <= 0 || N <= 0 || K <= 0 || K % GEMM_BK || iters <= 0)
     return fail(h, NNGP_EINVAL, "nngp_diag_gemm_probe: bad argument");
+  std::lock_guard<std::mutex> device_lock(g_device_work_mutex);
   CKR(bind_device(h));
   DevBuf A, B, C;
   const int64_t ld = round_up(K, 16), ldc = round_up(N, 16);
@@ -991,6 +1009,7 @@ int nngp_diag_gemm_probe(nngp_handle* h, int64_t M, int64_t N, int64_t K, int32_
 
 int nngp_diag_potrf(nngp_handle* h, double* a, int64_t N) {
   if (!h || !a || N <= 0) return NNGP_EINVAL;
+  std::lock_guard<std::mutex> device_lock(g_device_work_mutex);
   CKR(bind_device(h));
   const int64_t ld = round_up(N, 16);
   const int64_t extra = getenv("NNGP_DIAG_EXTRA") ? 1 : 0;  // debug: carry a row of ones like nngp_fit carries y^T

@@ -188,6 +188,36 @@ def test_repeated_fits_are_bit_identical(lib, synth):
             assert all(np.array_equal(a, b) for a, b in zip(cur, ref)), f"fit #{rep} differs from fit #0"
 
 
+def test_two_threads_match_the_serial_result(lib, synth):
+    """Two handles driven from two host threads: results must equal the serial reference bit for bit
+    (the library serialises its device work process-wide; see DESIGN.md section 5.3 for why)."""
+    import threading
+    xtr, ytr, xte, _ = synth.make_problem(4096, 2048, 64)
+    y1 = np.ones_like(ytr)
+    ref_h = lib.Handle()
+    ref_h.fit(xtr, y1)
+    ref = (ref_h.get_state(x=False, l=False)["alpha"],) + tuple(ref_h.predict(xte))
+    errors = []
+
+    def worker():
+        try:
+            h = lib.Handle()
+            for _ in range(4):
+                h.fit(xtr, y1)
+                cur = (h.get_state(x=False, l=False)["alpha"],) + tuple(h.predict(xte))
+                if not all(np.array_equal(a, b) for a, b in zip(cur, ref)):
+                    errors.append("mismatch")
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    ts = [threading.Thread(target=worker) for _ in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
+
+
 def test_full_size_properties_c2(lib, synth):
     """BASELINE config C2 sizes (N=8192, D=128, depth 2): size-independent properties + sampled oracle check."""
     xtr, ytr, xte, _ = synth.make_problem(8192, 8192, 128)
