@@ -83,7 +83,7 @@ struct nngp_handle {
   // predict workspace
   DevBuf xt, qt, kss, blk, mean_d, var_d, ssq, sync_ints;
   // NTK mode: M = L^-1 K_dd L^-T (N x N), scratch for building it, second row block, cross / partial terms
-  DevBuf Mmat, Kdd, blk2, cross, partial;
+  DevBuf Mmat, Kdd, blk2, cross, partial, mean_partial;
   // nngp_kernel workspace
   DevBuf ka, kb, kqa, kqb, kout;
 
@@ -263,8 +263,10 @@ int launch_gemm(nngp_handle* h, const MatView& A, int a_row0, int a_col0, const 
 // K(A rows, B rows) -> out (M x N, ld ldo).  A: M x D (lda), B: N x D (ldb); qa/qb layer-0 diagonals.
 // In NTK mode (cfg.kernel_type == 1) `out` receives Theta and `out2` (optional) the NNGP kernel K.
 int run_gram(nngp_handle* h, const double* A, int64_t lda, int64_t M, const double* qa, const double* B, int64_t ldb,
-             int64_t N, const double* qb, int64_t D, double* out, int64_t ldo, int lower, double* out2 = nullptr) {
+             int64_t N, const double* qb, int64_t D, double* out, int64_t ldo, int lower, double* out2 = nullptr,
+             const double* alpha = nullptr, double* mean_partial = nullptr) {
   GemmParams p{};
+  p.alpha = alpha; p.mean_partial = mean_partial;
   p.ntk = h->cfg.kernel_type == 1 ? 1 : 0;
   p.C2 = out2;
   p.M = (int)M; p.N = (int)N;
@@ -641,7 +643,7 @@ void nngp_destroy(nngp_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->X, &h->q, &h->L, &h->alpha, &h->flags, &h->lam_d, &h->xt, &h->qt, &h->kss,
-                    &h->blk, &h->mean_d, &h->var_d, &h->ssq, &h->sync_ints, &h->Mmat, &h->Kdd, &h->blk2, &h->cross, &h->partial, &h->ka, &h->kb, &h->kqa, &h->kqb, &h->kout})
+                    &h->blk, &h->mean_d, &h->var_d, &h->ssq, &h->sync_ints, &h->Mmat, &h->Kdd, &h->blk2, &h->cross, &h->partial, &h->mean_partial, &h->ka, &h->kb, &h->kqa, &h->kqb, &h->kout})
     release(*b);
   for (auto& r : h->pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : h->ev_pool) cudaEventDestroy(e);
@@ -806,6 +808,7 @@ int nngp_predict(nngp_handle* h, const double* x_test, int64_t T, double* mean_o
   CKR(ensure(h, h->kss, (size_t)TB * 8));
   CKR(ensure(h, h->blk, (size_t)TB * ldl * 8));
   const int col_tiles = (int)((N + GEMM_BN - 1) / GEMM_BN);
+  CKR(ensure(h, h->mean_partial, (size_t)TB * 2 * col_tiles * 8));  // one partial per 32-column warp slab
   if (ntk && var_out) {
     CKR(ensure(h, h->blk2, (size_t)TB * ldl * 8));
     CKR(ensure(h, h->cross, (size_t)TB * 8));
@@ -831,11 +834,11 @@ int nngp_predict(nngp_handle* h, const double* x_test, int64_t T, double* mean_o
     row_sqnorm_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, h->stream>>>(xt, ldx, (int)rows, (int)D, sw2, sb2, h->qt.as<double>());
     h->st.kernel_launches++;
     CKR(run_gram(h, xt, ldx, rows, h->qt.as<double>(), h->X.as<double>(), ldx, N, h->q.as<double>(), D, blk, ldl, 0,
-                 (ntk && var_out) ? h->blk2.as<double>() : nullptr));
+                 (ntk && var_out) ? h->blk2.as<double>() : nullptr, h->alpha.as<double>(), h->mean_partial.as<double>()));
     timers.back().stop();
 
     timers.emplace_back(h, &h->st.pred_mean_ms);
-    gemv_rows_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, h->stream>>>(blk, ldl, (int)rows, (int)N, h->alpha.as<double>(), h->mean_d.as<double>() + t0);
+    mean_reduce_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, h->stream>>>(h->mean_partial.as<double>(), 2 * col_tiles, (int)rows, h->mean_d.as<double>() + t0);
     h->st.kernel_launches++;
     timers.back().stop();
 

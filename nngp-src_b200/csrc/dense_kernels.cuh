@@ -5,7 +5,7 @@
 //   trsm_rows_64                  X L_JJ^T = B, one thread per row                (K5 panel, K10)
 //   trsv_bwd_step                 blocked backward substitution (the forward one rides through
 //                                 the Cholesky as an extra row of the factor buffer)              (K6)
-//   gemv_rows                     mean = K_* alpha, one warp per test row          (K8)
+//   mean_reduce                   finishes mean = K_* alpha (the GEMV itself is fused into the Gram epilogue) (K8)
 //   var_rows                      var = K(x,x) - ||V_row||^2, one warp per row     (K10/K11)
 // All reductions have a fixed order: results are bitwise reproducible and independent of how
 // test rows are sharded over GPUs.
@@ -363,37 +363,6 @@ __global__ void __launch_bounds__(TRSV_THREADS) trsv_bwd_step_kernel(const doubl
   }
 }
 
-// mean[r] = sum_j B[r][j] * alpha[j]; one warp per row, 4 independent partial sums per lane.
-__global__ void gemv_rows_kernel(const double* __restrict__ B, long long ldb, int rows, int N,
-                                 const double* __restrict__ alpha, double* __restrict__ mean) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= rows) return;
-  const double* br = B + (long long)warp * ldb;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  int j = 2 * lane;
-  for (; j + 193 < N; j += 256) {
-    const double2 b0 = *reinterpret_cast<const double2*>(br + j);
-    const double2 b1 = *reinterpret_cast<const double2*>(br + j + 64);
-    const double2 b2 = *reinterpret_cast<const double2*>(br + j + 128);
-    const double2 b3 = *reinterpret_cast<const double2*>(br + j + 192);
-    const double2 a0 = *reinterpret_cast<const double2*>(alpha + j);
-    const double2 a1 = *reinterpret_cast<const double2*>(alpha + j + 64);
-    const double2 a2 = *reinterpret_cast<const double2*>(alpha + j + 128);
-    const double2 a3 = *reinterpret_cast<const double2*>(alpha + j + 192);
-    s0 = fma(b0.x, a0.x, s0); s0 = fma(b0.y, a0.y, s0);
-    s1 = fma(b1.x, a1.x, s1); s1 = fma(b1.y, a1.y, s1);
-    s2 = fma(b2.x, a2.x, s2); s2 = fma(b2.y, a2.y, s2);
-    s3 = fma(b3.x, a3.x, s3); s3 = fma(b3.y, a3.y, s3);
-  }
-  for (; j < N; j += 64) {
-    s0 = fma(br[j], alpha[j], s0);
-    if (j + 1 < N) s0 = fma(br[j + 1], alpha[j + 1], s0);
-  }
-  const double s = warp_sum((s0 + s1) + (s2 + s3));
-  if (lane == 0) mean[warp] = s;
-}
-
 // var[r] = kss[r] - sum_j V[r][j]^2; one warp per row.
 __global__ void var_rows_kernel(const double* __restrict__ V, long long ldv, int rows, int N,
                                 const double* __restrict__ kss, double* __restrict__ var) {
@@ -467,6 +436,15 @@ __global__ void rowdot_kernel(const double* __restrict__ A, const double* __rest
   }
   const double s = warp_sum(s0 + s1);
   if (lane == 0) out[warp] = s;
+}
+
+// mean[r] = sum_t partial[t][r]: finishes the posterior-mean GEMV that the Gram epilogue fused (tiles in index order)
+__global__ void mean_reduce_kernel(const double* __restrict__ partial, int tiles, int rows, double* __restrict__ mean) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  double s = 0.0;
+  for (int t = 0; t < tiles; ++t) s += partial[(long long)t * rows + r];
+  mean[r] = s;
 }
 
 // NTK posterior variance: var[r] = kss[r] + sum_t partial[t][r] - 2 cross[r]   (tiles summed in index order)

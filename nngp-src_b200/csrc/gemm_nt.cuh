@@ -55,6 +55,9 @@ struct GemmParams {
   int steps;           // depth-1 arc-cosine steps
   int ntk;             // 1: C receives the NTK Theta, C2 (if not null) the NNGP kernel K
   double* C2;
+  const double* alpha; // EPI_GRAM, optional: fused posterior-mean GEMV,
+                       //   mean_partial[(2 * tile_n + wn) * M + r] = sum over that warp's 32 columns of K[r][c] alpha[c]
+  double* mean_partial;
   // EPI_ROWDOT only: partial[tile_n * M + r] = sum_{c in tile} acc[r][c] * W[r][c]
   const double* W;     // M x N, leading dimension ldc (reuses ldc)
   double* partial;
@@ -346,49 +349,64 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (r < p.M) p.partial[(long long)tile_n * p.M + r] = red[threadIdx.x] + red[GEMM_BM + threadIdx.x];
     }
   } else {
+    double msum[4] = {0.0, 0.0, 0.0, 0.0};  // fused GEMV partial sums (this thread's 8 columns of 4 rows)
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi) {
       const int r = row_base_e + 8 * mi;
-      if (r >= p.M) continue;
-      const double q1r = p.q1[r];
+      if (r < p.M) {
+        const double q1r = p.q1[r];
 #pragma unroll
-      for (int ni = 0; ni < 4; ++ni) {
-        const int c = col_base_e + 8 * ni;
-        double k0 = p.scale * acc[mi][ni][0] + p.sb2;
-        double k1 = p.scale * acc[mi][ni][1] + p.sb2;
-        double qa = q1r;
-        double qb0 = (c < p.N) ? __ldg(p.q2 + c) : 0.0;          // re-read per fragment (L1 hit): keeps 16 registers free
-        double qb1 = (c + 1 < p.N) ? __ldg(p.q2 + c + 1) : 0.0;
-        double* dst = p.C + (long long)r * p.ldc + c;
-        if (!p.ntk) {
-          for (int s = 0; s < p.steps; ++s) {
-            k0 = arccos_step(k0, qa, qb0, p.sw2, p.sb2);
-            k1 = arccos_step(k1, qa, qb1, p.sw2, p.sb2);
-            qa = p.sw2 * (0.5 * qa) + p.sb2;
-            qb0 = p.sw2 * (0.5 * qb0) + p.sb2;
-            qb1 = p.sw2 * (0.5 * qb1) + p.sb2;
+        for (int ni = 0; ni < 4; ++ni) {
+          const int c = col_base_e + 8 * ni;
+          double k0 = p.scale * acc[mi][ni][0] + p.sb2;
+          double k1 = p.scale * acc[mi][ni][1] + p.sb2;
+          double qa = q1r;
+          double qb0 = (c < p.N) ? __ldg(p.q2 + c) : 0.0;          // re-read per fragment (L1 hit): keeps 16 registers free
+          double qb1 = (c + 1 < p.N) ? __ldg(p.q2 + c + 1) : 0.0;
+          double* dst = p.C + (long long)r * p.ldc + c;
+          if (!p.ntk) {
+            for (int s = 0; s < p.steps; ++s) {
+              k0 = arccos_step(k0, qa, qb0, p.sw2, p.sb2);
+              k1 = arccos_step(k1, qa, qb1, p.sw2, p.sb2);
+              qa = p.sw2 * (0.5 * qa) + p.sb2;
+              qb0 = p.sw2 * (0.5 * qb0) + p.sb2;
+              qb1 = p.sw2 * (0.5 * qb1) + p.sb2;
+            }
+          } else {
+            double n0 = k0, n1 = k1;
+            for (int s = 0; s < p.steps; ++s) {
+              arccos_step_ntk(k0, n0, qa, qb0, p.sw2, p.sb2);
+              arccos_step_ntk(k1, n1, qa, qb1, p.sw2, p.sb2);
+              qa = p.sw2 * (0.5 * qa) + p.sb2;
+              qb0 = p.sw2 * (0.5 * qb0) + p.sb2;
+              qb1 = p.sw2 * (0.5 * qb1) + p.sb2;
+            }
+            if (p.C2) {
+              double* dst2 = p.C2 + (long long)r * p.ldc + c;
+              if (c + 1 < p.N) *reinterpret_cast<double2*>(dst2) = make_double2(k0, k1);
+              else if (c < p.N) dst2[0] = k0;
+            }
+            k0 = n0; k1 = n1;
           }
-        } else {
-          double n0 = k0, n1 = k1;
-          for (int s = 0; s < p.steps; ++s) {
-            arccos_step_ntk(k0, n0, qa, qb0, p.sw2, p.sb2);
-            arccos_step_ntk(k1, n1, qa, qb1, p.sw2, p.sb2);
-            qa = p.sw2 * (0.5 * qa) + p.sb2;
-            qb0 = p.sw2 * (0.5 * qb0) + p.sb2;
-            qb1 = p.sw2 * (0.5 * qb1) + p.sb2;
+          if (c + 1 < p.N) {
+            *reinterpret_cast<double2*>(dst) = make_double2(k0, k1);
+          } else if (c < p.N) {
+            dst[0] = k0;
           }
-          if (p.C2) {
-            double* dst2 = p.C2 + (long long)r * p.ldc + c;
-            if (c + 1 < p.N) *reinterpret_cast<double2*>(dst2) = make_double2(k0, k1);
-            else if (c < p.N) dst2[0] = k0;
+          if (p.alpha != nullptr) {  // K_* alpha (Theta_* alpha in NTK mode), columns in ascending order
+            if (c < p.N) msum[mi] = fma(k0, __ldg(p.alpha + c), msum[mi]);
+            if (c + 1 < p.N) msum[mi] = fma(k1, __ldg(p.alpha + c + 1), msum[mi]);
           }
-          k0 = n0; k1 = n1;
         }
-        if (c + 1 < p.N) {
-          *reinterpret_cast<double2*>(dst) = make_double2(k0, k1);
-        } else if (c < p.N) {
-          dst[0] = k0;
-        }
+      }
+    }
+    if (p.alpha != nullptr) {  // fixed-order reduction inside the quad, then one partial per (tile, warp column)
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) {
+        msum[mi] += __shfl_xor_sync(0xffffffffu, msum[mi], 1);
+        msum[mi] += __shfl_xor_sync(0xffffffffu, msum[mi], 2);
+        const int r = row_base_e + 8 * mi;
+        if (t == 0 && r < p.M) p.mean_partial[(long long)(2 * tile_n + wn) * p.M + r] = msum[mi];
       }
     }
   }
