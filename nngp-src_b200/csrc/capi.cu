@@ -13,7 +13,6 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
-#include <mutex>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -29,15 +28,6 @@ namespace {
 
 thread_local std::string g_create_error;
 
-// Process-wide serialisation of this library's GPU work.  Handles are independent objects, but kernels of two
-// handles running CONCURRENTLY on one GPU were observed to corrupt each other on this B200 pool: whenever the
-// one-CTA potf2_64_kernel of one stream shared an SM with a DMMA GEMM CTA of another stream, single 8 x 32
-// accumulator fragments of that GEMM came out wrong (tools/concurrency_check.py: 9 of 16 concurrent fits at
-// N = 8192; none when potf2 is kept off the GEMM's SMs, none when either kernel is isolated).
-// The root cause is not understood, so every entry point that launches work takes this lock; calls are synchronous,
-// hence no two calls of this library ever overlap on the device.  One call already saturates the GPU, so nothing
-// is lost in throughput; separate processes (one per GPU) are unaffected.
-std::mutex g_device_work_mutex;
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -329,7 +319,7 @@ int potrf_panel(nngp_handle* h, double* A, int64_t ld, int64_t N, int64_t R, int
     const int64_t nb = std::min<int64_t>(NB, N - s0);
     if (s0 > j0)  // A[s0:R, s0:s0+nb] -= A[s0:R, j0:s0] * A[s0:s0+nb, j0:s0]^T
       CKR(run_gemm_sub(h, Av, s0, j0, Av, s0, j0, R - s0, nb, s0 - j0, A + s0 * ld + s0, ld, 0));
-    potf2_64_kernel<<<1, 256, 0, h->cur>>>(A + s0 * ld + s0, ld, (int)nb, (int)s0, info);
+    potf2_64_kernel<<<1, POTF2_THREADS, 0, h->cur>>>(A + s0 * ld + s0, ld, (int)nb, (int)s0, info);
     h->st.kernel_launches++;
     const int64_t below = R - s0 - nb;
     if (below > 0) {
@@ -344,12 +334,11 @@ int potrf_panel(nngp_handle* h, double* A, int64_t ld, int64_t N, int64_t R, int
 
 // Blocked right-looking Cholesky.  The trailing update of outer step j is split into (A) the columns of the NEXT
 // panel and (B) the rest.
-// Optional look-ahead (NNGP_CHOL_LOOKAHEAD=1, OFF by default): as soon as (A) is done the next panel is factored on
-// a high-priority stream while (B) keeps the tensor pipes busy on the main stream (-6 % fit time at N = 32768,
-// -30 % at N = 8192).  It is off by default because overlapping the two streams was observed to corrupt results
-// on this B200 pool (about one fit in ten at N = 8192) although the streams touch disjoint column ranges and the
-// identical two-stream schedule WITHOUT overlap (NNGP_LA_MODE=2) is bit-stable; the findings are written up in
-// DESIGN.md section 5.3 and reproducible with tools/determinism_check.py.
+// Look-ahead (on by default, NNGP_CHOL_LOOKAHEAD=0 disables it): as soon as (A) is done the next panel is factored
+// on a high-priority stream while (B) keeps the tensor pipes busy on the main stream (-6 % fit time at N = 32768,
+// -30 % at N = 8192).  The two streams touch disjoint column ranges, so the factor is bitwise the same with and
+// without it (tests/test_gpu_parity.py, tools/determinism_check.py).  NNGP_LA_MODE=2 keeps the two-stream schedule
+// but removes the overlap (debugging aid).
 // `extra` rows stored below the matrix (rows N..N+extra-1, N columns each) are carried through every
 // panel solve and trailing update: on exit they hold  E L^-T.  The fit puts y^T there, so the forward
 // substitution z = L^-1 y of the alpha solve costs nothing extra (one more row in GEMMs already running).
@@ -606,10 +595,10 @@ int nngp_create(const nngp_config* cfg, nngp_handle** out) {
     return bail(NNGP_ECUDA);
   }
   h->cur = h->stream;
-  // Look-ahead is opt-in (see run_potrf): without NNGP_CHOL_LOOKAHEAD=1 the panel stream is not kept.
+  // Look-ahead can be switched off (see run_potrf): with NNGP_CHOL_LOOKAHEAD=0 the panel stream is not kept.
   {
     const char* e = getenv("NNGP_CHOL_LOOKAHEAD");
-    if (!(e && !strcmp(e, "1"))) { cudaStreamDestroy(h->panel_stream); h->panel_stream = nullptr; }
+    if (e && !strcmp(e, "0")) { cudaStreamDestroy(h->panel_stream); h->panel_stream = nullptr; }
   }
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -668,7 +657,6 @@ int nngp_stats_reset(nngp_handle* h) {
 // -------------------------------------------------------------------------------------------------
 int nngp_kernel(nngp_handle* h, const double* x1, int64_t M, const double* x2, int64_t N2, int64_t D, double* k_out) {
   if (!h) return NNGP_EINVAL;
-  std::lock_guard<std::mutex> device_lock(g_device_work_mutex);
   if (!x1 || !k_out || M <= 0 || D <= 0 || (x2 && N2 <= 0))
     return fail(h, NNGP_EINVAL, "nngp_kernel: bad argument (M=%lld N2=%lld D=%lld)", (long long)M, (long long)N2, (long long)D);
   CKR(bind_device(h));
@@ -710,7 +698,6 @@ int nngp_kernel(nngp_handle* h, const double* x1, int64_t M, const double* x2, i
 // -------------------------------------------------------------------------------------------------
 int nngp_fit(nngp_handle* h, const double* x_train, const double* y_train, int64_t N, int64_t D) {
   if (!h) return NNGP_EINVAL;
-  std::lock_guard<std::mutex> device_lock(g_device_work_mutex);
   if (!x_train || !y_train || N <= 0 || D <= 0)
     return fail(h, NNGP_EINVAL, "nngp_fit: bad argument (N=%lld D=%lld)", (long long)N, (long long)D);
   if (N > 65535LL * GEMM_BM || D > 0x7fffffffLL) return fail(h, NNGP_EINVAL, "nngp_fit: N=%lld too large", (long long)N);
@@ -787,7 +774,6 @@ int nngp_fit(nngp_handle* h, const double* x_train, const double* y_train, int64
 // -------------------------------------------------------------------------------------------------
 int nngp_predict(nngp_handle* h, const double* x_test, int64_t T, double* mean_out, double* var_out) {
   if (!h) return NNGP_EINVAL;
-  std::lock_guard<std::mutex> device_lock(g_device_work_mutex);
   if (!h->fitted) return fail(h, NNGP_ESTATE, "nngp_predict: no fitted model (call nngp_fit or nngp_set_state)");
   if (!x_test || !mean_out || T <= 0) return fail(h, NNGP_EINVAL, "nngp_predict: bad argument (T=%lld)", (long long)T);
   CKR(bind_device(h));
@@ -911,7 +897,6 @@ int nngp_log_marginal_likelihood(nngp_handle* h, double* lml_out) {
 
 int nngp_get_state(nngp_handle* h, double* x_out, double* l_out, double* alpha_out) {
   if (!h) return NNGP_EINVAL;
-  std::lock_guard<std::mutex> device_lock(g_device_work_mutex);
   if (!h->fitted) return fail(h, NNGP_ESTATE, "nngp_get_state: no fitted model");
   if (h->cfg.kernel_type == 1 && l_out)
     return fail(h, NNGP_ESTATE, "nngp_get_state: exporting the factor is not supported in 'ntk' mode (the state also holds M)");
@@ -931,7 +916,6 @@ int nngp_get_state(nngp_handle* h, double* x_out, double* l_out, double* alpha_o
 int nngp_set_state(nngp_handle* h, const double* x, const double* l, const double* alpha, int64_t N, int64_t D,
                    double lambda) {
   if (!h) return NNGP_EINVAL;
-  std::lock_guard<std::mutex> device_lock(g_device_work_mutex);
   if (!x || !l || !alpha || N <= 0 || D <= 0) return fail(h, NNGP_EINVAL, "nngp_set_state: bad argument");
   if (h->cfg.kernel_type == 1) return fail(h, NNGP_ESTATE, "nngp_set_state: not supported in 'ntk' mode");
   CKR(bind_device(h));
@@ -953,7 +937,6 @@ int nngp_set_state(nngp_handle* h, const double* x, const double* l, const doubl
 // -------------------------------------------------------------------------------------------------
 int nngp_diag_dmma_peak(nngp_handle* h, double* tflops_out) {
   if (!h || !tflops_out) return NNGP_EINVAL;
-  std::lock_guard<std::mutex> device_lock(g_device_work_mutex);
   CKR(bind_device(h));
   const int iters = 4096;
   const int ctas = h->sm_count * 4;
@@ -980,7 +963,6 @@ int nngp_diag_dmma_peak(nngp_handle* h, double* tflops_out) {
 int nngp_diag_gemm_probe(nngp_handle* h, int64_t M, int64_t N, int64_t K, int32_t iters, double* ms_out) {
   if (!h || !ms_out || M <= 0 || N <= 0 || K <= 0 || K % GEMM_BK || iters <= 0)
     return fail(h, NNGP_EINVAL, "nngp_diag_gemm_probe: bad argument");
-  std::lock_guard<std::mutex> device_lock(g_device_work_mutex);
   CKR(bind_device(h));
   DevBuf A, B, C;
   const int64_t ld = round_up(K, 16), ldc = round_up(N, 16);
@@ -1012,7 +994,6 @@ int nngp_diag_gemm_probe(nngp_handle* h, int64_t M, int64_t N, int64_t K, int32_
 
 int nngp_diag_potrf(nngp_handle* h, double* a, int64_t N) {
   if (!h || !a || N <= 0) return NNGP_EINVAL;
-  std::lock_guard<std::mutex> device_lock(g_device_work_mutex);
   CKR(bind_device(h));
   const int64_t ld = round_up(N, 16);
   const int64_t extra = getenv("NNGP_DIAG_EXTRA") ? 1 : 0;  // debug: carry a row of ones like nngp_fit carries y^T

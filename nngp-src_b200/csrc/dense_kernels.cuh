@@ -74,21 +74,27 @@ __global__ void diag_reg_kernel(double* __restrict__ K, long long ld, int N, dou
   for (int i = threadIdx.x; i < N; i += blockDim.x) K[(long long)i * ld + i] += lam;
 }
 
-// In-place lower Cholesky of the n x n (n <= 64) block at A (row-major, ld).  One CTA, 256 threads as a
-// 16 x 16 grid, each thread owning a 4 x 4 register sub-block (right-looking, two barriers per column;
-// the pivot column is scaled by the reciprocal pivot, as LAPACK dpotf2 does, obtained with one rsqrt).
+// In-place lower Cholesky of the n x n (n <= 64) block at A (row-major, ld).  One CTA of POTF2_THREADS threads as a
+// 16 x (POTF2_THREADS/16) grid, each thread owning a (64*16/POTF2_THREADS) x 4 register sub-block (right-looking,
+// two barriers per column; the pivot column is scaled by the reciprocal pivot, as LAPACK dpotf2 does, obtained
+// with one rsqrt).
 // On a non-positive pivot: *info = global pivot index + 1 (first failure wins), block left as is.
-__global__ void __launch_bounds__(256) potf2_64_kernel(double* __restrict__ A, long long ld, int n, int pivot0,
-                                                       int* __restrict__ info) {
+#ifndef NNGP_POTF2_THREADS
+#define NNGP_POTF2_THREADS 256
+#endif
+constexpr int POTF2_THREADS = NNGP_POTF2_THREADS;
+constexpr int POTF2_RB = NB * 16 / POTF2_THREADS;  // rows per thread: 4 (256 threads) or 8 (128 threads)
+__global__ void __launch_bounds__(POTF2_THREADS) potf2_64_kernel(double* __restrict__ A, long long ld, int n, int pivot0,
+                                                                 int* __restrict__ info) {
   __shared__ double colj[NB];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  double v[4][4];
+  double v[POTF2_RB][4];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < POTF2_RB; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-      const int r = ty * 4 + a, c = tx * 4 + b;
+      const int r = ty * POTF2_RB + a, c = tx * 4 + b;
       v[a][b] = (r < n && c <= r) ? __ldcg(A + (long long)r * ld + c) : ((r == c) ? 1.0 : 0.0);
     }
   bool bad = false;
@@ -96,11 +102,11 @@ __global__ void __launch_bounds__(256) potf2_64_kernel(double* __restrict__ A, l
     const int jb = j >> 2, ja = j & 3;
     if (tx == jb) {  // owners of column j publish the (unscaled) column; the diagonal owner also the pivot
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
+      for (int a = 0; a < POTF2_RB; ++a) {
         double cur = 0.0;
 #pragma unroll
         for (int b = 0; b < 4; ++b) if (b == ja) cur = v[a][b];
-        colj[ty * 4 + a] = cur;
+        colj[ty * POTF2_RB + a] = cur;
       }
     }
     __syncthreads();
@@ -113,32 +119,32 @@ __global__ void __launch_bounds__(256) potf2_64_kernel(double* __restrict__ A, l
     // every thread derives the pivot itself (one rsqrt chain, no second round trip through smem)
     const double rinv = rsqrt(d);
     const double piv = d * rinv;
-    double lr[4], lc[4];
+    double lr[POTF2_RB], lc[4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) lr[a] = (ty * 4 + a > j) ? colj[ty * 4 + a] * rinv : 0.0;
+    for (int a = 0; a < POTF2_RB; ++a) lr[a] = (ty * POTF2_RB + a > j) ? colj[ty * POTF2_RB + a] * rinv : 0.0;
 #pragma unroll
     for (int b = 0; b < 4; ++b) lc[b] = (tx * 4 + b > j) ? colj[tx * 4 + b] * rinv : 0.0;
     if (tx == jb) {
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int r = ty * 4 + a;
+      for (int a = 0; a < POTF2_RB; ++a) {
+        const int r = ty * POTF2_RB + a;
 #pragma unroll
         for (int b = 0; b < 4; ++b)
           if (b == ja) v[a][b] = (r > j) ? lr[a] : ((r == j) ? piv : v[a][b]);
       }
     }
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < POTF2_RB; ++a)
 #pragma unroll
       for (int b = 0; b < 4; ++b) v[a][b] = fma(-lr[a], lc[b], v[a][b]);
     __syncthreads();  // colj is rewritten by the next column's owners
   }
   if (bad) return;
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < POTF2_RB; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-      const int r = ty * 4 + a, c = tx * 4 + b;
+      const int r = ty * POTF2_RB + a, c = tx * 4 + b;
       if (r < n && c <= r) A[(long long)r * ld + c] = v[a][b];
     }
 }

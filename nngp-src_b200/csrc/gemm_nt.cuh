@@ -61,6 +61,7 @@ struct GemmParams {
   // EPI_ROWDOT only: partial[tile_n * M + r] = sum_{c in tile} acc[r][c] * W[r][c]
   const double* W;     // M x N, leading dimension ldc (reuses ldc)
   double* partial;
+  uint32_t zero;       // always 0 (value-initialised): opaque run-time zero for mma_mainloop's release dependence
 };
 
 // theta = atan2(s, k) for s >= 0 (theta in [0, pi]), pi/2 at s == k == 0 [nt: _arctan2(fill_zero = pi/2)].
@@ -137,6 +138,13 @@ __device__ __forceinline__ void arccos_step_ntk(double& k, double& ntk, double q
 // Operand ring, producer and consumer in one loop.  Every warp: wait for a stage, run its 4 x (4 x 4) DMMAs on
 // the warp's 32 x 32 tile, release the stage.  Thread 0 additionally re-arms the stage it has just finished with
 // k-tile kt + STAGES once all 8 warps have released it.  `stage` / `phase` persist across calls (persistent kernels).
+//
+// Releasing a stage (WAR across proxies): the refill is a TMA write (async proxy); nothing orders it after a
+// fragment LDS that has been *issued* but has not yet read shared memory, and ptxas does hoist the SYNCS.ARRIVE to
+// right behind the last LDS of the k-tile.  With a second, shared-memory-heavy CTA on the SM that LDS can be late
+// enough to read the next k-tile (observed: the mi = 3, k4 = 3 fragment of one warp).  The arrive
+// therefore carries a data dependence on every fragment register of the k-tile (`seen & zero`, zero == 0 at run
+// time but opaque to the compiler), so the scoreboard holds it back until all of them have landed.
 struct TileSrc {  // where the A / B operand tiles of this output tile come from
   const CUtensorMap* tmA;
   const CUtensorMap* tmB;
@@ -163,42 +171,62 @@ __device__ __forceinline__ void ring_prologue(const TileSrc& src, uint8_t* ringA
   }
 }
 
+#ifndef NNGP_RELEASE_AT
+#define NNGP_RELEASE_AT 0  // 0..3: release k-tile kt-1 after the k4-th fragment loads of k-tile kt; 4: at the end of kt itself
+#endif
 template <int STAGES>
 __device__ __forceinline__ void mma_mainloop(double (&acc)[4][4][2], const TileSrc& src, uint8_t* ringA, uint8_t* ringB,
                                              uint64_t* full_bar, uint64_t* empty_bar, int& stage, uint32_t& phase,
-                                             int ktiles, int wm, int wn, int lane) {
+                                             int ktiles, int wm, int wn, int lane, uint32_t zero) {
   const int g = lane >> 2, t = lane & 3;
-  // swizzled byte offset of (row with r&7 == g, k = 4*k4 + t) inside a stage, minus 128*row
-  uint32_t koff[4];
-#pragma unroll
-  for (int k4 = 0; k4 < 4; ++k4) koff[k4] = ((uint32_t)((2 * k4 + (t >> 1)) ^ g) << 4) | ((uint32_t)(t & 1) << 3);
-  const uint32_t a_warp = smem_u32(ringA) + (uint32_t)(wm * 32 + g) * 128u;
-  const uint32_t b_warp = smem_u32(ringB) + (uint32_t)(wn * 32 + g) * 128u;
+  // Swizzled byte offset of (row with r&7 == g, k = 4*k4 + t) inside a stage, minus 128*row:
+  //   (((2*k4 + (t>>1)) ^ g) << 4) | ((t&1) << 3)  ==  koff0 ^ (k4 << 5),   koff0 = (((t>>1) ^ g) << 4) | ((t&1) << 3)
+  // (2*k4 only occupies chunk-index bits 1..2).  Rows are 128 B apart and stages 1 KiB-aligned, so the XOR can be
+  // applied to the full address: two base registers instead of four offsets.
+  const uint32_t koff0 = ((uint32_t)((t >> 1) ^ g) << 4) | ((uint32_t)(t & 1) << 3);
+  const uint32_t a_warp = smem_u32(ringA) + (uint32_t)(wm * 32 + g) * 128u + koff0;
+  const uint32_t b_warp = smem_u32(ringB) + (uint32_t)(wn * 32 + g) * 128u + koff0;
+  // The release of k-tile kt-1 is issued inside k-tile kt (after its k4 == NNGP_RELEASE_AT loads): by then the
+  // fragments it depends on have long landed, so the dependence never stalls the warp.
+  auto release = [&](int s, uint32_t ph, uint32_t seen, int kdone) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive_addr(smem_u32(&empty_bar[s]) + (seen & zero));
+    if (threadIdx.x == 0 && kdone + STAGES < ktiles) {
+      mbar_wait(&empty_bar[s], ph);  // all 8 warps are done with this stage in this round
+      ring_issue<STAGES>(src, ringA, ringB, full_bar, s, kdone + STAGES);
+    }
+    __syncwarp();
+  };
+  uint32_t seen_prev = 0;
   for (int kt = 0; kt < ktiles; ++kt) {
     mbar_wait(&full_bar[stage], phase);
+    uint32_t seen = 0;
     const uint32_t a_st = a_warp + stage * GEMM_A_STAGE_BYTES;
     const uint32_t b_st = b_warp + stage * GEMM_B_STAGE_BYTES;
 #pragma unroll
     for (int k4 = 0; k4 < 4; ++k4) {
       double a[4], b[4];
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi) a[mi] = lds_f64(a_st + mi * 1024 + koff[k4]);
+      for (int mi = 0; mi < 4; ++mi) a[mi] = lds_f64((a_st ^ (uint32_t)(k4 << 5)) + mi * 1024);
 #pragma unroll
-      for (int ni = 0; ni < 4; ++ni) b[ni] = lds_f64(b_st + ni * 1024 + koff[k4]);
+      for (int ni = 0; ni < 4; ++ni) b[ni] = lds_f64((b_st ^ (uint32_t)(k4 << 5)) + ni * 1024);
+      if (k4 == NNGP_RELEASE_AT && kt > 0)
+        release(stage == 0 ? STAGES - 1 : stage - 1, stage == 0 ? phase ^ 1u : phase, seen_prev, kt - 1);
 #pragma unroll
       for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) dmma_884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+      // folded after the DMMAs that consume the same registers: the values have landed, the XORs never stall
+#pragma unroll
+      for (int i = 0; i < 4; ++i) seen ^= (uint32_t)__double2hiint(a[i]) ^ (uint32_t)__double2hiint(b[i]);
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_bar[stage]);
-    if (threadIdx.x == 0 && kt + STAGES < ktiles) {
-      mbar_wait(&empty_bar[stage], phase);  // all 8 warps are done with this stage in this round
-      ring_issue<STAGES>(src, ringA, ringB, full_bar, stage, kt + STAGES);
-    }
-    __syncwarp();
+#if NNGP_RELEASE_AT >= 4
+    release(stage, phase, seen, kt);
+#endif
+    seen_prev = seen;
     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
   }
+  if (NNGP_RELEASE_AT < 4 && ktiles > 0) release(stage == 0 ? STAGES - 1 : stage - 1, stage == 0 ? phase ^ 1u : phase, seen_prev, ktiles - 1);
 }
 
 #ifndef NNGP_GEMM_MINBLOCKS
@@ -287,7 +315,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   int stage = 0;
   uint32_t phase = 0;
-  mma_mainloop<GEMM_STAGES>(acc, src, ringA, ringB, full_bar, empty_bar, stage, phase, ktiles, wm, wn, lane);
+  mma_mainloop<GEMM_STAGES>(acc, src, ringA, ringB, full_bar, empty_bar, stage, phase, ktiles, wm, wn, lane, p.zero);
 
   // ===== epilogue (registers -> global) =====
   // The tile coordinates are laundered through an empty asm so that the compiler re-derives the output addresses

@@ -44,6 +44,7 @@ struct TrsmFusedParams {
   double* ssq;          // [rows] running sum of squares (not required to be zeroed)
   const double* kss;    // [rows] K(x,x)
   double* var;          // [rows] output; nullptr: plain solve, no variance bookkeeping
+  uint32_t zero;        // always 0 (value-initialised): see mma_mainloop's release dependence
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
@@ -139,7 +140,7 @@ trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
       }
     }
 
-    mma_mainloop<TF_STAGES>(acc, src, ringA, ringB, full_bar, empty_bar, stage, phase, ktiles, wm, wn, lane);
+    mma_mainloop<TF_STAGES>(acc, src, ringA, ringB, full_bar, empty_bar, stage, phase, ktiles, wm, wn, lane, p.zero);
 
     __syncthreads();  // every warp has left the ring: it becomes substitution scratch
     {

@@ -188,9 +188,28 @@ def test_repeated_fits_are_bit_identical(lib, synth):
             assert all(np.array_equal(a, b) for a, b in zip(cur, ref)), f"fit #{rep} differs from fit #0"
 
 
+def test_lookahead_schedule_is_bitwise_neutral(lib, synth, monkeypatch):
+    """The two-stream look-ahead Cholesky (default) must give the factor of the single-stream schedule, every time
+    (it overlaps the one-CTA panel kernels with DMMA GEMM CTAs on the same SMs -- the case that exposed the
+    stage-release hazard)."""
+    xtr, ytr, xte, _ = synth.make_problem(8192, 256, 64)
+    monkeypatch.setenv("NNGP_CHOL_LOOKAHEAD", "0")
+    h0 = lib.Handle()
+    h0.fit(xtr, ytr)
+    ref = h0.get_state(x=False)
+    monkeypatch.delenv("NNGP_CHOL_LOOKAHEAD")
+    h1 = lib.Handle()
+    for rep in range(8):
+        h1.fit(xtr, ytr)
+        cur = h1.get_state(x=False)
+        assert np.array_equal(cur["l"], ref["l"]), f"look-ahead fit #{rep}: factor differs from the single-stream one"
+        assert np.array_equal(cur["alpha"], ref["alpha"])
+
+
 def test_two_threads_match_the_serial_result(lib, synth):
-    """Two handles driven from two host threads: results must equal the serial reference bit for bit
-    (the library serialises its device work process-wide; see DESIGN.md section 5.3 for why)."""
+    """Two handles driven from two host threads, their kernels genuinely overlapping on the GPU (no library-level
+    lock): results must equal the serial reference bit for bit.  Regression test for the stage-release hazard of
+    DESIGN.md section 5.3 (a co-resident CTA delayed a fragment LDS past the TMA refill of its ring stage)."""
     import threading
     xtr, ytr, xte, _ = synth.make_problem(4096, 2048, 64)
     y1 = np.ones_like(ytr)
