@@ -17,8 +17,9 @@
 //
 // Shared-memory layout of one operand stage (what SWIZZLE_128B produces): row r occupies
 // bytes [128 r, 128 r + 128); the 16-byte chunk c of that row lands at chunk c ^ (r & 7).
-// A DMMA A/B fragment load (lane 4g+t reads row g, k = 4*k4 + t) therefore touches each of
-// the 8 chunk columns exactly twice per warp => 2 wavefronts for 256 B: conflict-free.
+// A DMMA A/B fragment load (lane 4g+t reads row g, k = 8*(t>>1) + 2*s + (t&1) in step s -- a
+// permutation of the k index shared by A and B, see mma_mainloop) touches, per half-warp, every
+// bank exactly once => 2 wavefronts for 256 B: conflict-free.
 #pragma once
 #include "ptx.cuh"
 
@@ -179,11 +180,16 @@ __device__ __forceinline__ void mma_mainloop(double (&acc)[4][4][2], const TileS
                                              uint64_t* full_bar, uint64_t* empty_bar, int& stage, uint32_t& phase,
                                              int ktiles, int wm, int wn, int lane, uint32_t zero) {
   const int g = lane >> 2, t = lane & 3;
-  // Swizzled byte offset of (row with r&7 == g, k = 4*k4 + t) inside a stage, minus 128*row:
-  //   (((2*k4 + (t>>1)) ^ g) << 4) | ((t&1) << 3)  ==  koff0 ^ (k4 << 5),   koff0 = (((t>>1) ^ g) << 4) | ((t&1) << 3)
-  // (2*k4 only occupies chunk-index bits 1..2).  Rows are 128 B apart and stages 1 KiB-aligned, so the XOR can be
-  // applied to the full address: two base registers instead of four offsets.
-  const uint32_t koff0 = ((uint32_t)((t >> 1) ^ g) << 4) | ((uint32_t)(t & 1) << 3);
+  // Which k does lane (g, t) feed into DMMA step s?  Any bijection (s, t) -> 0..15 is a valid GEMM as long as the A
+  // and the B fragment use the same one.  We use  k = 8*(t>>1) + 2*s + (t&1):  logical 16-byte chunk 4*(t>>1) + s,
+  // half t&1.  With SWIZZLE_128B (physical chunk = logical ^ (row & 7)) the 16 lanes of a half-warp (4 rows g x 4 t)
+  // then touch every (chunk, half) pair exactly once -> an LDS.64 of the warp is 2 wavefronts, conflict-free.
+  // (The textbook k = 4*s + t puts rows g and g^1 on the same chunks: 2-way conflicts, 4 wavefronts -- measured
+  // with ncu as 45 % of all shared-load wavefronts.)  Byte offset inside the row:
+  //   (((4*(t>>1) + s) ^ g) << 4) | ((t&1) << 3)  ==  koff0 ^ (s << 4),   koff0 = (((4*(t>>1)) ^ g) << 4) | ((t&1) << 3)
+  // Rows are 128 B apart and stages 1 KiB-aligned, so the XOR can be applied to the full address: two base
+  // registers instead of four offsets.
+  const uint32_t koff0 = ((uint32_t)((4 * (t >> 1)) ^ g) << 4) | ((uint32_t)(t & 1) << 3);
   const uint32_t a_warp = smem_u32(ringA) + (uint32_t)(wm * 32 + g) * 128u + koff0;
   const uint32_t b_warp = smem_u32(ringB) + (uint32_t)(wn * 32 + g) * 128u + koff0;
   // The release of k-tile kt-1 is issued inside k-tile kt (after its k4 == NNGP_RELEASE_AT loads): by then the
@@ -207,9 +213,9 @@ __device__ __forceinline__ void mma_mainloop(double (&acc)[4][4][2], const TileS
     for (int k4 = 0; k4 < 4; ++k4) {
       double a[4], b[4];
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi) a[mi] = lds_f64((a_st ^ (uint32_t)(k4 << 5)) + mi * 1024);
+      for (int mi = 0; mi < 4; ++mi) a[mi] = lds_f64((a_st ^ (uint32_t)(k4 << 4)) + mi * 1024);
 #pragma unroll
-      for (int ni = 0; ni < 4; ++ni) b[ni] = lds_f64((b_st ^ (uint32_t)(k4 << 5)) + ni * 1024);
+      for (int ni = 0; ni < 4; ++ni) b[ni] = lds_f64((b_st ^ (uint32_t)(k4 << 4)) + ni * 1024);
       if (k4 == NNGP_RELEASE_AT && kt > 0)
         release(stage == 0 ? STAGES - 1 : stage - 1, stage == 0 ? phase ^ 1u : phase, seen_prev, kt - 1);
 #pragma unroll
