@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define NNGP_B200_ABI_VERSION 2
+#define NNGP_B200_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define NNGP_API __attribute__((visibility("default")))
@@ -154,6 +154,27 @@ NNGP_API int nngp_set_state(nngp_handle* h, const double* x, const double* l, co
  *   -1/2 y^T (K + lambda I)^-1 y - sum_i log L_ii - N/2 log(2 pi).
  * Both sums are by-products of nngp_fit (z = L^-1 y rides through the factorisation). */
 NNGP_API int nngp_log_marginal_likelihood(nngp_handle* h, double* lml_out);
+
+/* ---- active-learning step on the device ------------------------------------------
+ * nngp_active_select == ActiveLearner.active_test (active/ActiveLearner.py:43-55): posterior mean / variance of
+ * the pool, score_i = sqrt(var_i) / max_j(mean_j), then
+ *   NNGP_SELECT_TOPK   : np.argsort(score)[-k:]            (biased_sample = False, :54) -- indices in ascending
+ *                        score order, ties broken by row index (larger index later), NaN scores sort last;
+ *   NNGP_SELECT_SAMPLE : random.choice(T, k, replace=False, p = score / sum(score))  (biased_sample = True, :49-53)
+ *                        as Gumbel-top-k with a splitmix64 stream of (seed, row) -- the reference draws from JAX's
+ *                        threefry stream with PRNGKey(10), which is not reproducible without jax (unpinned);
+ *                        indices come out in draw order.  Needs finite scores >= 0 (else NNGP_EINVAL).
+ * k = min(budget, T) is returned in *n_selected_out; idx_out receives k int64 row numbers (host or device
+ * memory); score_out (T doubles, optional) receives the normalised scores.  Selection runs on the device (exact
+ * radix select); only the k winners cross PCIe.
+ * nngp_append_fit == ActiveLearner.merge_data + train (:57-65, :23-31): appends M labelled rows to the training
+ * set already held by the handle and refits from scratch (the reference's relative diag_reg makes every refit a
+ * new lambda, so the factor cannot be extended exactly).  Needs a model fitted by nngp_fit on this handle. */
+#define NNGP_SELECT_TOPK 0
+#define NNGP_SELECT_SAMPLE 1
+NNGP_API int nngp_active_select(nngp_handle* h, const double* x_pool, int64_t T, int64_t budget, int32_t mode,
+                                uint64_t seed, int64_t* idx_out, int64_t* n_selected_out, double* score_out);
+NNGP_API int nngp_append_fit(nngp_handle* h, const double* x_new, const double* y_new, int64_t M);
 
 NNGP_API int nngp_stats(nngp_handle* h, nngp_stats_t* out);
 NNGP_API int nngp_stats_reset(nngp_handle* h);

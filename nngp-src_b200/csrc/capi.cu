@@ -21,6 +21,7 @@
 #include "dense_kernels.cuh"
 #include "gemm_nt.cuh"
 #include "trsm_fused.cuh"
+#include "active_kernels.cuh"
 
 using namespace nngp;
 
@@ -67,6 +68,8 @@ struct nngp_handle {
   double lml_terms[2] = {0.0, 0.0};  // {sum log diag(L), y^T (K+lambda I)^-1 y}; valid after nngp_fit
   bool have_lml = false;
   DevBuf X, q, L, alpha;
+  DevBuf y;       // raw labels of the last nngp_fit (kept for nngp_append_fit)
+  bool have_y = false;
   DevBuf flags;   // int[2]: {potrf info, non-finite input}
   DevBuf lam_d;   // double[4]: {lambda, sum log diag L, z^T z, spare}
 
@@ -76,6 +79,8 @@ struct nngp_handle {
   DevBuf Mmat, Kdd, blk2, cross, partial, mean_partial;
   // nngp_kernel workspace
   DevBuf ka, kb, kqa, kqb, kout;
+  // nngp_active_select workspace
+  DevBuf sel_mean, sel_var, sel_score, sel_key, sel_state, sel_okey, sel_oidx, sel_max;
 
   std::map<std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t>, CUtensorMap> tmaps;
 
@@ -519,7 +524,7 @@ int bind_device(nngp_handle* h) {
   return NNGP_OK;
 }
 
-void drop_fit(nngp_handle* h) { h->fitted = false; h->have_lml = false; }
+void drop_fit(nngp_handle* h) { h->fitted = false; h->have_lml = false; h->have_y = false; }
 
 int alloc_state(nngp_handle* h, int64_t N, int64_t D) {
   h->N = N; h->D = D;
@@ -632,7 +637,8 @@ void nngp_destroy(nngp_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->X, &h->q, &h->L, &h->alpha, &h->flags, &h->lam_d, &h->xt, &h->qt, &h->kss,
-                    &h->blk, &h->mean_d, &h->var_d, &h->ssq, &h->sync_ints, &h->Mmat, &h->Kdd, &h->blk2, &h->cross, &h->partial, &h->mean_partial, &h->ka, &h->kb, &h->kqa, &h->kqb, &h->kout})
+                    &h->blk, &h->mean_d, &h->var_d, &h->ssq, &h->sync_ints, &h->Mmat, &h->Kdd, &h->blk2, &h->cross, &h->partial, &h->mean_partial, &h->ka, &h->kb, &h->kqa, &h->kqb, &h->kout, &h->y, &h->sel_mean, &h->sel_var, &h->sel_score, &h->sel_key,
+                    &h->sel_state, &h->sel_okey, &h->sel_oidx, &h->sel_max})
     release(*b);
   for (auto& r : h->pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : h->ev_pool) cudaEventDestroy(e);
@@ -714,6 +720,8 @@ int nngp_fit(nngp_handle* h, const double* x_train, const double* y_train, int64
   CK(cudaMemsetAsync(h->flags.p, 0, 2 * sizeof(int), h->stream));
   CKR(upload_matrix(h, x_train, N, D, X, h->ldx));
   CKR(upload_matrix(h, y_train, N, 1, alpha, 1));
+  CKR(ensure(h, h->y, (size_t)N * sizeof(double)));
+  CK(cudaMemcpyAsync(h->y.p, alpha, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   t_h2d.stop();
   CKR(check_finite_async(h, X, h->ldx, N, D));
   CKR(check_finite_async(h, alpha, 1, N, 1));
@@ -768,7 +776,101 @@ int nngp_fit(nngp_handle* h, const double* x_train, const double* y_train, int64
                 flags[0] - 1, (long long)N, h->lambda);
   h->fitted = true;
   h->have_lml = true;
+  h->have_y = true;
   return NNGP_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Active-learning step.  Selection: active/ActiveLearner.py:43-55; merge + refit: :57-65, :76.
+int nngp_active_select(nngp_handle* h, const double* x_pool, int64_t T, int64_t budget, int32_t mode, uint64_t seed,
+                       int64_t* idx_out, int64_t* n_selected_out, double* score_out) {
+  if (!h) return NNGP_EINVAL;
+  if (!h->fitted) return fail(h, NNGP_ESTATE, "nngp_active_select: no fitted model");
+  if (!x_pool || !idx_out || T <= 0 || budget <= 0 || (mode != NNGP_SELECT_TOPK && mode != NNGP_SELECT_SAMPLE))
+    return fail(h, NNGP_EINVAL, "nngp_active_select: bad argument (T=%lld budget=%lld mode=%d)", (long long)T, (long long)budget, mode);
+  if (T > 0xffffffffLL) return fail(h, NNGP_EINVAL, "nngp_active_select: T=%lld exceeds 2^32-1 rows", (long long)T);
+  CKR(bind_device(h));
+  const int64_t k = budget < T ? budget : T;   // num_select = budget if num_test > budget else num_test
+  CKR(ensure(h, h->sel_mean, (size_t)T * 8));
+  CKR(ensure(h, h->sel_var, (size_t)T * 8));
+  CKR(ensure(h, h->sel_score, (size_t)T * 8));
+  CKR(ensure(h, h->sel_key, (size_t)T * 8));
+  CKR(ensure(h, h->sel_okey, (size_t)k * 8));
+  CKR(ensure(h, h->sel_oidx, (size_t)k * 4));
+  CKR(ensure(h, h->sel_state, sizeof(SelectState)));
+  CKR(ensure(h, h->sel_max, 8));
+  // posterior mean / variance of the pool, left on the device (outputs are device pointers)
+  CKR(nngp_predict(h, x_pool, T, h->sel_mean.as<double>(), h->sel_var.as<double>()));
+
+  SelectState init;
+  memset(&init, 0, sizeof init);
+  init.k_remaining = k;
+  SelectState* st = h->sel_state.as<SelectState>();
+  CK(cudaMemcpyAsync(st, &init, sizeof init, cudaMemcpyHostToDevice, h->stream));
+  max_reduce_kernel<<<1, 1024, 0, h->stream>>>(h->sel_mean.as<double>(), (long long)T, h->sel_max.as<double>());
+  const unsigned gridT = (unsigned)((T + 255) / 256);
+  unsigned long long* key = h->sel_key.as<unsigned long long>();
+  score_key_kernel<<<gridT, 256, 0, h->stream>>>(h->sel_var.as<double>(), h->sel_max.as<double>(), (long long)T, mode,
+                                                 (unsigned long long)seed, h->sel_score.as<double>(), key, st);
+  const int hist_grid = (int)std::min<int64_t>(gridT, 4 * h->sm_count);
+  for (int pass = 0; pass < 12; ++pass) {
+    select_hist_kernel<<<hist_grid, 256, 0, h->stream>>>(key, (long long)T, pass, st);
+    select_pick_kernel<<<1, 1, 0, h->stream>>>(pass, st);
+  }
+  select_compact_kernel<<<gridT, 256, 0, h->stream>>>(key, (long long)T, st, h->sel_okey.as<unsigned long long>(),
+                                                      h->sel_oidx.as<unsigned int>());
+  h->st.kernel_launches += 3 + 24;
+  // the k winners come back (16 B each) and are put in argsort order on the host
+  std::vector<unsigned long long> okey((size_t)k);
+  std::vector<unsigned int> oidx((size_t)k);
+  SelectState fin;
+  CK(cudaMemcpyAsync(&fin, st, sizeof fin, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(okey.data(), h->sel_okey.p, (size_t)k * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(oidx.data(), h->sel_oidx.p, (size_t)k * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (score_out) CKR(download(h, h->sel_score.as<double>(), T, 1, 1, score_out));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  if (fin.out_count != (unsigned int)k)
+    return fail(h, NNGP_ECUDA, "nngp_active_select: internal error, selected %u of %lld rows", fin.out_count, (long long)k);
+  if (mode == NNGP_SELECT_SAMPLE && fin.bad)
+    return fail(h, NNGP_EINVAL, "nngp_active_select: sampling needs finite, non-negative scores std/max(mean)");
+  std::vector<int64_t> order((size_t)k);
+  for (int64_t i = 0; i < k; ++i) order[(size_t)i] = i;
+  const bool ascending = mode == NNGP_SELECT_TOPK;   // argsort tail: ascending; Gumbel-top-k: best first
+  std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+    const bool less = okey[(size_t)a] != okey[(size_t)b] ? okey[(size_t)a] < okey[(size_t)b] : oidx[(size_t)a] < oidx[(size_t)b];
+    return ascending ? less : (a != b && !less);
+  });
+  std::vector<int64_t> out((size_t)k);
+  for (int64_t i = 0; i < k; ++i) out[(size_t)i] = (int64_t)oidx[(size_t)order[(size_t)i]];
+  CK(cudaMemcpy(idx_out, out.data(), (size_t)k * sizeof(int64_t), cudaMemcpyDefault));
+  if (n_selected_out) *n_selected_out = k;
+  return NNGP_OK;
+}
+
+int nngp_append_fit(nngp_handle* h, const double* x_new, const double* y_new, int64_t M) {
+  if (!h) return NNGP_EINVAL;
+  if (!h->fitted || !h->have_y)
+    return fail(h, NNGP_ESTATE, "nngp_append_fit: needs a model fitted by nngp_fit on this handle (the labels are kept there)");
+  if (!x_new || !y_new || M <= 0) return fail(h, NNGP_EINVAL, "nngp_append_fit: bad argument (M=%lld)", (long long)M);
+  CKR(bind_device(h));
+  const int64_t N = h->N, D = h->D;
+  DevBuf xc, yc;   // [X_old; x_new], [y_old; y_new] contiguous on the device, then an ordinary fit from device pointers
+  int rc = ensure(h, xc, (size_t)(N + M) * D * sizeof(double));
+  if (rc == NNGP_OK) rc = ensure(h, yc, (size_t)(N + M) * sizeof(double));
+  auto body = [&]() -> int {
+    CK(cudaMemcpy2DAsync(xc.p, D * sizeof(double), h->X.p, h->ldx * sizeof(double), D * sizeof(double), N,
+                         cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(yc.p, h->y.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CKR(upload_matrix(h, x_new, M, D, xc.as<double>() + N * D, D));
+    CKR(upload_matrix(h, y_new, M, 1, yc.as<double>() + N, 1));
+    CK(cudaStreamSynchronize(h->stream));
+    return nngp_fit(h, xc.as<double>(), yc.as<double>(), N + M, D);
+  };
+  if (rc == NNGP_OK) rc = body();
+  release(xc);
+  release(yc);
+  return rc;
 }
 
 // -------------------------------------------------------------------------------------------------

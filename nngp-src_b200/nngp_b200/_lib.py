@@ -65,6 +65,8 @@ EXPORTS = {
     "nngp_get_state": (C.c_int, [_P, _P, _P, _P]),
     "nngp_set_state": (C.c_int, [_P, _P, _P, _P, _I64, _I64, C.c_double]),
     "nngp_log_marginal_likelihood": (C.c_int, [_P, _DP]),
+    "nngp_active_select": (C.c_int, [_P, _P, _I64, _I64, C.c_int32, C.c_uint64, _P, C.POINTER(_I64), _P]),
+    "nngp_append_fit": (C.c_int, [_P, _P, _P, _I64]),
     "nngp_stats": (C.c_int, [_P, C.POINTER(NngpStats)]),
     "nngp_stats_reset": (C.c_int, [_P]),
     "nngp_diag_dmma_peak": (C.c_int, [_P, _DP]),
@@ -188,8 +190,14 @@ class Handle:
             raise ValueError(f"nngp_b200: y_train has {int(np.prod(ky.shape))} entries for {N} training rows")
         self._ck(self._lib.nngp_fit(self._h, xp, yp, N, D))
 
+    def _check_width(self, kx, what):
+        d = self.dims()[1]          # raises NngpError(NNGP_ESTATE) when nothing is fitted
+        if kx.ndim != 2 or kx.shape[1] != d:
+            raise ValueError(f"nngp_b200: {what} must be [rows, {d}] like the training set, got {tuple(kx.shape)}")
+
     def predict(self, x, want_var=True, mean_out=None, var_out=None):
         xp, kx = _ptr(x)
+        self._check_width(kx, "x_test")
         T = kx.shape[0]
         if mean_out is None:
             mean_out = np.empty(T, dtype=np.float64)
@@ -228,6 +236,34 @@ class Handle:
         ap, _ka = _ptr(alpha)
         N, D = kx.shape
         self._ck(self._lib.nngp_set_state(self._h, xp, lp, ap, N, D, float(lam)))
+
+    def active_select(self, x_pool, budget, biased_sample=False, seed=10, return_scores=False):
+        """Device-side ``ActiveLearner.active_test`` (active/ActiveLearner.py:43-55): rows of ``x_pool`` to label
+        next -- ``argsort(std/max(mean))[-budget:]`` or, with ``biased_sample``, a draw without replacement with
+        probability proportional to that score (Gumbel-top-k, splitmix64 stream of ``seed``)."""
+        xp, kx = _ptr(x_pool)
+        self._check_width(kx, "x_pool")
+        T = kx.shape[0]
+        k = min(int(budget), T)
+        idx = np.empty(k, dtype=np.int64)
+        n_sel = _I64()
+        scores = np.empty(T) if return_scores else None
+        self._ck(self._lib.nngp_active_select(self._h, xp, T, int(budget), 1 if biased_sample else 0, int(seed),
+                                              C.c_void_p(idx.ctypes.data), C.byref(n_sel),
+                                              C.c_void_p(scores.ctypes.data) if return_scores else None))
+        assert n_sel.value == k
+        return (idx, scores) if return_scores else idx
+
+    def append_fit(self, x_new, y_new) -> None:
+        """``merge_data`` + ``train`` of the active-learning loop (active/ActiveLearner.py:57-65,76): append labelled
+        rows to the training set held on the device and refit."""
+        xp, kx = _ptr(x_new)
+        yp, ky = _ptr(y_new)
+        self._check_width(kx, "x_new")
+        M = kx.shape[0]
+        if int(np.prod(ky.shape)) != M:
+            raise ValueError(f"x_new has {M} rows but y_new has shape {tuple(ky.shape)}")
+        self._ck(self._lib.nngp_append_fit(self._h, xp, yp, M))
 
     def log_marginal_likelihood(self) -> float:
         v = C.c_double()

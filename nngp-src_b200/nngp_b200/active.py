@@ -1,10 +1,15 @@
 """Mirror of ``active/ActiveLearner.py:14-77`` (the NNGP active-learning loop, BASELINE config C4).
 
-Host logic only -- refit-from-scratch on a growing training set with posterior-variance query selection; every
-fit / predict goes to the B200 path through ``predict.gradient_descent_mse_ensemble``.  The loop itself stays
-Python as in the reference.  Differences, both stated in DESIGN.md:
-  * the biased-sampling branch uses numpy's PCG64 instead of JAX's threefry stream (``jax.random.choice`` is not
-    reproducible without jax); the deterministic top-k branch is the one parity is checked on;
+Refit-from-scratch on a growing training set with posterior-variance query selection (SURVEY.md section 8a row
+a8, 8f-3).  The loop stays Python as in the reference; the two steps inside it run on the device through the C ABI:
+  * ``active_test``  -> ``nngp_active_select``: predict the pool, score = std / max(mean), exact top-k (or
+    Gumbel-top-k sampling) by radix select on the GPU; only the selected row numbers come back;
+  * ``train`` after a merge -> ``nngp_append_fit``: the selected rows are appended to the training set that already
+    sits in HBM and the model is refit (same arithmetic as a fresh fit -- bitwise -- without re-sending X_train).
+Differences, both stated in DESIGN.md:
+  * the biased-sampling branch draws from a splitmix64 stream instead of JAX's threefry stream
+    (``jax.random.choice`` is not reproducible without jax); the deterministic top-k branch is the one parity is
+    checked on;
   * reporting is the symmetric q-error summary instead of ``util.PredictionStatistics`` (plotting deps).
 """
 from __future__ import annotations
@@ -32,6 +37,17 @@ class ActiveLearner(object):
             self.test(predict_fn, X_test, Y_test, None)
         return predict_fn
 
+    def retrain(self, kernel_fn, predict_fn, X_train, Y_train, X_delta, Y_delta):
+        """``self.train(kernel_fn, X_train, Y_train)`` (ActiveLearner.py:76) where X_train = [old; X_delta]: the fitted
+        engine of ``predict_fn`` appends the new rows on the device and refits; the returned predict_fn is bound to it."""
+        if not hasattr(predict_fn, "engine"):
+            return self.train(kernel_fn, X_train, Y_train)
+        h = predict_fn.engine(self.kernel_type)
+        h.append_fit(X_delta, Y_delta)
+        kernel_fn = _batch.batch(kernel_fn, device_count=0, batch_size=0)
+        return _predict.gradient_descent_mse_ensemble(kernel_fn, X_train, Y_train, diag_reg=1e-3,
+                                                      _fitted_engines={self.kernel_type: h})
+
     def test(self, predict_fn, X_val, Y_val, query_infos_val=None, kernel_type="nngp", compute_cov=True):  # :33-40
         pred_mean, pred_cov = predict_fn(x_test=X_val, get=kernel_type, compute_cov=compute_cov)
         errors = pred_mean - Y_val
@@ -44,6 +60,12 @@ class ActiveLearner(object):
         return rec
 
     def active_test(self, predict_fn, X_test, kernel_type="nngp"):                          # ActiveLearner.py:43-55
+        if hasattr(predict_fn, "engine"):      # device path: selection happens next to the posterior, on the GPU
+            return predict_fn.engine(kernel_type).active_select(X_test, self.budget, self.biased_sample, seed=10)
+        return self._active_test_host(predict_fn, X_test, kernel_type)
+
+    def _active_test_host(self, predict_fn, X_test, kernel_type="nngp"):
+        """The same selection with numpy on the host (any predict_fn; used by the tests as a cross-check)."""
         pred_mean, pred_cov = predict_fn(x_test=X_test, get=kernel_type, compute_cov=True)
         pred_std = np.sqrt(np.diag(pred_cov))
         pred_std = pred_std / np.max(pred_mean, 0)
@@ -69,8 +91,9 @@ class ActiveLearner(object):
         for i in range(self.active_iters):
             select_indices = self.active_test(predict_fn, X_test, self.kernel_type)
             self._say("Active Iteration {}: Selection {}".format(i, select_indices.shape[0]))
+            X_delta, Y_delta = X_test[select_indices], Y_test[select_indices]
             X_train, Y_train, X_test, Y_test = self.merge_data(select_indices, X_train, Y_train, X_test, Y_test)
             self._say("# Training samples: {}".format(X_train.shape[0]))
-            predict_fn = self.train(kernel_fn, X_train, Y_train)
+            predict_fn = self.retrain(kernel_fn, predict_fn, X_train, Y_train, X_delta, Y_delta)
             self.test(predict_fn, X_val, Y_val, query_infos_val, self.kernel_type)
         return predict_fn, X_train, Y_train

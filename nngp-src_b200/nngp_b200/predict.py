@@ -57,7 +57,8 @@ class LazyCovariance:
 
 
 def gradient_descent_mse_ensemble(kernel_fn, x_train, y_train, learning_rate=1.0, diag_reg=0.0,
-                                  diag_reg_absolute_scale=False, trace_axes=(-1,), **kernel_fn_train_train_kwargs):
+                                  diag_reg_absolute_scale=False, trace_axes=(-1,), _fitted_engines=None,
+                                  **kernel_fn_train_train_kwargs):
     if not isinstance(kernel_fn, KernelFn):
         raise NotImplementedError("gradient_descent_mse_ensemble: kernel_fn must come from nngp_b200.stax.serial")
     if kernel_fn_train_train_kwargs:
@@ -71,7 +72,9 @@ def gradient_descent_mse_ensemble(kernel_fn, x_train, y_train, learning_rate=1.0
         raise NotImplementedError("only a single regression output (y_train of shape [N] or [N,1]) is supported")
     if y_shape[0] != x_train.shape[0]:
         raise ValueError(f"x_train has {x_train.shape[0]} rows but y_train has {y_shape[0]}")
-    state = {}                                 # one cached fit per `get`, like nt's lru_cache'd predict_inf
+    state = dict(_fitted_engines or {})        # one cached fit per `get`, like nt's lru_cache'd predict_inf
+                                               # (_fitted_engines: handles already fitted on exactly this data --
+                                               #  the device-side append of the active-learning loop, active.py)
 
     def _fitted(get="nngp"):
         if get not in state:

@@ -158,6 +158,32 @@ def active_select(mean, std, budget: int):
     return np.argsort(s)[-num:]
 
 
+def splitmix_uniform(seed: int, n: int):
+    """u_i in (0,1), i = 0..n-1: splitmix64 of (seed, i) -- the counter-based stream the device sampler uses."""
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + (np.arange(n, dtype=np.uint64) + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return ((z >> np.uint64(12)).astype(np.float64) + 0.5) * 2.0 ** -52     # 52 bits: the +0.5 is exact
+
+
+def active_sample(mean, std, budget: int, seed: int = 10):
+    """Biased-sampling branch of ActiveLearner.active_test (active/ActiveLearner.py:49-53, biased_sample=True):
+    `budget` draws without replacement with p_i = s_i / sum(s), restated as Gumbel-top-k (the construction
+    jax.random.choice itself uses): the rows with the largest log(s_i) - log(-log(u_i)), best first.  The uniform
+    stream is splitmix64, not JAX's threefry, so this branch is UNPINNED against the reference."""
+    s = np.asarray(std).reshape(-1) / np.max(mean, 0)
+    if not np.all(np.isfinite(s)) or np.any(s < 0):
+        raise ValueError("sampling needs finite, non-negative scores")
+    num = budget if s.shape[0] > budget else s.shape[0]
+    u = splitmix_uniform(seed, s.shape[0])
+    with np.errstate(divide="ignore"):
+        key = np.where(s > 0, np.log(s) - np.log(-np.log(u)), -np.inf)
+    order = np.lexsort((np.arange(s.shape[0]), key))      # ascending by (key, index)
+    return order[::-1][:num]
+
+
 def q_error_stats(pred_log2, true_log2):
     """Symmetric q-error 2**|err| summary (util.py:152-167 prints the signed ratio 2**err)."""
     qe = 2.0 ** np.abs(np.asarray(pred_log2).reshape(-1) - np.asarray(true_log2).reshape(-1))

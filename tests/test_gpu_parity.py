@@ -368,6 +368,104 @@ def test_active_learning_round_selects_the_oracle_rows(lib, synth):
     assert x_end.shape == (500, 16) and len(al.history) == 2
 
 
+def test_device_selection_is_the_argsort_tail(lib, synth):
+    """nngp_active_select == np.argsort(std / max(mean))[-budget:] (ActiveLearner.py:46-54): same rows
+    as the oracle, returned in ascending score order, ties (duplicated pool rows) resolved like a stable sort, and
+    budget >= T returns every row."""
+    xtr, ytr, xpool, _ = synth.make_problem(1024, 5000, 32)
+    xpool[100:164] = xpool[4000:4064]                     # 64 exact ties
+    h = lib.Handle()
+    h.fit(xtr, ytr)
+    idx, score = h.active_select(xpool, 300, return_scores=True)
+    assert idx.dtype == np.int64 and idx.shape == (300,)
+    assert np.array_equal(idx, np.argsort(score, kind="stable")[-300:])          # exact radix select, exact order
+    ref = oracle.Fit(xtr, ytr)
+    rm, rv = ref.predict(xpool)
+    ref_score = np.sqrt(rv) / np.max(rm)
+    assert relmax(score, ref_score) < 1e-7
+    want = oracle.active_select(rm[:, None], np.sqrt(rv), 300)
+    # same rows as the oracle, up to members whose scores are equal within the parity tolerance of the scores
+    diff = set(idx.tolist()) ^ set(want.tolist())
+    cut = np.sort(ref_score)[-300]
+    assert all(abs(ref_score[i] - cut) <= 1e-7 * cut for i in diff), sorted(diff)
+    # a tie straddling nothing: the duplicated rows have identical device scores
+    assert np.array_equal(score[100:164], score[4000:4064])
+    # budget >= T: every row, still in argsort order; tiny pools work too
+    idx_all = h.active_select(xpool[:77], 500)
+    s77 = h.active_select(xpool[:77], 500, return_scores=True)[1]
+    assert np.array_equal(idx_all, np.argsort(s77, kind="stable"))
+    assert np.array_equal(h.active_select(xpool[:1], 3), [0])
+    # the k = 1 and k = T - 1 ends of the radix select
+    assert h.active_select(xpool, 1)[0] == np.argsort(score, kind="stable")[-1]
+    assert np.array_equal(h.active_select(xpool, 4999), np.argsort(score, kind="stable")[-4999:])
+
+
+def test_device_sampling_is_gumbel_top_k(lib, synth):
+    """biased_sample=True branch (ActiveLearner.py:49-53) on the device: Gumbel-top-k over log(score) with the
+    oracle's splitmix64 stream -> the same draw as the oracle's restatement (log() may differ in the last ulp, so a
+    draw whose keys are within 1e-12 of the cut may swap), deterministic per seed, no repeats."""
+    xtr, ytr, xpool, _ = synth.make_problem(512, 3000, 16)
+    h = lib.Handle()
+    h.fit(xtr, ytr)
+    idx, score = h.active_select(xpool, 200, biased_sample=True, seed=10, return_scores=True)
+    assert len(set(idx.tolist())) == 200 and idx.min() >= 0 and idx.max() < 3000
+    assert np.array_equal(idx, h.active_select(xpool, 200, biased_sample=True, seed=10))
+    assert not np.array_equal(idx, h.active_select(xpool, 200, biased_sample=True, seed=11))
+    want = oracle.active_sample(np.ones(1), score, 200, seed=10)          # score is already std / max(mean)
+    assert len(set(idx.tolist()) ^ set(want.tolist())) <= 2
+    assert np.mean(idx == want) > 0.97                                    # draw order too
+    # larger scores are drawn more often: mean score of the draw exceeds the pool's
+    assert score[idx].mean() > score.mean()
+
+
+def test_append_fit_is_bitwise_a_fresh_fit(lib, synth):
+    """nngp_append_fit (merge_data + train, ActiveLearner.py:57-65,76) == nngp_fit on the stacked arrays, bit for bit;
+    needs the labels of a previous nngp_fit on the same handle."""
+    xtr, ytr, xpool, ypool = synth.make_problem(700, 300, 24)
+    h = lib.Handle()
+    h.fit(xtr, ytr)
+    h.append_fit(xpool[:150], ypool[:150])
+    h.append_fit(xpool[150:151], ypool[150:151])
+    ref = lib.Handle()
+    ref.fit(np.vstack([xtr, xpool[:151]]), np.concatenate([ytr, ypool[:151]]))
+    a, b = h.get_state(), ref.get_state()
+    assert h.dims() == ref.dims() and h.dims()[0] == 851
+    for k in ("x", "l", "alpha"):
+        assert np.array_equal(a[k], b[k]), k
+    assert h.log_marginal_likelihood() == ref.log_marginal_likelihood()
+    with pytest.raises(ValueError):
+        h.append_fit(xpool[:3, :5], ypool[:3])
+    h2 = lib.Handle()
+    st = ref.get_state()
+    h2.set_state(st["x"], st["l"], st["alpha"], st["lambda"])
+    with pytest.raises(lib.NngpError):                                    # imported state carries no labels
+        h2.append_fit(xpool[:3], ypool[:3])
+
+
+def test_active_learner_device_path_equals_host_path(lib, synth):
+    """ActiveLearner.active_train through nngp_active_select / nngp_append_fit ends with exactly the training set the
+    host-side restatement of the loop (numpy argsort + fresh fits) ends with."""
+    from nngp_b200 import stax
+    from nngp_b200.active import ActiveLearner
+    xtr, ytr, xpool, ypool = synth.make_problem(300, 1200, 16)
+    _, _, kernel_fn = stax.serial(stax.Dense(512), stax.Relu(), stax.Dense(1))
+    al = ActiveLearner(budget=128, active_iters=3, verbose=False)
+    pf, x_end, y_end = al.active_train(kernel_fn, xtr, ytr[:, None], xpool, ypool[:, None], xpool[:40], ypool[:40, None])
+    host = ActiveLearner(budget=128, active_iters=3, verbose=False)
+    xh, yh, xp, yp = xtr, ytr[:, None], xpool, ypool[:, None]
+    for _ in range(3):
+        pfh = host.train(kernel_fn, xh, yh)
+        sel = host._active_test_host(pfh, xp)
+        xh, yh, xp, yp = host.merge_data(sel, xh, yh, xp, yp)
+    assert x_end.shape == (300 + 3 * 128, 16)
+    assert np.array_equal(np.sort(x_end.view(np.uint64), axis=0), np.sort(xh.view(np.uint64), axis=0))
+    # the returned predict_fn is bound to the appended engine: same predictions as a fresh fit on the final set
+    fresh = host.train(kernel_fn, x_end, y_end)
+    m1, c1 = pf(x_test=xpool[:64], get="nngp", compute_cov=True)
+    m2, c2 = fresh(x_test=xpool[:64], get="nngp", compute_cov=True)
+    assert np.array_equal(m1, m2) and np.array_equal(np.diag(c1), np.diag(c2))
+
+
 def test_error_conventions(lib, synth):
     h = lib.Handle()
     xtr, ytr, xte, _ = synth.make_problem(64, 8, 8)

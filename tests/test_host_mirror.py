@@ -23,7 +23,16 @@ class FakeHandle:
     def fit(self, x, y):
         FakeHandle.fits += 1
         cls = oracle.FitNTK if self.kt == "ntk" else oracle.Fit
+        self.x_, self.y_ = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64).reshape(-1)
         self.fit_ = cls(x, y, self.spec.depth, self.spec.sigma_w, self.spec.sigma_b, self.diag_reg, self.absolute)
+
+    def active_select(self, x_pool, budget, biased_sample=False, seed=10):          # nngp_active_select
+        mean, var = self.fit_.predict(x_pool, True)
+        pick = oracle.active_sample if biased_sample else oracle.active_select
+        return pick(mean[:, None], np.sqrt(var), budget, *([seed] if biased_sample else []))
+
+    def append_fit(self, x_new, y_new):                                             # nngp_append_fit
+        self.fit(np.vstack([self.x_, x_new]), np.concatenate([self.y_, np.asarray(y_new).reshape(-1)]))
 
     def predict(self, x, want_var=True):
         return self.fit_.predict(x, want_var)

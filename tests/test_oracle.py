@@ -125,6 +125,29 @@ def test_active_selection_rule():
     assert sorted(o.active_select(mean, std, 10)) == [0, 1, 2, 3]
 
 
+def test_active_sampling_restatement():
+    """Gumbel-top-k restatement of the biased_sample branch (ActiveLearner.py:49-53): splitmix64 known answer, no
+    repeats, determinism, zero-probability rows never drawn, inclusion frequencies like numpy's choice(p=...)."""
+    u = o.splitmix_uniform(0, 4)
+    assert int(u[0] * 2.0 ** 52 - 0.5) == 0xE220A8397B1DCDAF >> 12      # first splitmix64 output for state 0
+    assert np.all((u > 0) & (u < 1))
+    rng = np.random.default_rng(0)
+    s = rng.random(40) + 0.01
+    s[7] = 0.0
+    a = o.active_sample(np.ones(1), s, 5, seed=3)
+    assert len(set(a.tolist())) == 5 and np.array_equal(a, o.active_sample(np.ones(1), s, 5, seed=3))
+    cnt, cnt_np = np.zeros(40), np.zeros(40)
+    p = s / s.sum()
+    for seed in range(3000):
+        cnt[o.active_sample(np.ones(1), s, 5, seed)] += 1
+        cnt_np[np.random.default_rng(seed).choice(40, 5, replace=False, p=p)] += 1
+    assert cnt[7] == 0
+    assert np.max(np.abs(cnt - cnt_np)) / 3000 < 0.03 and np.corrcoef(cnt, cnt_np)[0, 1] > 0.98
+    assert sorted(o.active_sample(np.ones(1), s[:4], 10, seed=1).tolist()) == [0, 1, 2, 3]
+    with pytest.raises(ValueError):
+        o.active_sample(np.ones(1), -s, 3)
+
+
 def test_device_atan2_algorithm_in_numpy():
     """The Gram epilogue's atan2_pos (csrc/gemm_nt.cuh) restated in numpy with the SAME coefficients (parsed from
     the source): <= 1 ulp-level agreement with libm and with 40-digit mpmath, incl. the axes and the origin."""

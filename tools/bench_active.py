@@ -41,10 +41,12 @@ def main():
     al = ActiveLearner(budget=a.budget, active_iters=0, verbose=False)
     rounds, agree = [], []
     t_all = time.perf_counter()
+    pf, xd, yd = None, None, None
     while True:
         t0 = time.perf_counter()
-        pf = al.train(kernel_fn, xtr, ytr)
-        idx = al.active_test(pf, xpool)                      # first predict_fn call = fit + predict of the pool
+        # first round: fit from host arrays; later rounds: nngp_append_fit of the selected rows (device-side merge)
+        pf = al.train(kernel_fn, xtr, ytr) if pf is None else al.retrain(kernel_fn, pf, xtr, ytr, xd, yd)
+        idx = al.active_test(pf, xpool)                      # nngp_active_select: predict the pool + top-k on the GPU
         dt = time.perf_counter() - t0
         st = pf.engine().stats()
         rounds.append({"n_train": int(xtr.shape[0]), "pool": int(xpool.shape[0]), "seconds": dt,
@@ -57,6 +59,7 @@ def main():
             agree.append(bool(set(want.tolist()) == set(np.asarray(idx).tolist())))
         if xtr.shape[0] + a.budget > a.n_max or xpool.shape[0] <= a.budget:
             break
+        xd, yd = xpool[idx], ypool[idx]
         xtr, ytr, xpool, ypool = al.merge_data(idx, xtr, ytr, xpool, ypool)
     out = {"workload": "C4 active-learning loop", "n0": a.n0, "budget": a.budget, "n_max": a.n_max, "pool": a.pool,
            "dim": a.dim, "depth": a.depth, "rounds": len(rounds), "total_seconds": time.perf_counter() - t_all,
