@@ -175,6 +175,10 @@ NNGP_API int nngp_log_marginal_likelihood(nngp_handle* h, double* lml_out);
 NNGP_API int nngp_active_select(nngp_handle* h, const double* x_pool, int64_t T, int64_t budget, int32_t mode,
                                 uint64_t seed, int64_t* idx_out, int64_t* n_selected_out, double* score_out);
 NNGP_API int nngp_append_fit(nngp_handle* h, const double* x_new, const double* y_new, int64_t M);
+/* Optional: size the handle's device buffers once for the largest training set / pool the loop will reach
+ * (n_train_max rows of `dim` features, n_test_max rows per predict / select call; 0 = fit-side only), so that
+ * no multi-GB cudaFree / cudaMalloc happens between rounds.  Call before nngp_fit: it drops a fitted model. */
+NNGP_API int nngp_reserve(nngp_handle* h, int64_t n_train_max, int64_t dim, int64_t n_test_max);
 
 NNGP_API int nngp_stats(nngp_handle* h, nngp_stats_t* out);
 NNGP_API int nngp_stats_reset(nngp_handle* h);

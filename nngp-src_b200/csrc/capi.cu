@@ -69,6 +69,7 @@ struct nngp_handle {
   bool have_lml = false;
   DevBuf X, q, L, alpha;
   DevBuf y;       // raw labels of the last nngp_fit (kept for nngp_append_fit)
+  DevBuf app_x, app_y;  // nngp_append_fit staging: [X; X_new], [y; y_new]
   bool have_y = false;
   DevBuf flags;   // int[2]: {potrf info, non-finite input}
   DevBuf lam_d;   // double[4]: {lambda, sum log diag L, z^T z, spare}
@@ -117,8 +118,17 @@ int fail(nngp_handle* h, int code, const char* fmt, ...) {
 
 int ensure(nngp_handle* h, DevBuf& b, size_t bytes) {
   if (bytes <= b.cap && b.p) return NNGP_OK;
+  const bool regrow = b.p != nullptr;
   if (b.p) { CK(cudaStreamSynchronize(h->stream)); CK(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
   if (bytes == 0) bytes = 256;
+  // A buffer that grows again (the active-learning loop: N += budget every round) gets 25 % head-room, so that
+  // multi-GB cudaFree / cudaMalloc pairs do not recur every round; exact size if that does not fit.
+  if (regrow && bytes >= (64u << 20)) {
+    const size_t roomy = bytes + bytes / 4;
+    if (cudaMalloc(&b.p, roomy) == cudaSuccess) { b.cap = roomy; return NNGP_OK; }
+    b.p = nullptr;
+    cudaGetLastError();
+  }
   cudaError_t e = cudaMalloc(&b.p, bytes);
   if (e != cudaSuccess) {
     b.p = nullptr;
@@ -637,7 +647,7 @@ void nngp_destroy(nngp_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->X, &h->q, &h->L, &h->alpha, &h->flags, &h->lam_d, &h->xt, &h->qt, &h->kss,
-                    &h->blk, &h->mean_d, &h->var_d, &h->ssq, &h->sync_ints, &h->Mmat, &h->Kdd, &h->blk2, &h->cross, &h->partial, &h->mean_partial, &h->ka, &h->kb, &h->kqa, &h->kqb, &h->kout, &h->y, &h->sel_mean, &h->sel_var, &h->sel_score, &h->sel_key,
+                    &h->blk, &h->mean_d, &h->var_d, &h->ssq, &h->sync_ints, &h->Mmat, &h->Kdd, &h->blk2, &h->cross, &h->partial, &h->mean_partial, &h->ka, &h->kb, &h->kqa, &h->kqb, &h->kout, &h->y, &h->app_x, &h->app_y, &h->sel_mean, &h->sel_var, &h->sel_score, &h->sel_key,
                     &h->sel_state, &h->sel_okey, &h->sel_oidx, &h->sel_max})
     release(*b);
   for (auto& r : h->pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -848,6 +858,41 @@ int nngp_active_select(nngp_handle* h, const double* x_pool, int64_t T, int64_t 
   return NNGP_OK;
 }
 
+int nngp_reserve(nngp_handle* h, int64_t n_train_max, int64_t dim, int64_t n_test_max) {
+  if (!h) return NNGP_EINVAL;
+  if (n_train_max <= 0 || dim <= 0 || n_test_max < 0 || n_train_max > 65535LL * GEMM_BM)
+    return fail(h, NNGP_EINVAL, "nngp_reserve: bad argument (n_train_max=%lld dim=%lld n_test_max=%lld)",
+                (long long)n_train_max, (long long)dim, (long long)n_test_max);
+  CKR(bind_device(h));
+  drop_fit(h);   // growing a buffer does not keep its contents
+  const int64_t N = n_train_max, T = n_test_max;
+  const int64_t ldx = round_up(dim, 2), ldl = round_up(N, 16);
+  CKR(ensure(h, h->X, (size_t)N * ldx * 8));
+  CKR(ensure(h, h->q, (size_t)N * 8));
+  CKR(ensure(h, h->y, (size_t)N * 8));
+  CKR(ensure(h, h->app_x, (size_t)N * dim * 8));
+  CKR(ensure(h, h->app_y, (size_t)N * 8));
+  CKR(ensure(h, h->L, (size_t)(N + 1) * ldl * 8));
+  CKR(ensure(h, h->alpha, (size_t)ldl * 8));
+  if (T > 0) {   // the row-block workspace of nngp_predict / nngp_active_select at (N, T)
+    const int64_t wave_rows = 2LL * h->sm_count * GEMM_BM;
+    int64_t cap_rows = h->cfg.max_block_bytes / (ldl * 8);
+    if (cap_rows >= wave_rows) cap_rows = cap_rows / wave_rows * wave_rows;
+    cap_rows = std::min<int64_t>(std::max<int64_t>(cap_rows, GEMM_BM), 65535LL * GEMM_BM);
+    const int64_t TB = std::min<int64_t>(round_up(T, 2), cap_rows);
+    const int64_t col_tiles = (N + GEMM_BN - 1) / GEMM_BN;
+    CKR(ensure(h, h->xt, (size_t)TB * ldx * 8));
+    CKR(ensure(h, h->qt, (size_t)TB * 8));
+    CKR(ensure(h, h->kss, (size_t)TB * 8));
+    CKR(ensure(h, h->blk, (size_t)TB * ldl * 8));
+    CKR(ensure(h, h->mean_partial, (size_t)TB * 2 * col_tiles * 8));
+    CKR(ensure(h, h->mean_d, (size_t)T * 8));
+    CKR(ensure(h, h->var_d, (size_t)T * 8));
+    for (DevBuf* b : {&h->sel_mean, &h->sel_var, &h->sel_score, &h->sel_key}) CKR(ensure(h, *b, (size_t)T * 8));
+  }
+  return NNGP_OK;
+}
+
 int nngp_append_fit(nngp_handle* h, const double* x_new, const double* y_new, int64_t M) {
   if (!h) return NNGP_EINVAL;
   if (!h->fitted || !h->have_y)
@@ -855,7 +900,9 @@ int nngp_append_fit(nngp_handle* h, const double* x_new, const double* y_new, in
   if (!x_new || !y_new || M <= 0) return fail(h, NNGP_EINVAL, "nngp_append_fit: bad argument (M=%lld)", (long long)M);
   CKR(bind_device(h));
   const int64_t N = h->N, D = h->D;
-  DevBuf xc, yc;   // [X_old; x_new], [y_old; y_new] contiguous on the device, then an ordinary fit from device pointers
+  // [X_old; x_new], [y_old; y_new] contiguous on the device, then an ordinary fit from device pointers
+  DevBuf& xc = h->app_x;
+  DevBuf& yc = h->app_y;
   int rc = ensure(h, xc, (size_t)(N + M) * D * sizeof(double));
   if (rc == NNGP_OK) rc = ensure(h, yc, (size_t)(N + M) * sizeof(double));
   auto body = [&]() -> int {
@@ -868,8 +915,6 @@ int nngp_append_fit(nngp_handle* h, const double* x_new, const double* y_new, in
     return nngp_fit(h, xc.as<double>(), yc.as<double>(), N + M, D);
   };
   if (rc == NNGP_OK) rc = body();
-  release(xc);
-  release(yc);
   return rc;
 }
 

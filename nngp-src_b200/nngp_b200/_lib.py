@@ -67,6 +67,7 @@ EXPORTS = {
     "nngp_log_marginal_likelihood": (C.c_int, [_P, _DP]),
     "nngp_active_select": (C.c_int, [_P, _P, _I64, _I64, C.c_int32, C.c_uint64, _P, C.POINTER(_I64), _P]),
     "nngp_append_fit": (C.c_int, [_P, _P, _P, _I64]),
+    "nngp_reserve": (C.c_int, [_P, _I64, _I64, _I64]),
     "nngp_stats": (C.c_int, [_P, C.POINTER(NngpStats)]),
     "nngp_stats_reset": (C.c_int, [_P]),
     "nngp_diag_dmma_peak": (C.c_int, [_P, _DP]),
@@ -264,6 +265,10 @@ class Handle:
         if int(np.prod(ky.shape)) != M:
             raise ValueError(f"x_new has {M} rows but y_new has shape {tuple(ky.shape)}")
         self._ck(self._lib.nngp_append_fit(self._h, xp, yp, M))
+
+    def reserve(self, n_train_max, dim, n_test_max=0) -> None:
+        """Pre-size the device buffers for the largest problem an active-learning loop will reach (before ``fit``)."""
+        self._ck(self._lib.nngp_reserve(self._h, int(n_train_max), int(dim), int(n_test_max)))
 
     def log_marginal_likelihood(self) -> float:
         v = C.c_double()

@@ -30,9 +30,10 @@ class ActiveLearner(object):
         self._say = print if verbose else (lambda *a, **k: None)
         self.history = []
 
-    def train(self, kernel_fn, X_train, Y_train, X_test=None, Y_test=None):                 # ActiveLearner.py:23-31
+    def train(self, kernel_fn, X_train, Y_train, X_test=None, Y_test=None, _reserve=None):  # ActiveLearner.py:23-31
         kernel_fn = _batch.batch(kernel_fn, device_count=0, batch_size=0)
-        predict_fn = _predict.gradient_descent_mse_ensemble(kernel_fn, X_train, Y_train, diag_reg=1e-3)
+        predict_fn = _predict.gradient_descent_mse_ensemble(kernel_fn, X_train, Y_train, diag_reg=1e-3,
+                                                            _reserve=_reserve)
         if X_test is not None and Y_test is not None:
             self.test(predict_fn, X_test, Y_test, None)
         return predict_fn
@@ -86,7 +87,10 @@ class ActiveLearner(object):
 
     def active_train(self, kernel_fn, X_train, Y_train, X_test, Y_test, X_val, Y_val, query_infos_val=None):  # :67-77
         self._say("# Initial Training samples: {}".format(X_train.shape[0]))
-        predict_fn = self.train(kernel_fn, X_train, Y_train)
+        # the loop's final sizes are known up front: size the device buffers once (nngp_reserve)
+        grow = min(self.active_iters * self.budget, X_test.shape[0])
+        predict_fn = self.train(kernel_fn, X_train, Y_train,
+                                _reserve=(X_train.shape[0] + grow, max(X_test.shape[0], X_val.shape[0])))
         self.test(predict_fn, X_val, Y_val, query_infos_val, self.kernel_type)
         for i in range(self.active_iters):
             select_indices = self.active_test(predict_fn, X_test, self.kernel_type)

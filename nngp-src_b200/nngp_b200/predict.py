@@ -57,7 +57,7 @@ class LazyCovariance:
 
 
 def gradient_descent_mse_ensemble(kernel_fn, x_train, y_train, learning_rate=1.0, diag_reg=0.0,
-                                  diag_reg_absolute_scale=False, trace_axes=(-1,), _fitted_engines=None,
+                                  diag_reg_absolute_scale=False, trace_axes=(-1,), _fitted_engines=None, _reserve=None,
                                   **kernel_fn_train_train_kwargs):
     if not isinstance(kernel_fn, KernelFn):
         raise NotImplementedError("gradient_descent_mse_ensemble: kernel_fn must come from nngp_b200.stax.serial")
@@ -80,6 +80,8 @@ def gradient_descent_mse_ensemble(kernel_fn, x_train, y_train, learning_rate=1.0
         if get not in state:
             h = runtime.new_handle(kernel_fn.spec, diag_reg=diag_reg, diag_reg_absolute=diag_reg_absolute_scale,
                                    kernel_type=get)
+            if _reserve is not None and hasattr(h, "reserve"):      # (n_train_max, n_test_max) of an AL loop
+                h.reserve(max(int(_reserve[0]), x_train.shape[0]), x_train.shape[1], int(_reserve[1]))
             h.fit(x_train, y_arr)          # raises ValueError / LinAlgError through the C-ABI error codes
             state[get] = h
         return state[get]

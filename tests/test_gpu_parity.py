@@ -423,6 +423,7 @@ def test_append_fit_is_bitwise_a_fresh_fit(lib, synth):
     needs the labels of a previous nngp_fit on the same handle."""
     xtr, ytr, xpool, ypool = synth.make_problem(700, 300, 24)
     h = lib.Handle()
+    h.reserve(900, 24, 300)                       # nngp_reserve: buffers sized once for the whole loop
     h.fit(xtr, ytr)
     h.append_fit(xpool[:150], ypool[:150])
     h.append_fit(xpool[150:151], ypool[150:151])
@@ -440,6 +441,9 @@ def test_append_fit_is_bitwise_a_fresh_fit(lib, synth):
     h2.set_state(st["x"], st["l"], st["alpha"], st["lambda"])
     with pytest.raises(lib.NngpError):                                    # imported state carries no labels
         h2.append_fit(xpool[:3], ypool[:3])
+    h.reserve(2000, 24)                                                   # re-sizing drops the fitted model
+    with pytest.raises(lib.NngpError):
+        h.predict(xpool[:3])
 
 
 def test_active_learner_device_path_equals_host_path(lib, synth):
