@@ -68,6 +68,7 @@ struct nngp_handle {
   double lml_terms[2] = {0.0, 0.0};  // {sum log diag(L), y^T (K+lambda I)^-1 y}; valid after nngp_fit
   bool have_lml = false;
   DevBuf X, q, L, alpha;
+  DevBuf Linv;    // inv(L_JJ) of every 64 x 64 diagonal block of L (trtri_diag_kernel), operand of the solves' diagonal step
   DevBuf y;       // raw labels of the last nngp_fit (kept for nngp_append_fit)
   DevBuf app_x, app_y;  // nngp_append_fit staging: [X; X_new], [y; y_new]
   bool have_y = false;
@@ -418,7 +419,7 @@ int run_trsm_rlt(nngp_handle* h, double* B, int64_t ldb, int64_t rows, const dou
 
 // Same solve as run_trsm_rlt plus the variance, as ONE persistent kernel (trsm_fused.cuh).
 int run_trsm_fused(nngp_handle* h, double* B, int64_t ldb, int64_t rows, const double* L, int64_t ldl, int64_t N,
-                   const double* kss, double* var) {
+                   const double* Linv, const double* kss, double* var) {
   TrsmFusedParams p{};
   p.B = B; p.ldb = ldb; p.rows = (int)rows; p.L = L; p.ldl = ldl; p.N = (int)N;
   p.row_tiles = (int)((rows + GEMM_BM - 1) / GEMM_BM);
@@ -429,16 +430,17 @@ int run_trsm_fused(nngp_handle* h, double* B, int64_t ldb, int64_t rows, const d
   p.counter = h->sync_ints.as<int>();
   p.progress = h->sync_ints.as<int>() + 1;
   p.ssq = h->ssq.as<double>(); p.kss = kss; p.var = var;
-  CUtensorMap tmB, tmL;
+  CUtensorMap tmB, tmL, tmW;
   CKR(get_tmap(h, B, rows, N, ldb, GEMM_BM, &tmB));
   CKR(get_tmap(h, L, N, N, ldl, GEMM_BN, &tmL));
+  CKR(get_tmap(h, Linv, round_up(N, NB), NB, NB, GEMM_BN, &tmW));
   const long long total = (long long)p.row_tiles * p.col_blocks;
   int grid = (int)std::min<long long>(total, 2LL * h->sm_count);
   if (p.row_tiles < grid) grid = p.row_tiles;  // fewer row tiles than CTA slots: one CTA per row tile
   p.static_sched = (p.row_tiles % grid == 0) ? 1 : 0;
   cudaEvent_t ev;
   class_begin(h, EV_GEMM, &ev);
-  trsm_fused_kernel<<<grid, GEMM_THREADS, TF_SMEM_BYTES, h->stream>>>(tmB, tmL, p);
+  trsm_fused_kernel<<<grid, GEMM_THREADS, TF_SMEM_BYTES, h->stream>>>(tmB, tmL, tmW, p);
   class_end(h, EV_GEMM, ev);
   CK(cudaGetLastError());
   h->st.kernel_launches++;
@@ -447,22 +449,24 @@ int run_trsm_fused(nngp_handle* h, double* B, int64_t ldb, int64_t rows, const d
   return NNGP_OK;
 }
 
-// Small-batch variant of the same solve (identical arithmetic, see solve_row_left_packed): right-looking over the
-// column blocks, so every step exposes (N - j)/64 column tiles of parallelism even when there is a single row
-// tile -- the persistent left-looking kernel would walk the N/64 blocks of a row tile sequentially on one SM.
-// Used when the block has few row tiles (serving a handful of queries, the forest workload).
+// Small-batch variant of the same solve (identical arithmetic: same DMMA order in the updates, same diagonal
+// step and epilogue, see diag_epilogue): right-looking over the column blocks, so every step exposes (N - j)/64
+// column tiles of parallelism even when there is a single row tile -- the persistent left-looking kernel would walk
+// the N/64 blocks of a row tile sequentially on one SM.  Used when the block has few row tiles (serving a handful
+// of queries, the forest workload).
 int run_trsm_right(nngp_handle* h, double* B, int64_t ldb, int64_t rows, const double* L, int64_t ldl, int64_t N,
-                   const double* kss, double* var) {
-  MatView Bv{B, rows, N, ldb}, Lv{L, N, N, ldl};
+                   const double* Linv, const double* kss, double* var) {
+  MatView Bv{B, rows, N, ldb}, Lv{L, N, N, ldl}, Wv{Linv, round_up(N, NB), NB, NB};
   const int col_blocks = (int)((N + NB - 1) / NB);
-  const int grid = (int)((rows + 127) / 128);
   if (var) CKR(ensure(h, h->ssq, (size_t)rows * sizeof(double)));
   for (int J = 0; J < col_blocks; ++J) {
     const int64_t j0 = (int64_t)J * NB;
     const int64_t nb = std::min<int64_t>(NB, N - j0);
-    trsm_rows_var_kernel<<<grid, 256, TRSMV_SMEM_BYTES, h->stream>>>(B + j0, ldb, (int)rows, L + j0 * ldl + j0, ldl, (int)nb, J,
-                                                                    col_blocks, h->ssq.as<double>(), kss, var);
-    h->st.kernel_launches++;
+    GemmParams p{};   // V[:, J] = R[:, J] * inv(L_JJ)^T in place (+ running sum of squares / variance)
+    p.M = (int)rows; p.N = (int)nb; p.ktiles = NB / GEMM_BK;
+    p.C = B + j0; p.ldc = ldb;
+    p.ssq = h->ssq.as<double>(); p.kss = kss; p.var = var; p.J = J; p.col_blocks = col_blocks;
+    CKR(launch_gemm<EPI_DIAG>(h, Bv, 0, (int)j0, Wv, (int)j0, 0, p));
     const int64_t j1 = j0 + nb;
     if (j1 < N)  // B[:, j1:] -= V[:, J] * L[j1:, J]^T
       CKR(run_gemm_sub(h, Bv, 0, j0, Lv, j1, j0, rows, N - j1, nb, B + j1, ldb, 0));
@@ -479,9 +483,10 @@ int small_batch_row_tiles() {  // read on every call so tests / A-B runs can fli
 // V = K_* L^-T (+ variance): persistent fused kernel for large blocks, right-looking steps for small ones.
 int run_predict_solve(nngp_handle* h, double* B, int64_t ldb, int64_t rows, const double* L, int64_t ldl, int64_t N,
                       const double* kss, double* var) {
+  const double* Linv = h->Linv.as<double>();   // L is always the handle's factor
   const int64_t row_tiles = (rows + GEMM_BM - 1) / GEMM_BM;
-  if (row_tiles <= small_batch_row_tiles()) return run_trsm_right(h, B, ldb, rows, L, ldl, N, kss, var);
-  return run_trsm_fused(h, B, ldb, rows, L, ldl, N, kss, var);
+  if (row_tiles <= small_batch_row_tiles()) return run_trsm_right(h, B, ldb, rows, L, ldl, N, Linv, kss, var);
+  return run_trsm_fused(h, B, ldb, rows, L, ldl, N, Linv, kss, var);
 }
 
 bool use_fused_trsm() {
@@ -544,6 +549,16 @@ int alloc_state(nngp_handle* h, int64_t N, int64_t D) {
   CKR(ensure(h, h->q, (size_t)N * sizeof(double)));
   CKR(ensure(h, h->L, (size_t)(N + 1) * h->ldl * sizeof(double)));  // +1 row: y^T rides through the factorisation
   CKR(ensure(h, h->alpha, (size_t)h->ldl * sizeof(double)));
+  CKR(ensure(h, h->Linv, (size_t)round_up(N, NB) * NB * sizeof(double)));
+  return NNGP_OK;
+}
+
+// inv(L_JJ) for all diagonal blocks of the factor in h->L (after a factorisation or an imported state)
+int run_trtri_diag(nngp_handle* h) {
+  const int nblk = (int)((h->N + NB - 1) / NB);
+  trtri_diag_kernel<<<nblk, NB, 0, h->stream>>>(h->L.as<double>(), h->ldl, (int)h->N, h->Linv.as<double>());
+  h->st.kernel_launches++;
+  CK(cudaGetLastError());
   return NNGP_OK;
 }
 
@@ -628,7 +643,7 @@ int nngp_create(const nngp_config* cfg, nngp_handle** out) {
   if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(gemm_nt_kernel<EPI_ROWDOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
   cudaError_t e3 = cudaFuncSetAttribute(trsm_rows_64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM_BYTES);
   if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(trsm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM_BYTES);
-  if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(trsm_rows_var_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSMV_SMEM_BYTES);
+  if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(gemm_nt_kernel<EPI_DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
     fail(h, NNGP_ECUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s",
          cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
@@ -647,7 +662,7 @@ void nngp_destroy(nngp_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->X, &h->q, &h->L, &h->alpha, &h->flags, &h->lam_d, &h->xt, &h->qt, &h->kss,
-                    &h->blk, &h->mean_d, &h->var_d, &h->ssq, &h->sync_ints, &h->Mmat, &h->Kdd, &h->blk2, &h->cross, &h->partial, &h->mean_partial, &h->ka, &h->kb, &h->kqa, &h->kqb, &h->kout, &h->y, &h->app_x, &h->app_y, &h->sel_mean, &h->sel_var, &h->sel_score, &h->sel_key,
+                    &h->blk, &h->mean_d, &h->var_d, &h->ssq, &h->sync_ints, &h->Mmat, &h->Kdd, &h->blk2, &h->cross, &h->partial, &h->mean_partial, &h->ka, &h->kb, &h->kqa, &h->kqb, &h->kout, &h->Linv, &h->y, &h->app_x, &h->app_y, &h->sel_mean, &h->sel_var, &h->sel_score, &h->sel_key,
                     &h->sel_state, &h->sel_okey, &h->sel_oidx, &h->sel_max})
     release(*b);
   for (auto& r : h->pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -755,6 +770,7 @@ int nngp_fit(nngp_handle* h, const double* x_train, const double* y_train, int64
   // y^T goes into row N of the factor buffer: the factorisation turns it into z^T = (L^-1 y)^T
   CK(cudaMemcpyAsync(L + N * h->ldl, alpha, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   CKR(run_potrf(h, L, h->ldl, N, 1));
+  CKR(run_trtri_diag(h));
   t_chol.stop();
 
   StageTimer t_solve(h, &h->st.fit_solve_ms);
@@ -874,6 +890,7 @@ int nngp_reserve(nngp_handle* h, int64_t n_train_max, int64_t dim, int64_t n_tes
   CKR(ensure(h, h->app_y, (size_t)N * 8));
   CKR(ensure(h, h->L, (size_t)(N + 1) * ldl * 8));
   CKR(ensure(h, h->alpha, (size_t)ldl * 8));
+  CKR(ensure(h, h->Linv, (size_t)round_up(N, NB) * NB * 8));
   if (T > 0) {   // the row-block workspace of nngp_predict / nngp_active_select at (N, T)
     const int64_t wave_rows = 2LL * h->sm_count * GEMM_BM;
     int64_t cap_rows = h->cfg.max_block_bytes / (ldl * 8);
@@ -1074,6 +1091,7 @@ int nngp_set_state(nngp_handle* h, const double* x, const double* l, const doubl
   CKR(upload_matrix(h, alpha, N, 1, h->alpha.as<double>(), 1));
   row_sqnorm_kernel<<<(unsigned)((N * 32 + 255) / 256), 256, 0, h->stream>>>(h->X.as<double>(), h->ldx, (int)N, (int)D, sw2, sb2, h->q.as<double>());
   h->st.kernel_launches++;
+  CKR(run_trtri_diag(h));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
   h->lambda = lambda;

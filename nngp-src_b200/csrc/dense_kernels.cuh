@@ -218,87 +218,31 @@ __global__ void __launch_bounds__(TRSM_ROWS) trsm_rows_64_kernel(double* __restr
   }
 }
 
-// One row of  X * Ljj^T = B  by left-looking forward substitution against the PACKED lower triangle Lp (row j at
-// j(j+1)/2) and the reciprocal diagonal; returns sum_j x_j^2.  This exact operation order is shared by the
-// persistent fused solve (trsm_fused.cuh) and by the small-batch right-looking path (trsm_rows_var_kernel), which
-// is what makes a row's result bitwise independent of the path / blocking / GPU count.
-__device__ __forceinline__ double solve_row_left_packed(double* __restrict__ xr, const double* __restrict__ Lp,
-                                                        const double* __restrict__ rdiag, int nb) {
-  double ss = 0.0;
-  for (int j = 0; j < nb; ++j) {
-    double s0 = xr[j], s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    const double* lj = Lp + j * (j + 1) / 2;
-    int k = 0;
-    for (; k + 3 < j; k += 4) {
-      s0 = fma(-xr[k], lj[k], s0);
-      s1 = fma(-xr[k + 1], lj[k + 1], s1);
-      s2 = fma(-xr[k + 2], lj[k + 2], s2);
-      s3 = fma(-xr[k + 3], lj[k + 3], s3);
-    }
-    for (; k < j; ++k) s0 = fma(-xr[k], lj[k], s0);
-    const double x = ((s0 + s1) + (s2 + s3)) * rdiag[j];
-    xr[j] = x;
-    ss = fma(x, x, ss);
-  }
-  return ss;
-}
-
-// Small-batch prediction path (few row tiles): column block J of  V = K_* L^-T  for all rows, plus the running
-// sum of squares / final variance -- arithmetic identical to one item of trsm_fused_kernel.
-// 128 rows per CTA, 256 threads (threads 0..127 solve one row each).
-constexpr int TRSMV_SMEM_BYTES = (128 * (NB + 1) + NB * (NB + 1) / 2 + NB) * 8;
-__global__ void __launch_bounds__(256) trsm_rows_var_kernel(double* __restrict__ B, long long ldb, int rows,
-                                                            const double* __restrict__ Ljj, long long ldl, int nb,
-                                                            int J, int col_blocks, double* __restrict__ ssq,
-                                                            const double* __restrict__ kss, double* __restrict__ var) {
-  extern __shared__ double sm[];
-  double(*Bs)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm);
-  double* Lp = sm + 128 * (NB + 1);
-  double* rdiag = Lp + NB * (NB + 1) / 2;
-  const int tid = threadIdx.x;
-  const int row0 = blockIdx.x * 128;
-  const int c = tid & 63, rsub = tid >> 6;
-  {
-    double tv[16];
-#pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      const int rr = 4 * u + rsub;
-      tv[u] = (rr < nb && c <= rr) ? Ljj[(long long)rr * ldl + c] : ((rr == c) ? 1.0 : 0.0);
-    }
-#pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      const int rr = 4 * u + rsub;
-      if (c <= rr) Lp[rr * (rr + 1) / 2 + c] = tv[u];
-      if (c == rr) rdiag[rr] = 1.0 / tv[u];
-    }
-  }
-  for (int r0 = 0; r0 < 128; r0 += 32) {
-    double t[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int r = r0 + 4 * u + rsub;
-      t[u] = (row0 + r < rows && c < nb) ? B[(long long)(row0 + r) * ldb + c] : 0.0;
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) Bs[r0 + 4 * u + rsub][c] = t[u];
-  }
+// W_J = inv(L_JJ) for every 64 x 64 diagonal block of the factor (identity padded when the last block is short):
+// one CTA per block, thread c solves L_JJ w = e_c by forward substitution (column c of the inverse).  Output: row-major
+// 64 x 64 blocks stacked along the rows (block J at rows [64 J, 64 J + 64)), the B operand of the diagonal step of
+// the row-wise triangular solves (trsm_fused.cuh / gemm_nt_kernel<EPI_DIAG>).  Runs once per fit; N/64 tiny CTAs.
+__global__ void __launch_bounds__(NB) trtri_diag_kernel(const double* __restrict__ L, long long ldl, int N,
+                                                        double* __restrict__ Winv) {
+  __shared__ double Ls[NB][NB + 1];
+  const int J = blockIdx.x;
+  const int j0 = J * NB;
+  const int n = min(NB, N - j0);
+  const int c = threadIdx.x;
+  for (int r = 0; r < NB; ++r)
+    Ls[r][c] = (r < n && c <= r) ? L[(long long)(j0 + r) * ldl + j0 + c] : ((r == c) ? 1.0 : 0.0);
   __syncthreads();
-  if (tid < 128) {
-    const double ss = solve_row_left_packed(Bs[tid], Lp, rdiag, nb);
-    const int grow = row0 + tid;
-    if (var != nullptr && grow < rows) {
-      const double tot = ((J > 0) ? ssq[grow] : 0.0) + ss;
-      if (J + 1 == col_blocks) var[grow] = kss[grow] - tot;
-      else ssq[grow] = tot;
-    }
+  double w[NB];
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    double sacc = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < i; ++k) sacc = fma(-Ls[i][k], w[k], sacc);
+    w[i] = (i >= c) ? sacc / Ls[i][i] : 0.0;
   }
-  __syncthreads();
-  if (c < nb) {
-    for (int r0 = 0; r0 < 128; r0 += 4) {
-      const int r = r0 + rsub;
-      if (row0 + r < rows) B[(long long)(row0 + r) * ldb + c] = Bs[r][c];
-    }
-  }
+  double* out = Winv + (long long)j0 * NB;
+#pragma unroll
+  for (int i = 0; i < NB; ++i) out[(long long)i * NB + c] = w[i];
 }
 
 // Shared helper: load the n x n lower block Ljj into Ls (identity padded), 8 loads in flight per thread,

@@ -38,7 +38,7 @@ constexpr int GEMM_STAGE_TX_BYTES = GEMM_A_STAGE_BYTES + GEMM_B_STAGE_BYTES;
 constexpr int GEMM_SMEM_BYTES =
     GEMM_STAGES * (GEMM_A_STAGE_BYTES + GEMM_B_STAGE_BYTES) + 2 * GEMM_STAGES * 8 + 1024;
 
-enum GemmEpilogue : int { EPI_GRAM = 0, EPI_SUB = 1, EPI_ROWDOT = 2 };
+enum GemmEpilogue : int { EPI_GRAM = 0, EPI_SUB = 1, EPI_ROWDOT = 2, EPI_DIAG = 3 };
 
 struct GemmParams {
   int M, N;            // valid output extent (rows of the A range, rows of the B range)
@@ -63,7 +63,61 @@ struct GemmParams {
   const double* W;     // M x N, leading dimension ldc (reuses ldc)
   double* partial;
   uint32_t zero;       // always 0 (value-initialised): opaque run-time zero for mma_mainloop's release dependence
+  // EPI_DIAG only (diagonal step of the row-wise triangular solve, see diag_epilogue): C <- A * Winv^T, K = 64
+  double* ssq;         // [M] running sum of squares of the solved row (cross-launch carry)
+  const double* kss;   // [M] K(x,x)
+  double* var;         // [M] or nullptr (plain solve)
+  int J, col_blocks;   // which 64-column block this launch solves, of how many
 };
+
+// Epilogue of the diagonal step of  V = K_* L^-T  (shared by trsm_fused_kernel and gemm_nt_kernel<EPI_DIAG>, which
+// is what makes a row's result bitwise independent of the path / blocking / GPU count): the accumulators hold the
+// solved 128 x 64 block X = R * inv(L_JJ)^T; store it, add sum_c X[r][c]^2 to the row's running sum of squares and,
+// with the last column block, write var = K(x,x) - sum.  Columns >= nb of X are exact zeros (zero residual,
+// identity-padded inverse).  `s_part` is 256 doubles of shared memory nobody else uses until the next barrier.
+struct DiagOut {
+  double* B;            // block origin: element (row 0 of the buffer, column col0 of the block)
+  long long ldb;
+  int rows;
+  double* ssq;
+  const double* kss;
+  double* var;
+  int J, col_blocks;
+};
+__device__ __forceinline__ void diag_epilogue(const double (&acc)[4][4][2], const DiagOut& o, int row0, int nb, int wm,
+                                              int wn, int g, int t, double* s_part) {
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi) {
+    const int lr = wm * 32 + mi * 8 + g;
+    const int row = row0 + lr;
+    double part = 0.0;
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      const int lc = wn * 32 + ni * 8 + 2 * t;
+      const double x0 = acc[mi][ni][0], x1 = acc[mi][ni][1];
+      if (row < o.rows) {
+        double* dst = o.B + (long long)row * o.ldb + lc;
+        if (lc + 1 < nb) *reinterpret_cast<double2*>(dst) = make_double2(x0, x1);
+        else if (lc < nb) dst[0] = x0;
+      }
+      part = fma(x0, x0, part);
+      part = fma(x1, x1, part);
+    }
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    if (t == 0) s_part[lr * 2 + wn] = part;
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int grow = row0 + (int)threadIdx.x;
+    if (o.var != nullptr && grow < o.rows) {
+      const double ss = s_part[threadIdx.x * 2] + s_part[threadIdx.x * 2 + 1];
+      const double tot = ((o.J > 0) ? __ldcg(o.ssq + grow) : 0.0) + ss;
+      if (o.J + 1 == o.col_blocks) o.var[grow] = o.kss[grow] - tot;
+      else __stcg(o.ssq + grow, tot);
+    }
+  }
+}
 
 // theta = atan2(s, k) for s >= 0 (theta in [0, pi]), pi/2 at s == k == 0 [nt: _arctan2(fill_zero = pi/2)].
 // One division + a degree-20 polynomial: atan(t) = t P(t^2) on t = min(s,|k|)/max(s,|k|) in [0,1] (interpolant of
@@ -344,6 +398,11 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+  } else if constexpr (EPI == EPI_DIAG) {
+    __syncthreads();  // every warp has left the ring: its first 2 KiB become the row-sum scratch
+    DiagOut o;
+    o.B = p.C; o.ldb = p.ldc; o.rows = p.M; o.ssq = p.ssq; o.kss = p.kss; o.var = p.var; o.J = p.J; o.col_blocks = p.col_blocks;
+    diag_epilogue(acc, o, tile_m * GEMM_BM, p.N, wm, wn, g, t, reinterpret_cast<double*>(ringA));
   } else if constexpr (EPI == EPI_ROWDOT) {
     // quad[r] contribution of this 64-column tile: sum_c acc[r][c] * W[r][c]  (fixed order => deterministic)
     double part[4];

@@ -4,15 +4,22 @@
 //     var[i] = K(x_i,x_i) - sum_j V[i][j]^2
 //
 // Work item (r, J) = row tile r (128 test rows) x column block J (64 columns):
-//     acc  = B[r, J] - V[r, 0:64J] * L[J, 0:64J]^T     TMA + DMMA main loop (mma_mainloop)
-//     V[r, J] = acc * L_JJ^-T                           one thread per row, forward substitution in smem
-//                                                       (scratch aliases the drained operand ring)
-//     ssq[row] += |V[row, J]|^2                         (var written with the last column block)
+//     acc  = -(B[r, J] - V[r, 0:64J] * L[J, 0:64J]^T) = -R      TMA + DMMA main loop (mma_mainloop)
+//     V[r, J] = R * W_J^T,  W_J = inv(L_JJ)                      4 more k-tiles on the SAME tensor pipe: R goes from
+//                                                                the accumulators into the (drained) A stages of the
+//                                                                ring in fragment layout, W_J arrives by TMA from the
+//                                                                per-block inverses computed once per fit
+//     ssq[row] += |V[row, J]|^2                                  (var written with the last column block)
+// The diagonal step used to be a one-thread-per-row forward substitution on the FP64 CUDA cores.  Those DFMAs
+// share the FP64 pipe with the co-resident CTA's DMMAs and queue behind them one by one: ncu showed 14 % of all
+// warp samples parked at the barrier that ends the substitution.  As a 128 x 64 x 64 DMMA product it costs 4
+// k-tiles (the average item has 254).  inv(L_JJ) of a 64 x 64 Cholesky diagonal block is benign: the error of
+// R * W^T is eps * cond(L_JJ) <= eps * sqrt(cond(K + lambda I)).
 // Items are claimed in J-major order from a global counter, so a CTA that needs V[r, 0:64J] finds the
 // item (r, J-1) already claimed by a running CTA: it acquire-spins on progress[r] (no deadlock, no
 // co-residency assumption).  Row tiles never interact, the per-row reduction order is fixed, so the
 // result of a row is bitwise independent of the grid, of the block it sits in and of the GPU count.
-// Compared with one GEMM launch + one substitution launch per column block this removes the per-launch
+// Compared with one GEMM launch + one solve launch per column block this removes the per-launch
 // tail (1.73 waves of 296 CTAs -> 13.5 % idle), 2 N/64 launches, and one full re-read of V for the variance.
 #pragma once
 #include "dense_kernels.cuh"
@@ -22,19 +29,15 @@ namespace nngp {
 
 constexpr int TF_STAGES = 4;
 constexpr int TF_RING_BYTES = TF_STAGES * (GEMM_A_STAGE_BYTES + GEMM_B_STAGE_BYTES);  // 96 KiB
-// After the main loop the ring is dead and is reused for the substitution: the 128 x 65 staging tile, the
-// packed lower triangle of L_JJ (row j at j(j+1)/2) and its reciprocal diagonal.
-constexpr int TF_STAGE_TILE_BYTES = GEMM_BM * (NB + 1) * 8;
-constexpr int TF_LP_BYTES = (NB * (NB + 1) / 2) * 8;
-static_assert(TF_STAGE_TILE_BYTES + TF_LP_BYTES + NB * 8 <= TF_RING_BYTES, "substitution scratch must fit in the ring");
+static_assert(TF_STAGES * GEMM_BK == NB, "the diagonal step stages all 64 columns of R in the ring's A stages");
 constexpr int TF_SMEM_BYTES = TF_RING_BYTES + 2 * TF_STAGES * 8 + 16 + 1024;
 
 struct TrsmFusedParams {
   double* B;            // rows x N block buffer: K_* on entry, V on exit
   long long ldb;
   int rows;
-  const double* L;      // N x N lower factor
-  long long ldl;
+  const double* L;      // N x N lower factor (tensor map tmL)
+  long long ldl;        // (the per-block inverses inv(L_JJ) come through tensor map tmW: 64 rows x 64 per block)
   int N;
   int row_tiles, col_blocks;
   int* counter;         // zeroed before launch (dynamic schedule only)
@@ -59,16 +62,13 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmL,
-                  const TrsmFusedParams p) {
+                  const __grid_constant__ CUtensorMap tmW, const TrsmFusedParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
   uint8_t* ring = smem_raw + pad;
   uint8_t* ringA = ring;
   uint8_t* ringB = ring + TF_STAGES * GEMM_A_STAGE_BYTES;
-  double(*Bs)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(ring);  // staging tile aliases the ring
-  double* Lp = reinterpret_cast<double*>(ring + TF_STAGE_TILE_BYTES);  // packed lower triangle of L_JJ (aliases too)
-  double* rdiag = Lp + NB * (NB + 1) / 2;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + TF_RING_BYTES);
   uint64_t* empty_bar = full_bar + TF_STAGES;
   int* s_item = reinterpret_cast<int*>(empty_bar + TF_STAGES);
@@ -85,6 +85,7 @@ trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
     fence_mbar_init();
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmL);
+    tma_prefetch_desc(&tmW);
   }
 
   const int total = p.row_tiles * p.col_blocks;
@@ -142,54 +143,41 @@ trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
 
     mma_mainloop<TF_STAGES>(acc, src, ringA, ringB, full_bar, empty_bar, stage, phase, ktiles, wm, wn, lane, p.zero);
 
-    __syncthreads();  // every warp has left the ring: it becomes substitution scratch
-    {
-      // diagonal block L_JJ (identity padded) -> registers first, so the global latency overlaps the smem writes
-      const double* Ljj = p.L + (long long)col0 * p.ldl + col0;
-      const int c = tid & 63, rsub = tid >> 6;
-      double tv[16];
+    // ---- diagonal step: V[r, J] = R * W_J^T on the tensor pipe -------------------------------------------
+    __syncthreads();  // every warp has left the ring (each warp's last release waited for its fragment loads)
+    if (tid == 0) {   // W_J (64 x 64) -> the B halves of the next 4 ring slots, one 16-wide k-tile each
+      int st = stage;
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        const int rr = 4 * u + rsub;
-        tv[u] = (rr < nb && c <= rr) ? __ldcg(Ljj + (long long)rr * p.ldl + c) : ((rr == c) ? 1.0 : 0.0);
-      }
-#pragma unroll
-      for (int mi = 0; mi < 4; ++mi) {
-        const int lr = wm * 32 + mi * 8 + g;
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-          const int lc = wn * 32 + ni * 8 + 2 * t;
-          Bs[lr][lc] = -acc[mi][ni][0];
-          Bs[lr][lc + 1] = -acc[mi][ni][1];
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        const int rr = 4 * u + rsub;
-        if (c <= rr) Lp[rr * (rr + 1) / 2 + c] = tv[u];
-        if (c == rr) rdiag[rr] = 1.0 / tv[u];
+      for (int kt = 0; kt < TF_STAGES; ++kt) {
+        mbar_arrive_expect_tx(&full_bar[st], GEMM_B_STAGE_BYTES);
+        tma_load_2d(ringB + st * GEMM_B_STAGE_BYTES, &tmW, kt * GEMM_BK, col0, &full_bar[st]);
+        if (++st == TF_STAGES) st = 0;
       }
     }
-    __syncthreads();
-    if (tid < GEMM_BM) {
-      const double ss = solve_row_left_packed(Bs[tid], Lp, rdiag, nb);
-      const int grow = row0 + tid;
-      if (p.var != nullptr && grow < p.rows) {
-        const double tot = ((J > 0) ? __ldcg(p.ssq + grow) : 0.0) + ss;
-        if (J + 1 == p.col_blocks) p.var[grow] = p.kss[grow] - tot;
-        else __stcg(p.ssq + grow, tot);
+    // R = -acc -> the A halves of the same slots, in the swizzled fragment layout mma_mainloop reads:
+    // columns [16 s, 16 s + 16) in slot (stage + s) % 4, row lr at 128 lr, 16-byte chunk c at c ^ (lr & 7)
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+      const int lr = wm * 32 + mi * 8 + g;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        int slot = stage + wn * 2 + (ni >> 1);
+        if (slot >= TF_STAGES) slot -= TF_STAGES;
+        const int chunk = ((ni & 1) * 4 + t) ^ g;   // lr & 7 == g
+        double2* dst = reinterpret_cast<double2*>(ringA + slot * GEMM_A_STAGE_BYTES + lr * 128 + chunk * 16);
+        *dst = make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
+        acc[mi][ni][0] = 0.0;
+        acc[mi][ni][1] = 0.0;
       }
     }
-    __syncthreads();
+    __syncthreads();  // R is visible to every warp (generic proxy on both sides)
+    mma_mainloop<TF_STAGES>(acc, src, ringA, ringB, full_bar, empty_bar, stage, phase, TF_STAGES, wm, wn, lane, p.zero);
+    __syncthreads();  // ring drained again: its first 2 KiB are the row-sum scratch of the epilogue
     {
-      const int c = tid & 63, rsub = tid >> 6;
-      if (c < nb) {
-#pragma unroll 4
-        for (int r0 = 0; r0 < GEMM_BM; r0 += 4) {
-          const int lr = r0 + rsub;
-          if (row0 + lr < p.rows) p.B[(long long)(row0 + lr) * p.ldb + col0 + c] = Bs[lr][c];
-        }
-      }
+      DiagOut o;
+      o.B = p.B + col0; o.ldb = p.ldb; o.rows = p.rows; o.ssq = p.ssq; o.kss = p.kss; o.var = p.var;
+      o.J = J; o.col_blocks = p.col_blocks;
+      diag_epilogue(acc, o, row0, nb, wm, wn, g, t, reinterpret_cast<double*>(ringA));
     }
     fence_proxy_async_all();
     __threadfence();
