@@ -1,0 +1,43 @@
+"""Print the parity numbers quoted in DESIGN.md / README.md: CUDA path vs the CPU oracle on the reference's forest
+workload (C1, tests/golden/forest_xy.npz) and on a seeded synthetic C2 subsample.  GPU box only.
+    python tools/parity_report.py"""
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+for p in (ROOT, ROOT / "nngp-src_b200", ROOT / "oracle"):
+    sys.path.insert(0, str(p))
+import nngp_oracle as oracle  # noqa: E402
+from nngp_b200 import _lib, synth  # noqa: E402
+
+
+def rel(a, b):
+    return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+
+def main():
+    out = {}
+    f = np.load(ROOT / "tests" / "golden" / "forest_xy.npz")
+    h = _lib.Handle()
+    h.fit(f["x_train"], f["y_train"])
+    mean, var = h.predict(f["x_test"])
+    ref = oracle.Fit(f["x_train"], f["y_train"])
+    rm, rv = ref.predict(f["x_test"])
+    out["forest_c1"] = {"n_train": int(f["x_train"].shape[0]), "n_test": int(f["x_test"].shape[0]),
+                        "mean_rel": rel(mean, rm), "var_rel": rel(var, rv), "std_rel": rel(np.sqrt(var), np.sqrt(rv)),
+                        "alpha_rel": rel(h.get_state(x=False, l=False)["alpha"], ref.alpha),
+                        "lambda": h.dims()[2], "lambda_oracle": float(ref.lam)}
+    xtr, ytr, xte, _ = synth.make_problem(8192, 2048, 128)
+    h.fit(xtr, ytr)
+    mean, var = h.predict(xte)
+    ref = oracle.Fit(xtr, ytr)
+    rm, rv = ref.predict(xte)
+    out["synthetic_c2_sample"] = {"n_train": 8192, "n_test": 2048, "mean_rel": rel(mean, rm), "var_rel": rel(var, rv)}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
