@@ -449,35 +449,49 @@ int run_trsm_fused(nngp_handle* h, double* B, int64_t ldb, int64_t rows, const d
   return NNGP_OK;
 }
 
-// Small-batch variant of the same solve (identical arithmetic: same DMMA order in the updates, same diagonal
-// step and epilogue, see diag_epilogue): right-looking over the column blocks, so every step exposes (N - j)/64
-// column tiles of parallelism even when there is a single row tile -- the persistent left-looking kernel would walk
-// the N/64 blocks of a row tile sequentially on one SM.  Used when the block has few row tiles (serving a handful
-// of queries, the forest workload).
+// Small-batch variant of the same solve (identical arithmetic: every element sees the same FMA chain in ascending
+// k, the same diagonal step and epilogue, see diag_epilogue): right-looking over OW-wide outer blocks, so every
+// trailing update exposes (N - j)/64 column tiles of parallelism even when there is a single row tile -- the
+// persistent left-looking kernel would walk the N/64 blocks of a row tile sequentially on one SM.  Inside an outer
+// block the 64-wide column blocks are solved left-looking (update with the block's own earlier columns, then the
+// diagonal step).  OW = 256 instead of 64 cuts the read-modify-write traffic of the trailing updates 4x (at 4096
+// rows x N = 8192: 34 GB -> 8.5 GB) and gives them K = 256.  Used when the block has few row tiles (serving a
+// handful of queries, the forest workload).
 int run_trsm_right(nngp_handle* h, double* B, int64_t ldb, int64_t rows, const double* L, int64_t ldl, int64_t N,
                    const double* Linv, const double* kss, double* var) {
   MatView Bv{B, rows, N, ldb}, Lv{L, N, N, ldl}, Wv{Linv, round_up(N, NB), NB, NB};
   const int col_blocks = (int)((N + NB - 1) / NB);
+  // one or two row tiles are launch-latency bound: keep the plain 64-wide sweep (2 launches per column block)
+  const int64_t OW = rows <= 2 * GEMM_BM ? NB : 4 * NB;
   if (var) CKR(ensure(h, h->ssq, (size_t)rows * sizeof(double)));
-  for (int J = 0; J < col_blocks; ++J) {
-    const int64_t j0 = (int64_t)J * NB;
-    const int64_t nb = std::min<int64_t>(NB, N - j0);
-    GemmParams p{};   // V[:, J] = R[:, J] * inv(L_JJ)^T in place (+ running sum of squares / variance)
-    p.M = (int)rows; p.N = (int)nb; p.ktiles = NB / GEMM_BK;
-    p.C = B + j0; p.ldc = ldb;
-    p.ssq = h->ssq.as<double>(); p.kss = kss; p.var = var; p.J = J; p.col_blocks = col_blocks;
-    CKR(launch_gemm<EPI_DIAG>(h, Bv, 0, (int)j0, Wv, (int)j0, 0, p));
-    const int64_t j1 = j0 + nb;
-    if (j1 < N)  // B[:, j1:] -= V[:, J] * L[j1:, J]^T
-      CKR(run_gemm_sub(h, Bv, 0, j0, Lv, j1, j0, rows, N - j1, nb, B + j1, ldb, 0));
+  for (int64_t o0 = 0; o0 < N; o0 += OW) {
+    const int64_t o1 = std::min<int64_t>(o0 + OW, N);
+    for (int64_t j0 = o0; j0 < o1; j0 += NB) {
+      const int64_t nb = std::min<int64_t>(NB, N - j0);
+      const int J = (int)(j0 / NB);
+      if (j0 > o0)  // B[:, J] -= V[:, o0:j0] * L[J, o0:j0]^T
+        CKR(run_gemm_sub(h, Bv, 0, o0, Lv, j0, o0, rows, nb, j0 - o0, B + j0, ldb, 0));
+      GemmParams p{};   // V[:, J] = R[:, J] * inv(L_JJ)^T in place (+ running sum of squares / variance)
+      p.M = (int)rows; p.N = (int)nb; p.ktiles = NB / GEMM_BK;
+      p.C = B + j0; p.ldc = ldb;
+      p.ssq = h->ssq.as<double>(); p.kss = kss; p.var = var; p.J = J; p.col_blocks = col_blocks;
+      CKR(launch_gemm<EPI_DIAG>(h, Bv, 0, (int)j0, Wv, (int)j0, 0, p));
+    }
+    if (o1 < N)  // B[:, o1:] -= V[:, o0:o1] * L[o1:, o0:o1]^T
+      CKR(run_gemm_sub(h, Bv, 0, o0, Lv, o1, o0, rows, N - o1, o1 - o0, B + o1, ldb, 0));
   }
   CK(cudaGetLastError());
   return NNGP_OK;
 }
 
-int small_batch_row_tiles() {  // read on every call so tests / A-B runs can flip it inside one process
+// Row-tile count up to which the right-looking path is used.  With R <= 2 x SMs row tiles the persistent kernel runs
+// one CTA per row tile and takes the time of ONE tile's N/64-item chain: ~42 ms at N = 8192 while every CTA has an
+// SM to itself (R <= 148), ~78 ms once some SMs hold two (measured at R = 157); the right-looking path scales
+// with the rows (21.6 ms at R = 64, 37 ms at R = 120).  Crossover ~ 1.5 x SMs.  Read on every call so tests / A-B
+// runs can flip it inside one process.
+int small_batch_row_tiles(const nngp_handle* h) {
   const char* e = getenv("NNGP_SMALL_BATCH_TILES");
-  return e ? atoi(e) : 64;
+  return e ? atoi(e) : 3 * h->sm_count / 2;
 }
 
 // V = K_* L^-T (+ variance): persistent fused kernel for large blocks, right-looking steps for small ones.
@@ -485,7 +499,7 @@ int run_predict_solve(nngp_handle* h, double* B, int64_t ldb, int64_t rows, cons
                       const double* kss, double* var) {
   const double* Linv = h->Linv.as<double>();   // L is always the handle's factor
   const int64_t row_tiles = (rows + GEMM_BM - 1) / GEMM_BM;
-  if (row_tiles <= small_batch_row_tiles()) return run_trsm_right(h, B, ldb, rows, L, ldl, N, Linv, kss, var);
+  if (row_tiles <= small_batch_row_tiles(h)) return run_trsm_right(h, B, ldb, rows, L, ldl, N, Linv, kss, var);
   return run_trsm_fused(h, B, ldb, rows, L, ldl, N, Linv, kss, var);
 }
 
