@@ -168,8 +168,11 @@ NNGP_API int nngp_log_marginal_likelihood(nngp_handle* h, double* lml_out);
  * memory); score_out (T doubles, optional) receives the normalised scores.  Selection runs on the device (exact
  * radix select); only the k winners cross PCIe.
  * nngp_append_fit == ActiveLearner.merge_data + train (:57-65, :23-31): appends M labelled rows to the training
- * set already held by the handle and refits from scratch (the reference's relative diag_reg makes every refit a
- * new lambda, so the factor cannot be extended exactly).  Needs a model fitted by nngp_fit on this handle. */
+ * set already held by the handle and refits from scratch -- bitwise the nngp_fit of the stacked arrays (the
+ * reference's relative diag_reg makes every refit a new lambda, so the factor cannot be extended exactly).  With
+ * cfg.diag_reg_absolute (fixed lambda, NNGP mode, even N) the factor IS extended instead: L21 = K21 L11^-T, Cholesky
+ * of the M x M Schur complement, N^2 M + M^3/3 flop instead of (N+M)^3/3 -- the same model up to rounding
+ * (NNGP_APPEND_INCREMENTAL=0 forces the refit).  Needs a model fitted by nngp_fit on this handle. */
 #define NNGP_SELECT_TOPK 0
 #define NNGP_SELECT_SAMPLE 1
 NNGP_API int nngp_active_select(nngp_handle* h, const double* x_pool, int64_t T, int64_t budget, int32_t mode,

@@ -71,6 +71,8 @@ struct nngp_handle {
   DevBuf Linv;    // inv(L_JJ) of every 64 x 64 diagonal block of L (trtri_diag_kernel), operand of the solves' diagonal step
   DevBuf y;       // raw labels of the last nngp_fit (kept for nngp_append_fit)
   DevBuf app_x, app_y;  // nngp_append_fit staging: [X; X_new], [y; y_new]
+  DevBuf zkeep;   // z = L^-1 y of the last fit (the backward substitution destroys its copy in the factor buffer)
+  DevBuf L2;      // second factor buffer: target of the incremental (fixed-lambda) append, then swapped with L
   bool have_y = false;
   DevBuf flags;   // int[2]: {potrf info, non-finite input}
   DevBuf lam_d;   // double[4]: {lambda, sum log diag L, z^T z, spare}
@@ -676,7 +678,7 @@ void nngp_destroy(nngp_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->X, &h->q, &h->L, &h->alpha, &h->flags, &h->lam_d, &h->xt, &h->qt, &h->kss,
-                    &h->blk, &h->mean_d, &h->var_d, &h->ssq, &h->sync_ints, &h->Mmat, &h->Kdd, &h->blk2, &h->cross, &h->partial, &h->mean_partial, &h->ka, &h->kb, &h->kqa, &h->kqb, &h->kout, &h->Linv, &h->y, &h->app_x, &h->app_y, &h->sel_mean, &h->sel_var, &h->sel_score, &h->sel_key,
+                    &h->blk, &h->mean_d, &h->var_d, &h->ssq, &h->sync_ints, &h->Mmat, &h->Kdd, &h->blk2, &h->cross, &h->partial, &h->mean_partial, &h->ka, &h->kb, &h->kqa, &h->kqb, &h->kout, &h->Linv, &h->zkeep, &h->L2, &h->y, &h->app_x, &h->app_y, &h->sel_mean, &h->sel_var, &h->sel_score, &h->sel_key,
                     &h->sel_state, &h->sel_okey, &h->sel_oidx, &h->sel_max})
     release(*b);
   for (auto& r : h->pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -790,6 +792,8 @@ int nngp_fit(nngp_handle* h, const double* x_train, const double* y_train, int64
   StageTimer t_solve(h, &h->st.fit_solve_ms);
   lml_terms_kernel<<<1, 1024, 0, h->stream>>>(L, h->ldl, (int)N, L + N * h->ldl, h->lam_d.as<double>() + 1);
   h->st.kernel_launches++;
+  CKR(ensure(h, h->zkeep, (size_t)N * sizeof(double)));
+  CK(cudaMemcpyAsync(h->zkeep.p, L + N * h->ldl, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   CKR(run_trsv_bwd(h, L, h->ldl, N, L + N * h->ldl, alpha));  // alpha = L^-T z
   if (ntk) {  // M = L^-1 K_dd L^-T : two row-wise solves around a transpose (M is symmetric)
     double* Kd = h->Kdd.as<double>();
@@ -905,6 +909,9 @@ int nngp_reserve(nngp_handle* h, int64_t n_train_max, int64_t dim, int64_t n_tes
   CKR(ensure(h, h->L, (size_t)(N + 1) * ldl * 8));
   CKR(ensure(h, h->alpha, (size_t)ldl * 8));
   CKR(ensure(h, h->Linv, (size_t)round_up(N, NB) * NB * 8));
+  CKR(ensure(h, h->zkeep, (size_t)N * 8));
+  if (h->cfg.diag_reg_absolute && h->cfg.kernel_type == 0)   // the incremental append ping-pongs between two factors
+    CKR(ensure(h, h->L2, (size_t)(N + 1) * ldl * 8));
   if (T > 0) {   // the row-block workspace of nngp_predict / nngp_active_select at (N, T)
     const int64_t wave_rows = 2LL * h->sm_count * GEMM_BM;
     int64_t cap_rows = h->cfg.max_block_bytes / (ldl * 8);
@@ -920,6 +927,89 @@ int nngp_reserve(nngp_handle* h, int64_t n_train_max, int64_t dim, int64_t n_tes
     CKR(ensure(h, h->mean_d, (size_t)T * 8));
     CKR(ensure(h, h->var_d, (size_t)T * 8));
     for (DevBuf* b : {&h->sel_mean, &h->sel_var, &h->sel_score, &h->sel_key}) CKR(ensure(h, *b, (size_t)T * 8));
+  }
+  return NNGP_OK;
+}
+
+// Fixed-lambda append (cfg.diag_reg_absolute): extend the factor instead of refactoring.  With A' = [[A, K21^T],
+// [K21, K22 + lambda I]] and A = L11 L11^T:   L21 = K21 L11^-T (the prediction solve),  L22 L22^T = K22 + lambda I
+// - L21 L21^T (Gram + one SYRK-shaped GEMM + a Cholesky of the M x M Schur complement),  z' = [z; L22^-1 (y_new -
+// L21 z)] (the y row rides through that small Cholesky as in the full fit), alpha' = L'^-T z'.  N^2 M + M^3/3 flop
+// instead of (N+M)^3/3.  Exact in exact arithmetic; in FP64 it agrees with a fresh fit to rounding (tested), not
+// bitwise.  Not applicable to the reference's relative diag_reg: there lambda = 1e-3 tr(K)/N moves with every row.
+// On entry X/y staging holds [X; X_new], [y; y_new]; h->L, h->Linv, h->zkeep describe the old N-row model.
+static int append_incremental(nngp_handle* h, int64_t M) {
+  const int64_t N = h->N, D = h->D, Nn = N + M;
+  const int64_t ldo = h->ldl, ldn = round_up(Nn, 16);
+  const double sw2 = h->cfg.sigma_w * h->cfg.sigma_w, sb2 = h->cfg.sigma_b * h->cfg.sigma_b;
+  StageTimer t_total(h, &h->st.fit_total_ms);
+  CKR(ensure(h, h->L2, (size_t)(Nn + 1) * ldn * sizeof(double)));
+  double* Ln = h->L2.as<double>();
+  CK(cudaMemsetAsync(h->flags.p, 0, 2 * sizeof(int), h->stream));
+  // old factor (lower part incl. diagonal blocks) and old z into the new pitch
+  CK(cudaMemcpy2DAsync(Ln, ldn * sizeof(double), h->L.p, ldo * sizeof(double), (size_t)N * sizeof(double), N,
+                       cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemsetAsync(Ln + Nn * ldn, 0, (size_t)ldn * sizeof(double), h->stream));
+  CK(cudaMemcpyAsync(Ln + Nn * ldn, h->zkeep.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(Ln + Nn * ldn + N, h->app_y.as<double>() + N, (size_t)M * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  // X, y, q for all Nn rows (the staging buffers are contiguous)
+  CKR(ensure(h, h->X, (size_t)Nn * h->ldx * sizeof(double)));
+  CKR(ensure(h, h->q, (size_t)Nn * sizeof(double)));
+  CKR(ensure(h, h->y, (size_t)Nn * sizeof(double)));
+  CKR(ensure(h, h->alpha, (size_t)ldn * sizeof(double)));
+  CKR(ensure(h, h->zkeep, (size_t)Nn * sizeof(double)));
+  double* X = h->X.as<double>();
+  double* q = h->q.as<double>();
+  CKR(upload_matrix(h, h->app_x.as<double>(), Nn, D, X, h->ldx));
+  CK(cudaMemcpyAsync(h->y.p, h->app_y.p, (size_t)Nn * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  CKR(check_finite_async(h, X + N * h->ldx, h->ldx, M, D));
+  CKR(check_finite_async(h, h->y.as<double>() + N, 1, M, 1));
+  row_sqnorm_kernel<<<(unsigned)((Nn * 32 + 255) / 256), 256, 0, h->stream>>>(X, h->ldx, (int)Nn, (int)D, sw2, sb2, q);
+  h->st.kernel_launches++;
+
+  StageTimer t_gram(h, &h->st.fit_gram_ms);
+  double* L21 = Ln + N * ldn;        // rows N..Nn-1, columns 0..N-1
+  double* S = Ln + N * ldn + N;      // the Schur complement block
+  CKR(run_gram(h, X + N * h->ldx, h->ldx, M, q + N, X, h->ldx, N, q, D, L21, ldn, 0));                     // K21
+  CKR(run_gram(h, X + N * h->ldx, h->ldx, M, q + N, X + N * h->ldx, h->ldx, M, q + N, D, S, ldn, 1));       // K22 (lower)
+  diag_reg_kernel<<<1, 1024, 0, h->stream>>>(S, ldn, (int)M, h->cfg.diag_reg, 1, h->lam_d.as<double>());
+  h->st.kernel_launches++;
+  t_gram.stop();
+
+  StageTimer t_chol(h, &h->st.fit_chol_ms);
+  CKR(run_predict_solve(h, L21, ldn, M, Ln, ldn, N, nullptr, nullptr));                                    // L21 = K21 L11^-T
+  {  // [S; y_new^T] -= [L21; z^T] L21^T   (K = N, zero-filled up to a multiple of 16 by the tensor map bounds)
+    MatView Av{Ln, Nn + 1, N, ldn};
+    CKR(run_gemm_sub(h, Av, N, 0, Av, N, 0, M + 1, M, round_up(N, GEMM_BK), S, ldn, 1));
+  }
+  CKR(run_potrf(h, S, ldn, M, 1));                                                                         // L22, z_new
+  // from here on the handle describes the extended model
+  std::swap(h->L, h->L2);
+  h->N = Nn; h->ldl = ldn;
+  CKR(ensure(h, h->Linv, (size_t)round_up(Nn, NB) * NB * sizeof(double)));   // (old inverses are no longer needed)
+  CKR(run_trtri_diag(h));
+  t_chol.stop();
+
+  StageTimer t_solve(h, &h->st.fit_solve_ms);
+  double* zrow = Ln + Nn * ldn;
+  lml_terms_kernel<<<1, 1024, 0, h->stream>>>(Ln, ldn, (int)Nn, zrow, h->lam_d.as<double>() + 1);
+  h->st.kernel_launches++;
+  CK(cudaMemcpyAsync(h->zkeep.p, zrow, (size_t)Nn * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  CKR(run_trsv_bwd(h, Ln, ldn, Nn, zrow, h->alpha.as<double>()));
+  t_solve.stop();
+  t_total.stop();
+
+  int flags[2];
+  CK(cudaMemcpyAsync(flags, h->flags.p, sizeof flags, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->lml_terms, h->lam_d.as<double>() + 1, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  t_total.collect(); t_gram.collect(); t_chol.collect(); t_solve.collect();
+  flush_class_events(h);
+  if (flags[1]) { drop_fit(h); return fail(h, NNGP_EINVAL, "nngp_append_fit: non-finite value in x_new / y_new"); }
+  if (flags[0]) {
+    drop_fit(h);
+    return fail(h, NNGP_ENOTPD, "nngp_append_fit: the extended K + lambda*I is not positive definite (pivot %lld of %lld)",
+                (long long)(N + flags[0] - 1), (long long)Nn);
   }
   return NNGP_OK;
 }
@@ -943,6 +1033,14 @@ int nngp_append_fit(nngp_handle* h, const double* x_new, const double* y_new, in
     CKR(upload_matrix(h, x_new, M, D, xc.as<double>() + N * D, D));
     CKR(upload_matrix(h, y_new, M, 1, yc.as<double>() + N, 1));
     CK(cudaStreamSynchronize(h->stream));
+    // fixed lambda: extend the factor (NNGP_APPEND_INCREMENTAL=0 forces the full refit, e.g. for A/B runs)
+    const char* inc = getenv("NNGP_APPEND_INCREMENTAL");
+    // (an odd N would put the Schur block at an 8-byte-aligned column: TMA bases and the double2 epilogues need 16)
+    if (h->cfg.diag_reg_absolute && h->cfg.kernel_type == 0 && N % 2 == 0 && !(inc && !strcmp(inc, "0"))) {
+      const int r = append_incremental(h, M);
+      if (r != NNGP_OK) drop_fit(h);   // a half-extended model is not a model
+      return r;
+    }
     return nngp_fit(h, xc.as<double>(), yc.as<double>(), N + M, D);
   };
   if (rc == NNGP_OK) rc = body();

@@ -113,7 +113,11 @@ trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
     src.a_col0 = 0; src.a_row = row0; src.b_col0 = 0; src.b_row = col0;
     if (tid == 0) {
       if (J > 0) {
-        while (ld_acquire_gpu(p.progress + r) < J) __nanosleep(64);
+        // bounded like mbar_wait: a scheduling bug traps (CUDA error at the next sync) instead of hanging the GPU
+        for (unsigned spin = 0; ld_acquire_gpu(p.progress + r) < J; ++spin) {
+          __nanosleep(64);
+          if (spin > (1u << 27)) __trap();
+        }
         fence_proxy_async_all();  // V was written through the generic proxy by other CTAs -> read by TMA
       }
       ring_prologue<TF_STAGES>(src, ringA, ringB, full_bar, stage, ktiles);

@@ -446,6 +446,41 @@ def test_append_fit_is_bitwise_a_fresh_fit(lib, synth):
         h.predict(xpool[:3])
 
 
+def test_incremental_append_with_absolute_lambda(lib, synth, monkeypatch):
+    """diag_reg_absolute_scale=True: nngp_append_fit extends the factor (block Cholesky of the Schur complement, N^2 M
+    flop) instead of refactoring -- same model as a fresh fit up to rounding, and the oracle's; N is deliberately not
+    a multiple of 16 / 64 and a one-row append is included."""
+    xtr, ytr, xpool, ypool = synth.make_problem(900, 400, 24)
+    lam = 50.0
+    h = lib.Handle(diag_reg=lam, diag_reg_absolute=True)
+    h.fit(xtr, ytr)
+    h.append_fit(xpool[:130], ypool[:130])
+    h.append_fit(xpool[130:131], ypool[130:131])
+    xs, ys = np.vstack([xtr, xpool[:131]]), np.concatenate([ytr, ypool[:131]])
+    fresh = lib.Handle(diag_reg=lam, diag_reg_absolute=True)
+    fresh.fit(xs, ys)
+    a, b = h.get_state(), fresh.get_state()
+    assert h.dims() == fresh.dims() == (1031, 24, lam)
+    assert np.array_equal(a["x"], b["x"])
+    assert relmax(a["l"], b["l"]) < 1e-11 and relmax(a["alpha"], b["alpha"]) < 1e-8
+    assert abs(h.log_marginal_likelihood() - fresh.log_marginal_likelihood()) < 1e-9 * abs(fresh.log_marginal_likelihood())
+    m1, v1 = h.predict(xpool[200:])
+    m2, v2 = fresh.predict(xpool[200:])
+    assert relmax(m1, m2) < 1e-9 and relmax(v1, v2) < 1e-9
+    ref = oracle.Fit(xs, ys, 2, 1.0, 0.0, lam, True)
+    rm, rv = ref.predict(xpool[200:])
+    assert relmax(m1, rm) < 1e-6 and relmax(v1, rv) < 1e-6
+    # a third append works on the extended state (N = 1031 is odd: that one refits, the block needs 16-byte
+    # alignment), and the switch forces the bitwise refit
+    h.append_fit(xpool[131:195], ypool[131:195])
+    monkeypatch.setenv("NNGP_APPEND_INCREMENTAL", "0")
+    fresh.append_fit(xpool[131:195], ypool[131:195])
+    full = lib.Handle(diag_reg=lam, diag_reg_absolute=True)
+    full.fit(np.vstack([xs, xpool[131:195]]), np.concatenate([ys, ypool[131:195]]))
+    assert np.array_equal(fresh.get_state()["l"], full.get_state()["l"])
+    assert relmax(h.get_state()["alpha"], full.get_state()["alpha"]) < 1e-8
+
+
 def test_active_learner_device_path_equals_host_path(lib, synth):
     """ActiveLearner.active_train through nngp_active_select / nngp_append_fit ends with exactly the training set the
     host-side restatement of the loop (numpy argsort + fresh fits) ends with."""
