@@ -9,7 +9,7 @@ from pathlib import Path
 
 import numpy as np
 
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 for p in (ROOT, ROOT / "nngp-src_b200", ROOT / "oracle"):
     sys.path.insert(0, str(p))
 

@@ -1,13 +1,13 @@
 """Print the parity numbers quoted in DESIGN.md / README.md: CUDA path vs the CPU oracle on the reference's forest
 workload (C1, tests/golden/forest_xy.npz) and on a seeded synthetic C2 subsample.  GPU box only.
-    python tools/parity_report.py"""
+    python tests/checks/parity_report.py"""
 import json
 import sys
 from pathlib import Path
 
 import numpy as np
 
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 for p in (ROOT, ROOT / "nngp-src_b200", ROOT / "oracle"):
     sys.path.insert(0, str(p))
 import nngp_oracle as oracle  # noqa: E402

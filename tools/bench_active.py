@@ -2,8 +2,8 @@
 
 Refit-from-scratch as the training set grows n0 -> n_max in steps of `budget`, each round predicting the whole
 remaining pool (mean + variance) and selecting the top-`budget` rows by std/max(mean) (the deterministic branch,
-ActiveLearner.py:54).  Prints one JSON line with per-round timings; `--oracle-rounds K` additionally replays the
-first K rounds with the CPU oracle and checks that the SAME rows are selected.
+ActiveLearner.py:54).  Prints one JSON line with per-round timings.  (That the selected rows are the oracle's is
+checked in tests/test_gpu_parity.py.)
 
     python tools/bench_active.py [--n0 2048 --budget 2048 --n-max 32768 --pool 65536 --dim 128 --depth 2]
 """
@@ -16,7 +16,7 @@ from pathlib import Path
 import numpy as np
 
 ROOT = Path(__file__).resolve().parents[1]
-for p in (ROOT, ROOT / "nngp-src_b200", ROOT / "oracle"):
+for p in (ROOT, ROOT / "nngp-src_b200"):
     sys.path.insert(0, str(p))
 from nngp_b200 import stax, synth  # noqa: E402
 from nngp_b200.active import ActiveLearner  # noqa: E402
@@ -30,7 +30,6 @@ def main():
     ap.add_argument("--pool", type=int, default=65536)
     ap.add_argument("--dim", type=int, default=128)
     ap.add_argument("--depth", type=int, default=2)
-    ap.add_argument("--oracle-rounds", type=int, default=0)
     a = ap.parse_args()
     total = a.pool + a.n0
     x = synth.encodings(total, a.dim, 1)
@@ -39,7 +38,7 @@ def main():
     layers = [stax.Dense(512)] + [l for _ in range(a.depth - 1) for l in (stax.Relu(), stax.Dense(1))]
     _, _, kernel_fn = stax.serial(*layers)
     al = ActiveLearner(budget=a.budget, active_iters=0, verbose=False)
-    rounds, agree = [], []
+    rounds = []
     t_all = time.perf_counter()
     pf, xd, yd = None, None, None
     while True:
@@ -55,12 +54,6 @@ def main():
         rounds.append({"n_train": int(xtr.shape[0]), "pool": int(xpool.shape[0]), "seconds": dt, "fit_call_s": t_fit,
                        "select_call_s": dt - t_fit,
                        "fit_ms": st["fit_total_ms"], "predict_ms": st["pred_total_ms"]})
-        if len(agree) < a.oracle_rounds:
-            import nngp_oracle as oracle
-            ref = oracle.Fit(xtr, ytr.ravel(), a.depth)
-            rm, rv = ref.predict(xpool)
-            want = oracle.active_select(rm[:, None], np.sqrt(rv), a.budget)
-            agree.append(bool(set(want.tolist()) == set(np.asarray(idx).tolist())))
         if xtr.shape[0] + a.budget > a.n_max or xpool.shape[0] <= a.budget:
             break
         xd, yd = xpool[idx], ypool[idx]
@@ -68,7 +61,7 @@ def main():
     out = {"workload": "C4 active-learning loop", "n0": a.n0, "budget": a.budget, "n_max": a.n_max, "pool": a.pool,
            "dim": a.dim, "depth": a.depth, "rounds": len(rounds), "total_seconds": time.perf_counter() - t_all,
            "sum_fit_ms": sum(r["fit_ms"] for r in rounds), "sum_predict_ms": sum(r["predict_ms"] for r in rounds),
-           "per_round": rounds, "selection_matches_oracle": agree}
+           "per_round": rounds}
     print(json.dumps(out))
 
 
