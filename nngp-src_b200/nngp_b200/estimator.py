@@ -8,6 +8,7 @@ reference's own ``load_training_schema_data`` (its signature is kept) or pre-enc
 from __future__ import annotations
 
 import datetime
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -17,6 +18,10 @@ from . import stax
 
 
 class Estimator(object):
+    # query lines per pipeline stage of predict(): one stage is one full-efficiency GPU batch (the persistent solve
+    # wants >= 2 x 148 row tiles of 128); the next stage's lines are parsed on the host cores meanwhile
+    pipeline_chunk = 65536
+
     def __init__(self, schema_name: str = "", data_path: str = "", train_query_path: str = "", chunk_size: int = 64,
                  use_aux: bool = False, q_error_threshold: float = 100.0, coef_var_threshold: float = 1.0, *,
                  loader=None, X_train=None, Y_train=None, nngp_encoder=None, verbose: bool = True):
@@ -49,6 +54,8 @@ class Estimator(object):
         if self.nngp_encoder is None:
             raise ValueError("Estimator.predict needs nngp_encoder.parse_line_without_card_then_encode")
         if hasattr(self.nngp_encoder, "encode"):        # nngp_b200.encoder.BatchEncoder: all lines in one C++ call
+            if len(query_lines) > self.pipeline_chunk:  # ... or chunk i+1 parsed while the GPU predicts chunk i
+                return self._predict_pipelined(list(query_lines), start)
             X_test = self.nngp_encoder.encode(query_lines)
         else:                                           # the reference's per-line loop, estimator.py:46-50
             X_test = np.asarray([self.nngp_encoder.parse_line_without_card_then_encode(line) for line in query_lines],
@@ -58,6 +65,26 @@ class Estimator(object):
         self._say("prediction time={} seconds".format(duration))
         pred_std = np.sqrt(np.diag(pred_cov))                                                      # estimator.py:55
         return pred_mean.ravel(), pred_std.ravel()                                                 # estimator.py:56,61
+
+    def _predict_pipelined(self, query_lines, start):
+        """Large batches: the C++ line encoder (host cores, GIL released) runs one chunk ahead of the GPU.  Rows are
+        independent and the CUDA path is bitwise invariant to how rows are blocked, so the result equals the
+        one-shot path's; the two stages cost max(encode, predict) per chunk instead of their sum."""
+        step = self.pipeline_chunk
+        chunks = [query_lines[i:i + step] for i in range(0, len(query_lines), step)]
+        means, stds = [], []
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            pending = pool.submit(self.nngp_encoder.encode, chunks[0])
+            for i in range(len(chunks)):
+                X_test = pending.result()
+                if i + 1 < len(chunks):
+                    pending = pool.submit(self.nngp_encoder.encode, chunks[i + 1])
+                pred_mean, pred_cov = self._nngp_prediction(X_test)
+                means.append(np.asarray(pred_mean).ravel())
+                stds.append(np.sqrt(np.diag(pred_cov)).ravel())
+        duration = (datetime.datetime.now() - start).total_seconds()
+        self._say("prediction time={} seconds".format(duration))
+        return np.concatenate(means), np.concatenate(stds)
 
     def _nngp_prediction(self, X_test, kernel_type="nngp", compute_cov=True):
         return self.predict_fn(x_test=X_test, get=kernel_type, compute_cov=compute_cov)           # estimator.py:64-68

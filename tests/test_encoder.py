@@ -85,3 +85,10 @@ def test_estimator_uses_the_batch_encoder(encmod, gold, monkeypatch):
     mean, std = est.predict([str(l) for l in gold["lines"][:20]])
     rm, rv = oracle.Fit(gold["x_train"], y).predict(gold["x"][:20])
     assert np.allclose(mean, rm) and np.allclose(std, np.sqrt(rv))
+    # large batches are pipelined (encode chunk i+1 on the host while chunk i is predicted): same answer, same order
+    lines = [str(l) for l in gold["lines"][:20]] * 3 + [str(gold["lines"][3])]
+    est.pipeline_chunk = 7
+    mean_p, std_p = est.predict(lines)
+    assert mean_p.shape == (61,) and std_p.shape == (61,)
+    assert np.allclose(mean_p[:60], np.tile(rm, 3), rtol=1e-12) and np.allclose(std_p[:60], np.tile(np.sqrt(rv), 3), rtol=1e-9)
+    assert np.isclose(mean_p[60], rm[3], rtol=1e-12)
