@@ -513,6 +513,22 @@ bool use_fused_trsm() {
 // out <- L^-T z  (blocked backward substitution; z is destroyed; reads L exactly once)
 int run_trsv_bwd(nngp_handle* h, const double* L, int64_t ld, int64_t N, double* z, double* out) {
   const int64_t nblk = (N + NB - 1) / NB;
+  static const bool steps = [] { const char* e = getenv("NNGP_TRSV"); return e && !strcmp(e, "steps"); }();
+  if (!steps) {  // one persistent launch: column slices of SW, one CTA each, all co-resident (grid <= #SMs)
+    int64_t sw = 4 * NB;
+    while ((N + sw - 1) / sw > h->sm_count) sw += NB;
+    const int grid = (int)((N + sw - 1) / sw);
+    const size_t smem = (size_t)(NB * (NB + 1) + 2 * NB + sw) * sizeof(double);
+    if (smem <= 200 * 1024) {
+      CKR(ensure(h, h->sync_ints, (size_t)(nblk + 1) * sizeof(int)));
+      CK(cudaMemsetAsync(h->sync_ints.p, 0, (size_t)nblk * sizeof(int), h->stream));
+      CK(cudaFuncSetAttribute(trsv_bwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      trsv_bwd_persistent_kernel<<<grid, TRSVP_THREADS, smem, h->stream>>>(L, ld, (int)N, (int)sw, z, out, h->sync_ints.as<int>());
+      h->st.kernel_launches++;
+      CK(cudaGetLastError());
+      return NNGP_OK;
+    }
+  }
   for (int64_t jb = nblk - 1; jb >= 0; --jb) {
     const int64_t j0 = jb * NB;
     const int64_t nb = std::min<int64_t>(NB, N - j0);

@@ -349,6 +349,102 @@ __global__ void __launch_bounds__(TRSV_THREADS) trsv_bwd_step_kernel(const doubl
   }
 }
 
+// The whole backward substitution  L^T a = z  as ONE kernel (the stepwise version above costs one launch per 64-row
+// block: N/64 launches of ~15 us on a serial chain).  CTA k owns the SW-column slice [k SW, (k+1) SW) of z in shared
+// memory, SW a multiple of 64 chosen so that all CTAs are co-resident (grid <= #SMs, asserted by the host).  Blocks
+// J = N/64-1 ... 0 in order:  the CTA that owns block J's columns has, by then, applied every earlier update to
+// them; it solves L_JJ^T a_J = z_J (the same warp-shuffle substitution as the stepwise kernel), writes a_J to `aout`
+// and releases flag[J];  every CTA with columns below block J acquires the flag and applies
+// z[c] -= sum_i L[64J+i][c] a_i  to its own columns (the L strip is loaded BEFORE the wait, so its latency hides
+// behind the chain).  Per column the arithmetic and its order are exactly those of the stepwise kernel => same bits.
+// Spins are bounded: a scheduling bug traps instead of hanging the GPU.
+constexpr int TRSVP_THREADS = 256;
+__global__ void __launch_bounds__(TRSVP_THREADS) trsv_bwd_persistent_kernel(const double* __restrict__ L, long long ld,
+                                                                            int N, int SW, const double* __restrict__ z,
+                                                                            double* __restrict__ aout, int* flags) {
+  extern __shared__ double sm[];
+  double(*Ls)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm);   // [64][65]
+  double* as = sm + NB * (NB + 1);                                   // [64]
+  double* rd = as + NB;                                              // [64]
+  double* zs = rd + NB;                                              // [SW]
+  const int tid = threadIdx.x;
+  // slices are handed out back to front: the CTAs scheduled first own the blocks that are solved first, so a CTA
+  // only ever waits for CTAs with a LOWER blockIdx
+  const int c0 = (int)(gridDim.x - 1 - blockIdx.x) * SW;
+  const int c1 = min(c0 + SW, N);
+  for (int c = tid; c < SW; c += TRSVP_THREADS) zs[c] = (c0 + c < N) ? z[c0 + c] : 0.0;
+  const int nblk = (N + NB - 1) / NB;
+  const int my_first_blk = c0 / NB;   // the lowest block whose columns this CTA owns
+  __syncthreads();
+  for (int J = nblk - 1; J >= my_first_blk; --J) {
+    const int j0 = J * NB;
+    const int n = min(NB, N - j0);
+    const bool owner = j0 >= c0 && j0 < c1;
+    if (owner) {
+      load_diag_block(L + (long long)j0 * ld + j0, ld, n, Ls, rd);
+      if (tid < NB) as[tid] = (tid < n) ? zs[j0 - c0 + tid] : 0.0;
+      __syncthreads();
+      if (tid < 32) {
+        const int lane = tid;
+        double y0 = as[lane], y1 = as[lane + 32];
+        for (int k = NB - 1; k >= 0; --k) {
+          const double num = __shfl_sync(0xffffffffu, (k < 32) ? y0 : y1, k & 31);
+          const double ak = num * rd[k];
+          if (lane == (k & 31)) { if (k < 32) y0 = ak; else y1 = ak; }
+          if (lane < k) y0 = fma(-Ls[k][lane], ak, y0);
+          if (lane + 32 < k) y1 = fma(-Ls[k][lane + 32], ak, y1);
+        }
+        as[lane] = y0;
+        as[lane + 32] = y1;
+      }
+      __syncthreads();
+      if (tid < n) aout[j0 + tid] = as[tid];
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flags + J), "r"(1) : "memory");
+    }
+    // columns of this CTA below block J:  [c0, min(c1, j0))
+    const int ce = min(c1, j0);
+    for (int cb = c0; cb < ce; cb += TRSVP_THREADS) {
+      const int c = cb + tid;
+      double t[NB];
+      if (c < ce) {
+        const double* lc = L + (long long)j0 * ld + c;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) t[i] = (i < n) ? __ldcg(lc + (long long)i * ld) : 0.0;
+      }
+      if (!owner && cb == c0) {   // a_J comes from another CTA: wait for it (once per step), then stage it
+        if (tid == 0) {
+          int v;
+          unsigned spin = 0;
+          do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + J) : "memory");
+            if (v == 0) { __nanosleep(32); if (++spin > (1u << 27)) __trap(); }
+          } while (v == 0);
+        }
+        __syncthreads();
+        if (tid < NB) as[tid] = (tid < n) ? __ldcg(aout + j0 + tid) : 0.0;
+        __syncthreads();
+      }
+      if (c < ce) {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+        for (int i0 = 0; i0 < NB; i0 += 16) {
+#pragma unroll
+          for (int u = 0; u < 16; u += 4) {
+            s0 = fma(t[i0 + u], as[i0 + u], s0);
+            s1 = fma(t[i0 + u + 1], as[i0 + u + 1], s1);
+            s2 = fma(t[i0 + u + 2], as[i0 + u + 2], s2);
+            s3 = fma(t[i0 + u + 3], as[i0 + u + 3], s3);
+          }
+        }
+        zs[c - c0] -= (s0 + s1) + (s2 + s3);
+      }
+    }
+    __syncthreads();   // zs / as settled before the next block
+  }
+}
+
 // var[r] = kss[r] - sum_j V[r][j]^2; one warp per row.
 __global__ void var_rows_kernel(const double* __restrict__ V, long long ldv, int rows, int N,
                                 const double* __restrict__ kss, double* __restrict__ var) {
