@@ -1232,7 +1232,12 @@ int nngp_diag_dmma_peak(nngp_handle* h, double* tflops_out) {
   if (!h || !tflops_out) return NNGP_EINVAL;
   CKR(bind_device(h));
   const int iters = 4096;
-  const int ctas = h->sm_count * 4;
+  // exactly one full wave: every SM holds its maximum number of CTAs.  (With fewer CTAs than slots the block
+  // scheduler may load some SMs with 5 and others with 3 -- the probe then reads 4/5 of the peak.)
+  int per_sm = 4;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dmma_peak_kernel, 256, 0));
+  if (per_sm < 1) per_sm = 1;
+  const int ctas = h->sm_count * per_sm;
   cudaEvent_t a = get_event(h), b = get_event(h);
   for (int w = 0; w < 8; ++w)  // ~35 ms of warm-up so the SM clock is at its loaded value
     dmma_peak_kernel<<<ctas, 256, 0, h->stream>>>(iters, h->lam_d.as<double>());

@@ -266,6 +266,35 @@ def test_full_size_properties_c2(lib, synth):
     assert relmax(m1[:512], rm) < 1e-6 and np.max(np.abs(v1[:512] - rv) / np.abs(rv)) < 1e-6
 
 
+def test_full_size_properties_depth3_16k(lib, synth):
+    """C5-like sizes (N=16384, D=512 with 96 join dims, depth 3; W=512 Cholesky panels): the oracle needs minutes
+    here, so parity rests on size-independent identities -- lambda from the computed diagonal, the posterior at the
+    training rows (mean = y - lambda*alpha, 0 < var < lambda), the closed-form diagonal q_L = q_0 / 2^(L-1), and
+    the persistent kernel against the right-looking path on 40 000 rows (313 row tiles), bit for bit."""
+    xtr, _, xte, _ = synth.make_problem(16384, 40000, 512, join_dims=96)
+    ytr = np.random.default_rng(3).uniform(0.0, 20.0, 16384)      # (the synthetic label saturates at this width)
+    h = lib.Handle(depth=3)
+    h.fit(xtr, ytr)
+    n, d, lam = h.dims()
+    q0 = np.einsum("ij,ij->i", xtr, xtr) / 512
+    assert (n, d) == (16384, 512) and abs(lam - 1e-3 * np.mean(q0) / 4) < 1e-12 * lam
+    alpha = h.get_state(x=False, l=False)["alpha"]
+    mean_tr, var_tr = h.predict(xtr)
+    assert np.max(np.abs(mean_tr - (ytr - lam * alpha))) < 1e-6 * np.max(np.abs(ytr))
+    assert np.all(var_tr > 0) and np.all(var_tr < lam * (1 + 1e-9))
+    kd = np.diag(h.kernel(xtr[:300]))
+    assert np.max(np.abs(kd - q0[:300] / 4)) < 1e-12 * np.max(kd)
+    import os
+    m_f, v_f = h.predict(xte)                                     # 313 row tiles: persistent fused kernel
+    os.environ["NNGP_SMALL_BATCH_TILES"] = "1000000"
+    try:
+        m_s, v_s = h.predict(xte[:6000])                          # right-looking path on a slice
+    finally:
+        del os.environ["NNGP_SMALL_BATCH_TILES"]
+    assert np.array_equal(m_f[:6000], m_s) and np.array_equal(v_f[:6000], v_s)
+    assert np.all(np.isfinite(m_f)) and np.all(v_f > 0)
+
+
 def test_state_roundtrip_and_device_pointers(lib, synth):
     import torch
     xtr, ytr, xte, _ = synth.make_problem(600, 300, 16)
