@@ -65,3 +65,27 @@ def test_no_kernel_uses_local_memory(lib):
     for f, r in regs.items():
         if "gemm_nt_kernel" in f or "trsm_fused_kernel" in f:
             assert r <= 128, (f, r)        # 2 CTAs x 256 threads x 128 registers = one SM's register file
+
+
+def test_stage_release_carries_a_dependence_on_the_fragment_loads(lib):
+    """Regression guard for the ring-stage release hazard: in every kernel built on mma_mainloop the
+    consumer's mbarrier arrive (SASS ``SYNCS.ARRIVE.TRANS64.A1T0``) must take its address from an add whose input is
+    ``seen & zero`` (a ``LOP3.LUT ... 0xc0``) -- i.e. the arrive cannot issue before the fragment LDS results have
+    landed.  If a compiler or a refactor folds that away, the arrive is again free to overtake the loads."""
+    import shutil
+    import subprocess
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    sass = subprocess.run([tool, "-sass", str(lib.LIB_PATH)], capture_output=True, text=True).stdout
+    instrs = [m.group(1).strip() for m in re.finditer(r"/\*[0-9a-f]{4,}\*/\s+(.*?);", sass)]
+    arrives = [i for i, t in enumerate(instrs) if "SYNCS.ARRIVE.TRANS64.A1T0" in t]
+    assert len(arrives) >= 10, "expected the consumer releases of gemm_nt_kernel<0..3> and trsm_fused_kernel"
+    for i in arrives:
+        reg = re.search(r"\[(R\d+)\+", instrs[i]).group(1)
+        add = next((j for j in range(i - 1, max(i - 16, 0), -1)
+                    if re.search(r"IADD\w*(\.\w+)* %s," % reg, instrs[j])), None)
+        assert add is not None, f"arrive address {reg} is not computed by an add: {instrs[max(i - 4, 0):i + 1]}"
+        srcs = set(re.findall(r"R\d+", instrs[add].split(",", 1)[1]))
+        masked = [j for j in range(add - 1, max(add - 60, 0), -1)
+                  if "LOP3.LUT" in instrs[j] and "0xc0" in instrs[j]
+                  and (re.search(r"LOP3\.LUT (?:P\d+, )?(R\d+|RZ),", instrs[j]) or [None, None])[1] in srcs]
+        assert masked, f"no `seen & zero` feeding the arrive address: {instrs[max(add - 6, 0):i + 1]}"
