@@ -58,6 +58,7 @@ struct nngp_handle {
   cudaStream_t stream = nullptr;        // main stream (all stage timing events live here)
   cudaStream_t panel_stream = nullptr;  // high-priority stream: Cholesky panel look-ahead
   cudaStream_t cur = nullptr;           // stream the launch helpers currently target
+  cudaStream_t copy_stream = nullptr;   // H2D of test-row chunks, running ahead of the Gram launches (nngp_predict)
   PFN_encodeTiled encode = nullptr;
   std::string err;
 
@@ -541,11 +542,13 @@ int run_trsv_bwd(nngp_handle* h, const double* L, int64_t ld, int64_t N, double*
 }
 
 // copy a caller matrix (host or device, dense rows x cols) into a padded device matrix (ld), zero pad
-int upload_matrix(nngp_handle* h, const double* src, int64_t rows, int64_t cols, double* dst, int64_t ld) {
-  if (ld != cols) CK(cudaMemsetAsync(dst, 0, (size_t)rows * ld * sizeof(double), h->stream));
+int upload_matrix(nngp_handle* h, const double* src, int64_t rows, int64_t cols, double* dst, int64_t ld,
+                  cudaStream_t stream = nullptr) {
+  if (!stream) stream = h->stream;
+  if (ld != cols) CK(cudaMemsetAsync(dst, 0, (size_t)rows * ld * sizeof(double), stream));
   const bool dev = is_device_ptr(src);
   CK(cudaMemcpy2DAsync(dst, ld * sizeof(double), src, cols * sizeof(double), cols * sizeof(double), rows,
-                       dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+                       dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
   if (!dev) h->st.h2d_bytes += rows * cols * (int64_t)sizeof(double);
   return NNGP_OK;
 }
@@ -657,6 +660,10 @@ int nngp_create(const nngp_config* cfg, nngp_handle** out) {
     return bail(NNGP_ECUDA);
   }
   h->cur = h->stream;
+  if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    fail(h, NNGP_ECUDA, "cudaStreamCreate failed");
+    return bail(NNGP_ECUDA);
+  }
   // Look-ahead can be switched off (see run_potrf): with NNGP_CHOL_LOOKAHEAD=0 the panel stream is not kept.
   {
     const char* e = getenv("NNGP_CHOL_LOOKAHEAD");
@@ -700,6 +707,7 @@ void nngp_destroy(nngp_handle* h) {
   for (auto& r : h->pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   if (h->panel_stream) cudaStreamDestroy(h->panel_stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -1101,24 +1109,43 @@ int nngp_predict(nngp_handle* h, const double* x_test, int64_t T, double* mean_o
   StageTimer t_total(h, &h->st.pred_total_ms);
   std::vector<StageTimer> timers;
   timers.reserve(10 * ((T + TB - 1) / TB) + 8);
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> h2d_spans;   // per block, on the copy stream
+  cudaEvent_t ev_xt_free = nullptr;
   for (int64_t t0 = 0; t0 < T; t0 += TB) {
     const int64_t rows = std::min<int64_t>(TB, T - t0);
-    timers.emplace_back(h, &h->st.h2d_ms);
-    CKR(upload_matrix(h, x_test + t0 * D, rows, D, xt, ldx));
-    timers.back().stop();
-    CKR(check_finite_async(h, xt, ldx, rows, D));
-
+    // Upload and Gram are pipelined in chunks of CH rows: the copy stream runs ahead, the main stream starts the
+    // Gram of a chunk as soon as that chunk has landed -- H2D (and, for pageable host memory, the driver's staging
+    // memcpy, which blocks this thread, not the GPU) hides behind the Gram of the previous chunk.  Rows are
+    // independent, so chunking does not change a bit of the result.
+    const int64_t CH = 16384;
+    const int nchunks = (int)((rows + CH - 1) / CH);
+    cudaEvent_t ev_h2d_a = get_event(h), ev_h2d_b = get_event(h);
+    std::vector<cudaEvent_t> ev_chunk((size_t)nchunks);
+    for (auto& e : ev_chunk) e = get_event(h);
+    if (ev_xt_free) CK(cudaStreamWaitEvent(h->copy_stream, ev_xt_free, 0));   // previous block's Gram has read xt
+    CK(cudaEventRecord(ev_h2d_a, h->copy_stream));
     timers.emplace_back(h, &h->st.pred_gram_ms);
-    row_sqnorm_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, h->stream>>>(xt, ldx, (int)rows, (int)D, sw2, sb2, h->qt.as<double>());
-    h->st.kernel_launches++;
-    CKR(run_gram(h, xt, ldx, rows, h->qt.as<double>(), h->X.as<double>(), ldx, N, h->q.as<double>(), D, blk, ldl, 0,
-                 (ntk && var_out) ? h->blk2.as<double>() : nullptr, h->alpha.as<double>(), h->mean_partial.as<double>()));
+    for (int c = 0; c < nchunks; ++c) {
+      const int64_t c0 = (int64_t)c * CH, cr = std::min<int64_t>(CH, rows - c0);
+      CKR(upload_matrix(h, x_test + (t0 + c0) * D, cr, D, xt + c0 * ldx, ldx, h->copy_stream));
+      CK(cudaEventRecord(ev_chunk[(size_t)c], h->copy_stream));
+      CK(cudaStreamWaitEvent(h->stream, ev_chunk[(size_t)c], 0));
+      CKR(check_finite_async(h, xt + c0 * ldx, ldx, cr, D));
+      double* qt_c = h->qt.as<double>() + c0;
+      double* mp_c = h->mean_partial.as<double>() + c0 * 2 * col_tiles;
+      row_sqnorm_kernel<<<(unsigned)((cr * 32 + 255) / 256), 256, 0, h->stream>>>(xt + c0 * ldx, ldx, (int)cr, (int)D, sw2, sb2, qt_c);
+      h->st.kernel_launches++;
+      CKR(run_gram(h, xt + c0 * ldx, ldx, cr, qt_c, h->X.as<double>(), ldx, N, h->q.as<double>(), D, blk + c0 * ldl, ldl, 0,
+                   (ntk && var_out) ? h->blk2.as<double>() + c0 * ldl : nullptr, h->alpha.as<double>(), mp_c));
+      mean_reduce_kernel<<<(unsigned)((cr + 255) / 256), 256, 0, h->stream>>>(mp_c, 2 * col_tiles, (int)cr, h->mean_d.as<double>() + t0 + c0);
+      h->st.kernel_launches++;
+    }
     timers.back().stop();
-
-    timers.emplace_back(h, &h->st.pred_mean_ms);
-    mean_reduce_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, h->stream>>>(h->mean_partial.as<double>(), 2 * col_tiles, (int)rows, h->mean_d.as<double>() + t0);
-    h->st.kernel_launches++;
-    timers.back().stop();
+    CK(cudaEventRecord(ev_h2d_b, h->copy_stream));
+    h2d_spans.push_back({ev_h2d_a, ev_h2d_b});
+    if (!ev_xt_free) ev_xt_free = get_event(h);
+    CK(cudaEventRecord(ev_xt_free, h->stream));   // the next block's upload may overlap this block's solve
+    for (auto e : ev_chunk) h->ev_pool.push_back(e);
 
     if (var_out) {
       q_final_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, h->stream>>>(h->qt.as<double>(), (int)rows, h->cfg.depth - 1, sw2, sb2, h->kss.as<double>());
@@ -1162,6 +1189,12 @@ int nngp_predict(nngp_handle* h, const double* x_test, int64_t T, double* mean_o
   CK(cudaGetLastError());
   t_total.collect();
   for (auto& t : timers) t.collect();
+  if (ev_xt_free) h->ev_pool.push_back(ev_xt_free);
+  for (auto& sp : h2d_spans) {
+    float ms = 0.f;
+    if (h->cfg.stats_level >= 1 && cudaEventElapsedTime(&ms, sp.first, sp.second) == cudaSuccess) h->st.h2d_ms += ms;
+    h->ev_pool.push_back(sp.first); h->ev_pool.push_back(sp.second);
+  }
   flush_class_events(h);
   if (flags[1]) return fail(h, NNGP_EINVAL, "nngp_predict: non-finite value in x_test");
   h->st.queries += T;
