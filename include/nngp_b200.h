@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define NNGP_B200_ABI_VERSION 3
+#define NNGP_B200_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define NNGP_API __attribute__((visibility("default")))
@@ -148,6 +148,11 @@ NNGP_API int nngp_get_dims(nngp_handle* h, int64_t* N, int64_t* D, double* lambd
 NNGP_API int nngp_get_state(nngp_handle* h, double* x_out, double* l_out, double* alpha_out);
 NNGP_API int nngp_set_state(nngp_handle* h, const double* x, const double* l, const double* alpha, int64_t N,
                    int64_t D, double lambda);
+/* 'ntk' mode only: the state additionally holds M = L^-1 K_dd L^-T (N x N row-major), which the posterior variance
+ * needs.  Export after nngp_fit; import after nngp_set_state.  Until M is set, an imported 'ntk' state
+ * predicts the mean only (variance requests return NNGP_ESTATE). */
+NNGP_API int nngp_get_state_ntk_m(nngp_handle* h, double* m_out);
+NNGP_API int nngp_set_state_ntk_m(nngp_handle* h, const double* m);
 
 /* Gaussian log marginal likelihood of the fitted model (model selection over depth / W_std / b_std /
  * diag_reg -- the reference's abandoned hyper-parameter path, train.py:86-103, active/active_train.py:44-49):

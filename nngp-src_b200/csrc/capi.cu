@@ -68,6 +68,7 @@ struct nngp_handle {
   double lambda = 0.0;
   double lml_terms[2] = {0.0, 0.0};  // {sum log diag(L), y^T (K+lambda I)^-1 y}; valid after nngp_fit
   bool have_lml = false;
+  bool have_M = false;   // NTK mode: M = L^-1 K_dd L^-T is present (nngp_fit or nngp_set_state_ntk_m)
   DevBuf X, q, L, alpha;
   DevBuf Linv;    // inv(L_JJ) of every 64 x 64 diagonal block of L (trtri_diag_kernel), operand of the solves' diagonal step
   DevBuf y;       // raw labels of the last nngp_fit (kept for nngp_append_fit)
@@ -574,7 +575,7 @@ int bind_device(nngp_handle* h) {
   return NNGP_OK;
 }
 
-void drop_fit(nngp_handle* h) { h->fitted = false; h->have_lml = false; h->have_y = false; }
+void drop_fit(nngp_handle* h) { h->fitted = false; h->have_lml = false; h->have_y = false; h->have_M = false; }
 
 int alloc_state(nngp_handle* h, int64_t N, int64_t D) {
   h->N = N; h->D = D;
@@ -845,6 +846,7 @@ int nngp_fit(nngp_handle* h, const double* x_train, const double* y_train, int64
   h->fitted = true;
   h->have_lml = true;
   h->have_y = true;
+  h->have_M = ntk;
   return NNGP_OK;
 }
 
@@ -1076,6 +1078,8 @@ int nngp_predict(nngp_handle* h, const double* x_test, int64_t T, double* mean_o
   if (!h) return NNGP_EINVAL;
   if (!h->fitted) return fail(h, NNGP_ESTATE, "nngp_predict: no fitted model (call nngp_fit or nngp_set_state)");
   if (!x_test || !mean_out || T <= 0) return fail(h, NNGP_EINVAL, "nngp_predict: bad argument (T=%lld)", (long long)T);
+  if (h->cfg.kernel_type == 1 && var_out && !h->have_M)
+    return fail(h, NNGP_ESTATE, "nngp_predict: this imported 'ntk' state has no M yet (nngp_set_state_ntk_m) -- the variance needs it");
   CKR(bind_device(h));
   const int64_t N = h->N, D = h->D, ldx = h->ldx, ldl = h->ldl;
   const double sw2 = h->cfg.sigma_w * h->cfg.sigma_w, sb2 = h->cfg.sigma_b * h->cfg.sigma_b;
@@ -1223,8 +1227,6 @@ int nngp_log_marginal_likelihood(nngp_handle* h, double* lml_out) {
 int nngp_get_state(nngp_handle* h, double* x_out, double* l_out, double* alpha_out) {
   if (!h) return NNGP_EINVAL;
   if (!h->fitted) return fail(h, NNGP_ESTATE, "nngp_get_state: no fitted model");
-  if (h->cfg.kernel_type == 1 && l_out)
-    return fail(h, NNGP_ESTATE, "nngp_get_state: exporting the factor is not supported in 'ntk' mode (the state also holds M)");
   CKR(bind_device(h));
   if (x_out) CKR(download(h, h->X.as<double>(), h->N, h->D, h->ldx, x_out));
   if (l_out) {
@@ -1242,7 +1244,6 @@ int nngp_set_state(nngp_handle* h, const double* x, const double* l, const doubl
                    double lambda) {
   if (!h) return NNGP_EINVAL;
   if (!x || !l || !alpha || N <= 0 || D <= 0) return fail(h, NNGP_EINVAL, "nngp_set_state: bad argument");
-  if (h->cfg.kernel_type == 1) return fail(h, NNGP_ESTATE, "nngp_set_state: not supported in 'ntk' mode");
   CKR(bind_device(h));
   drop_fit(h);
   CKR(alloc_state(h, N, D));
@@ -1257,6 +1258,29 @@ int nngp_set_state(nngp_handle* h, const double* x, const double* l, const doubl
   CK(cudaGetLastError());
   h->lambda = lambda;
   h->fitted = true;
+  return NNGP_OK;
+}
+
+// NTK mode: the fitted state also holds M = L^-1 K_dd L^-T (N x N, symmetric, dense), needed by the posterior variance.
+int nngp_get_state_ntk_m(nngp_handle* h, double* m_out) {
+  if (!h || !m_out) return NNGP_EINVAL;
+  if (!h->fitted || h->cfg.kernel_type != 1 || !h->have_M)
+    return fail(h, NNGP_ESTATE, "nngp_get_state_ntk_m: needs a fitted 'ntk' model that holds M");
+  CKR(bind_device(h));
+  CKR(download(h, h->Mmat.as<double>(), h->N, h->N, h->ldl, m_out));
+  CK(cudaStreamSynchronize(h->stream));
+  return NNGP_OK;
+}
+
+int nngp_set_state_ntk_m(nngp_handle* h, const double* m) {
+  if (!h || !m) return NNGP_EINVAL;
+  if (!h->fitted || h->cfg.kernel_type != 1)
+    return fail(h, NNGP_ESTATE, "nngp_set_state_ntk_m: call nngp_set_state on an 'ntk' handle first");
+  CKR(bind_device(h));
+  CKR(ensure(h, h->Mmat, (size_t)h->N * h->ldl * sizeof(double)));
+  CKR(upload_matrix(h, m, h->N, h->N, h->Mmat.as<double>(), h->ldl));
+  CK(cudaStreamSynchronize(h->stream));
+  h->have_M = true;
   return NNGP_OK;
 }
 

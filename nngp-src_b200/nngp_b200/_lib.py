@@ -64,6 +64,8 @@ EXPORTS = {
     "nngp_get_dims": (C.c_int, [_P, C.POINTER(_I64), C.POINTER(_I64), _DP]),
     "nngp_get_state": (C.c_int, [_P, _P, _P, _P]),
     "nngp_set_state": (C.c_int, [_P, _P, _P, _P, _I64, _I64, C.c_double]),
+    "nngp_get_state_ntk_m": (C.c_int, [_P, _P]),
+    "nngp_set_state_ntk_m": (C.c_int, [_P, _P]),
     "nngp_log_marginal_likelihood": (C.c_int, [_P, _DP]),
     "nngp_active_select": (C.c_int, [_P, _P, _I64, _I64, C.c_int32, C.c_uint64, _P, C.POINTER(_I64), _P]),
     "nngp_append_fit": (C.c_int, [_P, _P, _P, _I64]),
@@ -214,10 +216,22 @@ class Handle:
         self._ck(self._lib.nngp_get_dims(self._h, C.byref(n), C.byref(d), C.byref(lam)))
         return n.value, d.value, lam.value
 
-    def get_state(self, x=True, l=True, alpha=True, out=None):
-        """Copy the fitted state out. ``out`` may be a dict of preallocated arrays/tensors (host or device)."""
+    @property
+    def is_ntk(self) -> bool:
+        return self.cfg.kernel_type == 1
+
+    def get_state(self, x=True, l=True, alpha=True, out=None, m=None):
+        """Copy the fitted state out. ``out`` may be a dict of preallocated arrays/tensors (host or device).
+        In 'ntk' mode the state also holds ``m`` = L^-1 K_dd L^-T (exported whenever ``l`` is, unless m=False)."""
         n, d, lam = self.dims()
         out = dict(out or {})
+        if m is None:
+            m = bool(l) and self.is_ntk
+        if m:
+            if "m" not in out:
+                out["m"] = np.empty((n, n))
+            mp, _m = _ptr(out["m"])
+            self._ck(self._lib.nngp_get_state_ntk_m(self._h, mp))
         if x and "x" not in out:
             out["x"] = np.empty((n, d))
         if l and "l" not in out:
@@ -231,12 +245,17 @@ class Handle:
         out["lambda"] = lam
         return out
 
-    def set_state(self, x, l, alpha, lam):
+    def set_state(self, x, l, alpha, lam, m=None):
         xp, kx = _ptr(x)
         lp, _kl = _ptr(l)
         ap, _ka = _ptr(alpha)
         N, D = kx.shape
         self._ck(self._lib.nngp_set_state(self._h, xp, lp, ap, N, D, float(lam)))
+        if m is not None:                     # 'ntk' mode: the variance also needs M = L^-1 K_dd L^-T
+            mp, km = _ptr(m)
+            if tuple(km.shape) != (N, N):
+                raise ValueError(f"nngp_b200: m must be [{N}, {N}], got {tuple(km.shape)}")
+            self._ck(self._lib.nngp_set_state_ntk_m(self._h, mp))
 
     def active_select(self, x_pool, budget, biased_sample=False, seed=10, return_scores=False):
         """Device-side ``ActiveLearner.active_test`` (active/ActiveLearner.py:43-55): rows of ``x_pool`` to label
@@ -279,16 +298,18 @@ class Handle:
         """Fitted state + hyper-parameters -> .npz (the reference has no model file: it refits on every start,
         neuroestimator/README.md:28-29; its ``load_model`` is a warm-up, estimator.py:37-40)."""
         st = self.get_state()
+        extra = {"m": st["m"]} if self.is_ntk else {}
         np.savez(path, x=st["x"], l=st["l"], alpha=st["alpha"], lam=st["lambda"], depth=self.cfg.depth,
                  sigma_w=self.cfg.sigma_w, sigma_b=self.cfg.sigma_b, diag_reg=self.cfg.diag_reg,
-                 diag_reg_absolute=self.cfg.diag_reg_absolute)
+                 diag_reg_absolute=self.cfg.diag_reg_absolute, kernel_type="ntk" if self.is_ntk else "nngp", **extra)
 
     @classmethod
     def load(cls, path, **kw) -> "Handle":
         z = np.load(path)
+        kt = str(z["kernel_type"]) if "kernel_type" in z.files else "nngp"
         h = cls(depth=int(z["depth"]), sigma_w=float(z["sigma_w"]), sigma_b=float(z["sigma_b"]),
-                diag_reg=float(z["diag_reg"]), diag_reg_absolute=bool(z["diag_reg_absolute"]), **kw)
-        h.set_state(z["x"], z["l"], z["alpha"], float(z["lam"]))
+                diag_reg=float(z["diag_reg"]), diag_reg_absolute=bool(z["diag_reg_absolute"]), kernel_type=kt, **kw)
+        h.set_state(z["x"], z["l"], z["alpha"], float(z["lam"]), m=z["m"] if kt == "ntk" else None)
         return h
 
     def stats(self) -> dict:

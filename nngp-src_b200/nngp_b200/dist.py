@@ -39,29 +39,34 @@ def _comm_device(group=None):
 def broadcast_fit(engine, src: int = 0, group=None):
     """Rank ``src`` holds a fitted engine; on return every rank's engine holds the same state.
 
-    Traffic: 8*(N*N + N*D + N) bytes per receiving rank, once per fit.  Returns (N, D, lambda)."""
+    Traffic: 8*(N*N + N*D + N) bytes per receiving rank, once per fit (twice the N*N part in 'ntk' mode, whose state
+    also holds M = L^-1 K_dd L^-T).  Returns (N, D, lambda)."""
     import torch
     dist = _dist()
     rank = dist.get_rank(group)
     dev = _comm_device(group)
-    hdr = torch.zeros(3, dtype=torch.float64, device=dev)
+    hdr = torch.zeros(4, dtype=torch.float64, device=dev)
     if rank == src:
         n, d, lam = engine.dims()
-        hdr[0], hdr[1], hdr[2] = n, d, lam
+        hdr[0], hdr[1], hdr[2], hdr[3] = n, d, lam, float(bool(getattr(engine, "is_ntk", False)))
     dist.broadcast(hdr, src=src, group=group)
-    n, d, lam = int(hdr[0].item()), int(hdr[1].item()), float(hdr[2].item())
+    n, d, lam, ntk = int(hdr[0].item()), int(hdr[1].item()), float(hdr[2].item()), bool(hdr[3].item())
     x = torch.empty((n, d), dtype=torch.float64, device=dev)
     l = torch.empty((n, n), dtype=torch.float64, device=dev)
     alpha = torch.empty(n, dtype=torch.float64, device=dev)
+    m = torch.empty((n, n), dtype=torch.float64, device=dev) if ntk else None
     if rank == src:
-        engine.get_state(out={"x": x, "l": l, "alpha": alpha})
-    for t in (x, l, alpha):
+        engine.get_state(out={"x": x, "l": l, "alpha": alpha, **({"m": m} if ntk else {})})
+    for t in (x, l, alpha) + ((m,) if ntk else ()):
         dist.broadcast(t, src=src, group=group)
     if rank != src:
-        engine.set_state(x, l, alpha, lam)
+        if ntk:
+            engine.set_state(x, l, alpha, lam, m=m)
+        else:
+            engine.set_state(x, l, alpha, lam)
     if dev.type == "cuda":
         torch.cuda.synchronize(dev)
-    del x, l, alpha
+    del x, l, alpha, m
     return n, d, lam
 
 

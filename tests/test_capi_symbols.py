@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(lib):
     cdll = ctypes.CDLL(str(lib.LIB_PATH))
     for name in declared_functions():
         assert hasattr(cdll, name), f"{name} declared in include/nngp_b200.h but not exported"
-    assert cdll.nngp_abi_version() == 3
+    assert cdll.nngp_abi_version() == 4
 
 
 def test_struct_layouts_match_header(lib):

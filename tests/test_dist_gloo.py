@@ -52,6 +52,21 @@ class FakeEngine:
         return mean, oracle.final_diag(oracle.layer0_diag(xt)) - np.einsum("ij,ij->j", v, v)
 
 
+class FakeNtkEngine(FakeEngine):
+    """State-only double of a Handle(kernel_type='ntk'): {x, l, alpha, lambda, m}."""
+    is_ntk = True
+
+    def get_state(self, out=None):
+        import torch
+        for k in ("x", "l", "alpha", "m"):
+            out[k].copy_(torch.from_numpy(np.ascontiguousarray(self.state[k])))
+        return out
+
+    def set_state(self, x, l, alpha, lam, m=None):
+        self.state = {"x": x.numpy().copy(), "l": l.numpy().copy(), "alpha": alpha.numpy().copy(), "lambda": lam,
+                      "m": m.numpy().copy()}
+
+
 def _worker(rank, world, port, q):
     sys.path[:0] = [str(ROOT), str(ROOT / "nngp-src_b200"), str(ROOT / "oracle"), str(ROOT / "tests")]
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -66,7 +81,15 @@ def _worker(rank, world, port, q):
     mean, var = ndist.sharded_predict(eng, xte, want_var=True, gather=True)
     own_m, own_v = ndist.sharded_predict(eng, xte, want_var=True, gather=False)
     m_only, none = ndist.sharded_predict(eng, xte, want_var=False, gather=True)
-    q.put((rank, n, d, lam, mean, var, own_m, m_only, none is None))
+    # 'ntk' engines carry a fourth state tensor (M): it must arrive on the other rank too
+    ntk_eng = FakeNtkEngine()
+    if rank == 0:
+        ntk_eng.state = {"x": xtr, "l": np.tril(np.outer(ytr, ytr)), "alpha": ytr, "lambda": 0.25,
+                         "m": np.arange(96.0 * 96.0).reshape(96, 96)}
+    ndist.broadcast_fit(ntk_eng, src=0)
+    ntk_ok = bool(np.array_equal(ntk_eng.state["m"], np.arange(96.0 * 96.0).reshape(96, 96))
+                  and ntk_eng.state["lambda"] == 0.25 and np.array_equal(ntk_eng.state["alpha"], ytr))
+    q.put((rank, n, d, lam, mean, var, own_m, m_only, (none is None) and ntk_ok))
     dist.barrier()
     dist.destroy_process_group()
 

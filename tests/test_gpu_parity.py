@@ -356,8 +356,33 @@ def test_ntk_fit_predict_match_oracle(lib, synth, n, t, d, depth):
     small.fit(xtr, ytr)
     m2, v2 = small.predict(xte)                      # 128-row blocks: bitwise invariant to the blocking
     assert np.array_equal(m2, mean) and np.array_equal(v2, var)
+    assert set(h.get_state(x=False)) == {"l", "alpha", "m", "lambda"}     # 'ntk' state also carries M
+
+
+def test_ntk_state_roundtrip_and_model_file(lib, synth, tmp_path):
+    """'ntk' state = {X, L, alpha, lambda, M}: export -> import on a fresh handle (what broadcast_fit does on the other
+    ranks) and save -> load give bitwise the same predictions; without M an imported state serves the mean only."""
+    xtr, ytr, xte, _ = synth.make_problem(500, 200, 16)
+    h = lib.Handle(kernel_type="ntk")
+    h.fit(xtr, ytr)
+    mean, var = h.predict(xte)
+    st = h.get_state()
+    assert set(st) == {"x", "l", "alpha", "m", "lambda"} and st["m"].shape == (500, 500)
+    assert np.allclose(st["m"], st["m"].T, rtol=0, atol=1e-9 * np.max(np.abs(st["m"])))
+    h2 = lib.Handle(kernel_type="ntk")
+    h2.set_state(st["x"], st["l"], st["alpha"], st["lambda"])
+    m_only, _ = h2.predict(xte, want_var=False)
+    assert np.array_equal(m_only, mean)
     with pytest.raises(lib.NngpError):
-        h.get_state()                                 # factor export is NNGP-mode only
+        h2.predict(xte)                                     # variance needs M
+    h2.set_state(st["x"], st["l"], st["alpha"], st["lambda"], m=st["m"])
+    m2, v2 = h2.predict(xte)
+    assert np.array_equal(m2, mean) and np.array_equal(v2, var)
+    h.save(tmp_path / "ntk.npz")
+    h3 = lib.Handle.load(tmp_path / "ntk.npz")
+    assert h3.is_ntk
+    m3, v3 = h3.predict(xte)
+    assert np.array_equal(m3, mean) and np.array_equal(v3, var)
 
 
 def test_log_marginal_likelihood_and_model_file(lib, synth, tmp_path):
