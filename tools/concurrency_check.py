@@ -13,6 +13,7 @@ from nngp_b200 import _lib, synth  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+nthreads = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 xtr, ytr, xte, _ = synth.make_problem(n, 8192, 128)
 ytr = np.ones_like(ytr)
 ref_h = _lib.Handle()
@@ -37,9 +38,9 @@ def worker(tid):
                 print(f"thread {tid} rep {r}: prediction differs", flush=True)
 
 
-ts = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+ts = [threading.Thread(target=worker, args=(i,)) for i in range(nthreads)]
 for t in ts:
     t.start()
 for t in ts:
     t.join()
-print(f"N={n} threads=2 reps={reps}: mismatching fits {bad['fit']}, mismatching predictions {bad['predict']}")
+print(f"N={n} threads={nthreads} reps={reps}: mismatching fits {bad['fit']}, mismatching predictions {bad['predict']}")
