@@ -439,12 +439,19 @@ int run_trsm_fused(nngp_handle* h, double* B, int64_t ldb, int64_t rows, const d
   CKR(get_tmap(h, L, N, N, ldl, GEMM_BN, &tmL));
   CKR(get_tmap(h, Linv, round_up(N, NB), NB, NB, GEMM_BN, &tmW));
   const long long total = (long long)p.row_tiles * p.col_blocks;
-  int grid = (int)std::min<long long>(total, 2LL * h->sm_count);
-  if (p.row_tiles < grid) grid = p.row_tiles;  // fewer row tiles than CTA slots: one CTA per row tile
+  // Fewer row tiles than CTA slots: several CTAs work on the same row tile at different J, each consuming the
+  // column blocks of V as their producers publish them (software pipeline along J, see the gate in the kernel).
+  const int grid = (int)std::min<long long>(total, 2LL * h->sm_count);
   p.static_sched = (p.row_tiles % grid == 0) ? 1 : 0;
   cudaEvent_t ev;
   class_begin(h, EV_GEMM, &ev);
-  trsm_fused_kernel<<<grid, GEMM_THREADS, TF_SMEM_BYTES, h->stream>>>(tmB, tmL, tmW, p);
+  // Plenty of row tiles (or exactly one static round of them): dependencies are practically always met when an item
+  // starts, and the ungated kernel is 0.5 % faster (34.8 vs 34.6 TFLOP/s at C2).  Measured at N = 8192: 296 tiles
+  // 81 ms ungated / 83 gated; 313 tiles 92 ms ungated / 86 gated.
+  if (p.static_sched || p.row_tiles >= grid + grid / 4)
+    trsm_fused_kernel<false><<<grid, GEMM_THREADS, TF_SMEM_BYTES, h->stream>>>(tmB, tmL, tmW, p);
+  else                       // several CTAs per row tile: pipeline along J
+    trsm_fused_kernel<true><<<grid, GEMM_THREADS, TF_SMEM_BYTES, h->stream>>>(tmB, tmL, tmW, p);
   class_end(h, EV_GEMM, ev);
   CK(cudaGetLastError());
   h->st.kernel_launches++;
@@ -488,17 +495,18 @@ int run_trsm_right(nngp_handle* h, double* B, int64_t ldb, int64_t rows, const d
   return NNGP_OK;
 }
 
-// Row-tile count up to which the right-looking path is used.  With R <= 2 x SMs row tiles the persistent kernel runs
-// one CTA per row tile and takes the time of ONE tile's N/64-item chain: ~42 ms at N = 8192 while every CTA has an
-// SM to itself (R <= 148), ~78 ms once some SMs hold two (measured at R = 157); the right-looking path scales
-// with the rows (21.6 ms at R = 64, 37 ms at R = 120).  Crossover ~ 1.5 x SMs.  Read on every call so tests / A-B
-// runs can flip it inside one process.
+// Row-tile count up to which the right-looking path is used: 0, i.e. never, by default.  Since the persistent kernel
+// gates every operand tile on its producer's progress (several CTAs pipeline along J inside one row tile) it is
+// the faster path at every batch size measured (N = 8192: 1 row 2.0 vs 2.6 ms, 1024 rows 4.0 vs 6.1, 8192 rows
+// 19.2 vs 21.6, 20 000 rows 44 vs 48 ms).  The right-looking path stays as the independent implementation the
+// parity tests cross-check bit for bit.  Read on every call so tests / A-B runs can flip it inside one process.
 int small_batch_row_tiles(const nngp_handle* h) {
+  (void)h;
   const char* e = getenv("NNGP_SMALL_BATCH_TILES");
-  return e ? atoi(e) : 3 * h->sm_count / 2;
+  return e ? atoi(e) : 0;
 }
 
-// V = K_* L^-T (+ variance): persistent fused kernel for large blocks, right-looking steps for small ones.
+// V = K_* L^-T (+ variance): the persistent fused kernel, or (on request) the right-looking steps.
 int run_predict_solve(nngp_handle* h, double* B, int64_t ldb, int64_t rows, const double* L, int64_t ldl, int64_t N,
                       const double* kss, double* var) {
   const double* Linv = h->Linv.as<double>();   // L is always the handle's factor
@@ -682,7 +690,8 @@ int nngp_create(const nngp_config* cfg, nngp_handle** out) {
   cudaError_t e2 = cudaFuncSetAttribute(gemm_nt_kernel<EPI_SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
   if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(gemm_nt_kernel<EPI_ROWDOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
   cudaError_t e3 = cudaFuncSetAttribute(trsm_rows_64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM_BYTES);
-  if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(trsm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM_BYTES);
+  if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(trsm_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM_BYTES);
+  if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(trsm_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM_BYTES);
   if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(gemm_nt_kernel<EPI_DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
     fail(h, NNGP_ECUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s",

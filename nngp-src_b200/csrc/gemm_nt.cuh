@@ -229,10 +229,16 @@ __device__ __forceinline__ void ring_prologue(const TileSrc& src, uint8_t* ringA
 #ifndef NNGP_RELEASE_AT
 #define NNGP_RELEASE_AT 0  // 0..3: release k-tile kt-1 after the k4-th fragment loads of k-tile kt; 4: at the end of kt itself
 #endif
-template <int STAGES>
+struct NoGate {  // default refill gate: operand tiles are always ready to be loaded
+  __device__ __forceinline__ void operator()(int) const {}
+};
+// `gate(kt)` is called by thread 0 right before it issues the TMA loads of k-tile kt (refills only; the caller
+// gates its own prologue): the persistent solve uses it to wait until the producer of that k-tile's A operand
+// (another CTA) has published it.
+template <int STAGES, class Gate = NoGate>
 __device__ __forceinline__ void mma_mainloop(double (&acc)[4][4][2], const TileSrc& src, uint8_t* ringA, uint8_t* ringB,
                                              uint64_t* full_bar, uint64_t* empty_bar, int& stage, uint32_t& phase,
-                                             int ktiles, int wm, int wn, int lane, uint32_t zero) {
+                                             int ktiles, int wm, int wn, int lane, uint32_t zero, Gate gate = Gate()) {
   const int g = lane >> 2, t = lane & 3;
   // Which k does lane (g, t) feed into DMMA step s?  Any bijection (s, t) -> 0..15 is a valid GEMM as long as the A
   // and the B fragment use the same one.  We use  k = 8*(t>>1) + 2*s + (t&1):  logical 16-byte chunk 4*(t>>1) + s,
@@ -253,6 +259,7 @@ __device__ __forceinline__ void mma_mainloop(double (&acc)[4][4][2], const TileS
     if (lane == 0) mbar_arrive_addr(smem_u32(&empty_bar[s]) + (seen & zero));
     if (threadIdx.x == 0 && kdone + STAGES < ktiles) {
       mbar_wait(&empty_bar[s], ph);  // all 8 warps are done with this stage in this round
+      gate(kdone + STAGES);
       ring_issue<STAGES>(src, ringA, ringB, full_bar, s, kdone + STAGES);
     }
     __syncwarp();

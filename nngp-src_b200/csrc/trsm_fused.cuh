@@ -60,6 +60,11 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
+// PIPE = false: an item waits (once, up front) until all the column blocks it consumes are published -- the variant
+//   for blocks with at least as many row tiles as CTAs, where that is practically always already the case.
+// PIPE = true: every operand-tile load is gated on its producer's progress, so the CTAs working on one row tile
+//   pipeline along J -- the variant for few row tiles (a handful of queries up to ~37 000).
+template <bool PIPE>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmL,
                   const __grid_constant__ CUtensorMap tmW, const TrsmFusedParams p) {
@@ -96,13 +101,19 @@ trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
 
   int next_static = blockIdx.x;
   for (;;) {
-    if (tid == 0) *s_item = p.static_sched ? next_static : atomicAdd(p.counter, 1);
+    if (tid == 0) {
+      const int it = p.static_sched ? next_static : atomicAdd(p.counter, 1);
+      s_item[0] = it;
+      // PIPE: how far is this item's row tile already solved?  (decides between the ungated and the gated main loop)
+      if (PIPE) s_item[1] = (it < total && it >= p.row_tiles) ? ld_acquire_gpu(p.progress + it % p.row_tiles) : 0;
+    }
     next_static += gridDim.x;
     __syncthreads();  // publishes the item; also: nobody still uses the ring / the scratch of the last item
-    const int item = *s_item;
+    const int item = s_item[0];
     if (item >= total) break;
     const int J = item / p.row_tiles;
     const int r = item - J * p.row_tiles;
+    const bool all_ready = !PIPE || s_item[1] >= J;   // CTA-uniform: every column block this item consumes is published
     const int ktiles = J * (NB / GEMM_BK);
     const int col0 = J * NB;
     const int nb = min(NB, p.N - col0);
@@ -111,16 +122,36 @@ trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
     TileSrc src;
     src.tmA = &tmB; src.tmB = &tmL;
     src.a_col0 = 0; src.a_row = row0; src.b_col0 = 0; src.b_row = col0;
-    if (tid == 0) {
-      if (J > 0) {
-        // bounded like mbar_wait: a scheduling bug traps (CUDA error at the next sync) instead of hanging the GPU
-        for (unsigned spin = 0; ld_acquire_gpu(p.progress + r) < J; ++spin) {
+    // The V operand of k-tile kt is column block kt/4 of this row tile, produced by item (r, kt/4): possibly by
+    // another CTA, possibly still in flight.  Thread 0 gates every TMA issue on progress[r] > kt/4 (cached: one
+    // acquire per newly needed block), so an item starts consuming the blocks that exist instead of waiting for all
+    // of them -- with few row tiles the items of one row tile form a software pipeline along J across the CTAs.
+    // Claims are handed out in J-major order, so whatever this CTA waits for is owned by a running CTA.
+    int known = PIPE ? s_item[1] : 0;   // progress[r] as last seen by thread 0
+    auto gate = [&](int kt) {
+      const int need = kt / (NB / GEMM_BK) + 1;
+      if (known < need) {
+        for (unsigned spin = 0; (known = ld_acquire_gpu(p.progress + r)) < need; ++spin) {
           __nanosleep(64);
-          if (spin > (1u << 27)) __trap();
+          if (spin > (1u << 27)) __trap();   // bounded like mbar_wait: a scheduling bug traps instead of hanging
         }
         fence_proxy_async_all();  // V was written through the generic proxy by other CTAs -> read by TMA
       }
-      ring_prologue<TF_STAGES>(src, ringA, ringB, full_bar, stage, ktiles);
+    };
+    if (tid == 0) {
+      if (all_ready) {   // nothing (more) to wait for: plain prologue
+        if (!PIPE) { if (J > 0) gate(ktiles - 1); }   // the up-front wait for item (r, J-1) (+ proxy fence)
+        else if (J > 0) fence_proxy_async_all();
+        ring_prologue<TF_STAGES>(src, ringA, ringB, full_bar, stage, ktiles);
+      } else {
+        const int n0 = ktiles < TF_STAGES ? ktiles : TF_STAGES;
+        int st = stage;
+        for (int i = 0; i < n0; ++i) {
+          gate(i);
+          ring_issue<TF_STAGES>(src, ringA, ringB, full_bar, st, i);
+          if (++st == TF_STAGES) st = 0;
+        }
+      }
     }
 
     double acc[4][4][2];
@@ -145,7 +176,10 @@ trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
       }
     }
 
-    mma_mainloop<TF_STAGES>(acc, src, ringA, ringB, full_bar, empty_bar, stage, phase, ktiles, wm, wn, lane, p.zero);
+    if (all_ready)   // (PIPE: two instantiations of the loop in one kernel)
+      mma_mainloop<TF_STAGES>(acc, src, ringA, ringB, full_bar, empty_bar, stage, phase, ktiles, wm, wn, lane, p.zero);
+    else
+      mma_mainloop<TF_STAGES>(acc, src, ringA, ringB, full_bar, empty_bar, stage, phase, ktiles, wm, wn, lane, p.zero, gate);
 
     // ---- diagonal step: V[r, J] = R * W_J^T on the tensor pipe -------------------------------------------
     __syncthreads();  // every warp has left the ring (each warp's last release waited for its fragment loads)

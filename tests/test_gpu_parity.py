@@ -172,6 +172,22 @@ def test_small_batch_and_persistent_solve_paths_agree_bitwise(lib, synth, monkey
     assert relmax(m_s, rm) < 1e-6 and relmax(v_s, rv) < 1e-6
 
 
+def test_pipelined_and_ungated_kernel_variants_agree_bitwise(lib, synth):
+    """trsm_fused_kernel<PIPE=false> (many row tiles: one up-front wait per item) and <PIPE=true> (few row tiles:
+    every operand tile gated on its producer, several CTAs pipelining along J inside a row tile) are the same
+    arithmetic: a row's result does not depend on which variant -- i.e. on how many rows came with it."""
+    xtr, ytr, _, _ = synth.make_problem(1100, 4, 20)
+    xte = synth.encodings(48000, 20, 7)
+    h = lib.Handle()
+    h.fit(xtr, ytr)
+    m_big, v_big = h.predict(xte)                      # 375 row tiles -> ungated variant
+    for rows in (1, 130, 5000, 37888):                 # 1 .. 296 row tiles -> pipelined variant (296: static, ungated)
+        m, v = h.predict(xte[:rows])
+        assert np.array_equal(m, m_big[:rows]) and np.array_equal(v, v_big[:rows]), rows
+    m_tail, v_tail = h.predict(xte[40000:])            # other rows, pipelined
+    assert np.array_equal(m_tail, m_big[40000:]) and np.array_equal(v_tail, v_big[40000:])
+
+
 def test_repeated_fits_are_bit_identical(lib, synth):
     """Race detector of last resort (compute-sanitizer is closed on this pool): the same fit + predict, repeated on
     three alternating handles, must give identical bits (this is what exposed the look-ahead corruption)."""
