@@ -405,23 +405,8 @@ int run_potrf(nngp_handle* h, double* A, int64_t ld, int64_t N, int64_t extra = 
   return NNGP_OK;
 }
 
-// B (rows x N, ldb) <- B * L^-T  (solve X L^T = B), L lower N x N row-major: left-looking over
-// 64-wide column blocks; the update is one DMMA GEMM with K = j0, the diagonal solve is per row.
-int run_trsm_rlt(nngp_handle* h, double* B, int64_t ldb, int64_t rows, const double* L, int64_t ldl, int64_t N) {
-  MatView Bv{B, rows, N, ldb}, Lv{L, N, N, ldl};
-  const int grid = (int)((rows + TRSM_ROWS - 1) / TRSM_ROWS);
-  for (int64_t j0 = 0; j0 < N; j0 += NB) {
-    const int64_t nb = std::min<int64_t>(NB, N - j0);
-    if (j0 > 0) CKR(run_gemm_sub(h, Bv, 0, 0, Lv, j0, 0, rows, nb, j0, B + j0, ldb, 0));
-    trsm_rows_64_kernel<<<grid, TRSM_ROWS, TRSM_SMEM_BYTES, h->stream>>>(B + j0, ldb, (int)rows, L + j0 * ldl + j0, ldl,
-                                                                        (int)nb);
-    h->st.kernel_launches++;
-  }
-  CK(cudaGetLastError());
-  return NNGP_OK;
-}
-
-// Same solve as run_trsm_rlt plus the variance, as ONE persistent kernel (trsm_fused.cuh).
+// B (rows x N, ldb) <- B * L^-T  (solve X L^T = B; L lower N x N row-major) plus, optionally, the posterior
+// variance of every row, as ONE persistent kernel (trsm_fused.cuh).
 int run_trsm_fused(nngp_handle* h, double* B, int64_t ldb, int64_t rows, const double* L, int64_t ldl, int64_t N,
                    const double* Linv, const double* kss, double* var) {
   TrsmFusedParams p{};
@@ -513,11 +498,6 @@ int run_predict_solve(nngp_handle* h, double* B, int64_t ldb, int64_t rows, cons
   const int64_t row_tiles = (rows + GEMM_BM - 1) / GEMM_BM;
   if (row_tiles <= small_batch_row_tiles(h)) return run_trsm_right(h, B, ldb, rows, L, ldl, N, Linv, kss, var);
   return run_trsm_fused(h, B, ldb, rows, L, ldl, N, Linv, kss, var);
-}
-
-bool use_fused_trsm() {
-  static int v = [] { const char* e = getenv("NNGP_PREDICT_TRSM"); return (e && !strcmp(e, "steps")) ? 0 : 1; }();
-  return v != 0;
 }
 
 // out <- L^-T z  (blocked backward substitution; z is destroyed; reads L exactly once)
@@ -1176,17 +1156,9 @@ int nngp_predict(nngp_handle* h, const double* x_test, int64_t T, double* mean_o
         ntk_var_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, h->stream>>>(h->kss.as<double>(), h->partial.as<double>(), col_tiles, (int)rows, h->cross.as<double>(), h->var_d.as<double>() + t0);
         h->st.kernel_launches += 2;
         timers.back().stop();
-      } else if (use_fused_trsm()) {
+      } else {
         timers.emplace_back(h, &h->st.pred_trsm_ms);   // solve + variance in one persistent kernel
         CKR(run_predict_solve(h, blk, ldl, rows, h->L.as<double>(), ldl, N, h->kss.as<double>(), h->var_d.as<double>() + t0));
-        timers.back().stop();
-      } else {
-        timers.emplace_back(h, &h->st.pred_trsm_ms);
-        CKR(run_trsm_rlt(h, blk, ldl, rows, h->L.as<double>(), ldl, N));
-        timers.back().stop();
-        timers.emplace_back(h, &h->st.pred_var_ms);
-        var_rows_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, h->stream>>>(blk, ldl, (int)rows, (int)N, h->kss.as<double>(), h->var_d.as<double>() + t0);
-        h->st.kernel_launches++;
         timers.back().stop();
       }
     }

@@ -1,12 +1,13 @@
 // dense_kernels.cuh -- the small kernels around the DMMA GEMM core:
 //   row_sqnorm / q_final          layer-0 kernel diagonal and K(x,x)            (K2, K9)
 //   diag_reg                      lambda = diag_reg * trace(K)/N ; K += lambda I (K4)
-//   potf2_64                      64x64 diagonal-block Cholesky in shared memory  (K5 panel)
-//   trsm_rows_64                  X L_JJ^T = B, one thread per row                (K5 panel, K10)
-//   trsv_bwd_step                 blocked backward substitution (the forward one rides through
+//   potf2_64                      64x64 diagonal-block Cholesky, 4 x 4 register blocks            (K5 panel)
+//   trsm_rows_64                  X L_JJ^T = B, one thread per row                               (K5 panel)
+//   trtri_diag                    inv(L_JJ) of every diagonal block: operand of the solves' diagonal step (K10)
+//   trsv_bwd_persistent / _step   backward substitution L^T alpha = z (the forward one rides through
 //                                 the Cholesky as an extra row of the factor buffer)              (K6)
 //   mean_reduce                   finishes mean = K_* alpha (the GEMV itself is fused into the Gram epilogue) (K8)
-//   var_rows                      var = K(x,x) - ||V_row||^2, one warp per row     (K10/K11)
+//   rowdot / ntk_var / transpose  NTK-mode variance pieces;  lml_terms, finite_check, zero_upper, dmma_peak
 // All reductions have a fixed order: results are bitwise reproducible and independent of how
 // test rows are sharded over GPUs.
 #pragma once
@@ -443,33 +444,6 @@ __global__ void __launch_bounds__(TRSVP_THREADS) trsv_bwd_persistent_kernel(cons
     }
     __syncthreads();   // zs / as settled before the next block
   }
-}
-
-// var[r] = kss[r] - sum_j V[r][j]^2; one warp per row.
-__global__ void var_rows_kernel(const double* __restrict__ V, long long ldv, int rows, int N,
-                                const double* __restrict__ kss, double* __restrict__ var) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= rows) return;
-  const double* vr = V + (long long)warp * ldv;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  int j = 2 * lane;
-  for (; j + 193 < N; j += 256) {
-    const double2 b0 = *reinterpret_cast<const double2*>(vr + j);
-    const double2 b1 = *reinterpret_cast<const double2*>(vr + j + 64);
-    const double2 b2 = *reinterpret_cast<const double2*>(vr + j + 128);
-    const double2 b3 = *reinterpret_cast<const double2*>(vr + j + 192);
-    s0 = fma(b0.x, b0.x, s0); s0 = fma(b0.y, b0.y, s0);
-    s1 = fma(b1.x, b1.x, s1); s1 = fma(b1.y, b1.y, s1);
-    s2 = fma(b2.x, b2.x, s2); s2 = fma(b2.y, b2.y, s2);
-    s3 = fma(b3.x, b3.x, s3); s3 = fma(b3.y, b3.y, s3);
-  }
-  for (; j < N; j += 64) {
-    s0 = fma(vr[j], vr[j], s0);
-    if (j + 1 < N) s0 = fma(vr[j + 1], vr[j + 1], s0);
-  }
-  const double s = warp_sum((s0 + s1) + (s2 + s3));
-  if (lane == 0) var[warp] = kss[warp] - s;
 }
 
 // Single CTA (1024 threads), fixed-order reductions for the log marginal likelihood:
