@@ -92,3 +92,59 @@ def test_estimator_uses_the_batch_encoder(encmod, gold, monkeypatch):
     assert mean_p.shape == (61,) and std_p.shape == (61,)
     assert np.allclose(mean_p[:60], np.tile(rm, 3), rtol=1e-12) and np.allclose(std_p[:60], np.tile(np.sqrt(rv), 3), rtol=1e-9)
     assert np.isclose(mean_p[60], rm[3], rtol=1e-12)
+
+
+REFERENCE_ESTIMATOR = "/root/reference/neuroestimator/estimator/estimator.py"
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(REFERENCE_ESTIMATOR),
+                    reason="the reference tree is only mounted in the build container")
+def test_unmodified_reference_estimator_runs_on_the_shims(encmod, gold, monkeypatch):
+    """Drop-in check for row a7: the reference's OWN neuroestimator/estimator/estimator.py, imported unmodified with
+    nngp-src_b200/compat on sys.path, builds its kernel through the stax shim, fits lazily in load_model() and serves
+    predict(query_lines) -> (mean, std) through the mirror; `estimator.util.load_training_schema_data` (pandas schema
+    loading, out of scope) is stubbed to hand over the fixture's training set and the C++ batch encoder, whose
+    parse_line_without_card_then_encode the reference's per-line loop calls."""
+    import importlib.util
+    import sys
+    import types
+    from pathlib import Path
+    import nngp_oracle as oracle
+    from nngp_b200 import runtime
+
+    class FakeHandle:
+        def __init__(self, spec, diag_reg, absolute):
+            self.spec, self.diag_reg = spec, diag_reg
+
+        def fit(self, x, y):
+            self.f = oracle.Fit(x, y, self.spec.depth, diag_reg=self.diag_reg)
+
+        def predict(self, x, want_var=True):
+            return self.f.predict(x, want_var)
+
+    monkeypatch.setattr(runtime, "new_handle", lambda spec, diag_reg=0.0, diag_reg_absolute=False, kernel_type="nngp": FakeHandle(spec, diag_reg, diag_reg_absolute))
+    enc = encmod.BatchEncoder(str(gold["schema"]))
+    y = np.log2(gold["cards"])[:, None]
+    compat = str(Path(__file__).resolve().parents[1] / "nngp-src_b200" / "compat")
+    pkg = types.ModuleType("estimator")
+    pkg.__path__ = []
+    util = types.ModuleType("estimator.util")
+    util.load_training_schema_data = lambda *a, **k: (gold["x_train"], y, enc)
+    sys.path.insert(0, compat)
+    sys.modules["estimator"], sys.modules["estimator.util"] = pkg, util
+    try:
+        spec = importlib.util.spec_from_file_location("estimator.estimator", REFERENCE_ESTIMATOR)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules["estimator.estimator"] = mod
+        spec.loader.exec_module(mod)
+        est = mod.Estimator("tpch", "/data", "/queries")
+        est.load_model()
+        mean, std = est.predict([str(l) for l in gold["lines"][:20]])
+        rm, rv = oracle.Fit(gold["x_train"], y).predict(gold["x"][:20])
+        assert mean.shape == (20,) and std.shape == (20,)
+        assert np.allclose(mean, rm) and np.allclose(std, np.sqrt(rv))
+    finally:
+        sys.path.remove(compat)
+        for m in [k for k in sys.modules if k == "jax" or k.startswith("jax.") or k == "neural_tangents"
+                  or k == "estimator" or k.startswith("estimator.")]:
+            del sys.modules[m]

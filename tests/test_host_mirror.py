@@ -183,3 +183,61 @@ def test_compat_shims_resolve_to_the_mirror():
         sys.path.remove(compat)
         for m in [k for k in sys.modules if k == "jax" or k.startswith("jax.") or k == "neural_tangents"]:
             del sys.modules[m]
+
+
+REFERENCE_AL = "/root/reference/active/ActiveLearner.py"
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(REFERENCE_AL),
+                    reason="the reference tree is only mounted in the build container")
+def test_unmodified_reference_active_learner_runs_on_the_shims(fake_engine):
+    """Drop-in check for row a8: the reference's OWN active/ActiveLearner.py, imported unmodified from the reference
+    tree with nngp-src_b200/compat on sys.path (jax / neural_tangents shims), drives the mirror -- train, test,
+    active_test (np.sqrt(np.diag(pred_cov)) on the lazy covariance, argsort tail), merge_data, refit -- and ends with
+    the same training set as nngp_b200.active.ActiveLearner.  Only `util` (seaborn / matplotlib plotting helpers,
+    out of scope) is stubbed."""
+    import importlib.util
+    import sys
+    import types
+    from pathlib import Path
+    from nngp_b200 import synth
+    from nngp_b200.active import ActiveLearner as MirrorLearner
+    compat = str(Path(__file__).resolve().parents[1] / "nngp-src_b200" / "compat")
+    util_stub = types.ModuleType("util")
+
+    class PredictionStatistics:                      # util.py:152-167 prints q-error tables; irrelevant here
+        def get_prediction_details(self, *a, **k):
+            return None
+
+    util_stub.PredictionStatistics = PredictionStatistics
+    sys.path.insert(0, compat)
+    sys.modules["util"] = util_stub
+    try:
+        spec = importlib.util.spec_from_file_location("reference_active_learner", REFERENCE_AL)
+        ref_mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref_mod)
+        nt = importlib.import_module("neural_tangents")
+        _, _, kernel_fn = nt.stax.serial(nt.stax.Dense(512), nt.stax.Relu(), nt.stax.Dense(1))
+        xtr, ytr, xpool, ypool = synth.make_problem(50, 80, 8)
+        xval, yval = synth.encodings(20, 8, 5), None
+        yval = synth.labels(xval)
+        args = types.SimpleNamespace(budget=15, active_iters=2, kernel_type="nngp", biased_sample=False)
+        learner = ref_mod.ActiveLearner(args)
+        learner.active_train(kernel_fn, xtr, ytr[:, None], xpool, ypool[:, None], xval, yval[:, None], None)
+        # the reference's loop keeps its arrays local; replay its selection rule through its own methods
+        pf = learner.train(kernel_fn, xtr, ytr[:, None])
+        sel = np.asarray(learner.active_test(pf, xpool, "nngp"))
+        x1, y1, xp1, yp1 = learner.merge_data(sel, xtr, ytr[:, None], xpool, ypool[:, None])
+        mirror = MirrorLearner(budget=15, active_iters=0, verbose=False)
+        pf_m = mirror.train(kernel_fn, xtr, ytr[:, None])
+        sel_m = np.asarray(mirror.active_test(pf_m, xpool))
+        assert sel.shape == (15,) and list(sel) == list(sel_m)
+        assert x1.shape == (65, 8) and xp1.shape == (65, 8) and y1.shape == (65, 1)
+        x1m, _, xp1m, _ = mirror.merge_data(sel_m, xtr, ytr[:, None], xpool, ypool[:, None])
+        assert np.array_equal(np.asarray(x1), x1m) and np.array_equal(np.asarray(xp1), xp1m)
+        assert fake_engine.fits >= 4               # 3 fits inside active_train + the replay
+    finally:
+        sys.path.remove(compat)
+        sys.modules.pop("util", None)
+        for m in [k for k in sys.modules if k == "jax" or k.startswith("jax.") or k == "neural_tangents"]:
+            del sys.modules[m]
