@@ -241,3 +241,54 @@ def test_unmodified_reference_active_learner_runs_on_the_shims(fake_engine):
         sys.modules.pop("util", None)
         for m in [k for k in sys.modules if k == "jax" or k.startswith("jax.") or k == "neural_tangents"]:
             del sys.modules[m]
+
+
+REFERENCE_TRAIN = "/root/reference/train.py"
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(REFERENCE_TRAIN),
+                    reason="the reference tree is only mounted in the build container")
+def test_unmodified_reference_train_py_nngp_path_runs_on_the_shims(fake_engine, capsys):
+    """Drop-in check for rows a1-a6 at their primary call site: the reference's OWN train.py, imported unmodified with
+    the shims on sys.path, runs NNGP_train_and_test (train.py:153-203: stax.serial -> nt.batch ->
+    gradient_descent_mse_ensemble -> predict_fn(get='nngp', compute_cov=True) -> sqrt(diag(cov))) and prints the
+    squared error the oracle gives.  Stubbed: `datasets`, `schemas` (DB loaders) and `util` (plotting / statistics)."""
+    import importlib.util
+    import re
+    import sys
+    import types
+    from pathlib import Path
+    from nngp_b200 import synth
+    compat = str(Path(__file__).resolve().parents[1] / "nngp-src_b200" / "compat")
+    util_stub = types.ModuleType("util")
+
+    class PredictionStatistics:
+        def get_prediction_details(self, *a, **k):
+            return None
+
+    util_stub.PredictionStatistics = PredictionStatistics
+    for name in ("draw_uncertainty", "calibration_plot", "draw_kernel_heatmap", "show_memory_usage",
+                 "uneven_train_test_split", "train_test_val_split"):
+        setattr(util_stub, name, lambda *a, **k: None)
+    stubs = {"util": util_stub, "datasets": types.ModuleType("datasets"), "schemas": types.ModuleType("schemas")}
+    sys.path.insert(0, compat)
+    sys.modules.update(stubs)
+    try:
+        spec = importlib.util.spec_from_file_location("reference_train", REFERENCE_TRAIN)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        xtr, ytr, xte, yte = synth.make_problem(70, 25, 10)
+        args = types.SimpleNamespace(kernel_type="nngp", cuda=False)
+        mod.NNGP_train_and_test(args, xtr, ytr[:, None], xte, yte[:, None], None, None)
+        out = capsys.readouterr().out
+        printed = float(re.search(r"Mean Square Error: ([-+0-9.eE]+)", out).group(1))
+        rm, _ = oracle.Fit(xtr, ytr).predict(xte)
+        assert abs(printed - float(np.sum((rm - yte) ** 2))) <= 1e-9 * max(1.0, abs(printed))
+        assert "Kernel construction in" in out and "Inference time=" in out
+        assert fake_engine.fits == 1               # lazy fit on the first predict_fn call, cached for the second
+    finally:
+        sys.path.remove(compat)
+        for k in stubs:
+            sys.modules.pop(k, None)
+        for m in [k for k in sys.modules if k == "jax" or k.startswith("jax.") or k == "neural_tangents"]:
+            del sys.modules[m]
