@@ -286,6 +286,11 @@ def test_unmodified_reference_train_py_nngp_path_runs_on_the_shims(fake_engine, 
         assert abs(printed - float(np.sum((rm - yte) ** 2))) <= 1e-9 * max(1.0, abs(printed))
         assert "Kernel construction in" in out and "Inference time=" in out
         assert fake_engine.fits == 1               # lazy fit on the first predict_fn call, cached for the second
+        # train.py:254 --kernel_type ntk goes through the same function
+        mod.NNGP_train_and_test(types.SimpleNamespace(kernel_type="ntk", cuda=False), xtr, ytr[:, None], xte, yte[:, None])
+        printed = float(re.search(r"Mean Square Error: ([-+0-9.eE]+)", capsys.readouterr().out).group(1))
+        rm_ntk, _ = oracle.FitNTK(xtr, ytr).predict(xte)
+        assert abs(printed - float(np.sum((rm_ntk - yte) ** 2))) <= 1e-9 * max(1.0, abs(printed))
     finally:
         sys.path.remove(compat)
         for k in stubs:
