@@ -297,3 +297,59 @@ def test_unmodified_reference_train_py_nngp_path_runs_on_the_shims(fake_engine, 
             sys.modules.pop(k, None)
         for m in [k for k in sys.modules if k == "jax" or k.startswith("jax.") or k == "neural_tangents"]:
             del sys.modules[m]
+
+
+REFERENCE_ACTIVE_TRAIN = "/root/reference/active/active_train.py"
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(REFERENCE_ACTIVE_TRAIN),
+                    reason="the reference tree is only mounted in the build container")
+def test_unmodified_reference_active_train_driver_runs_on_the_shims(fake_engine, capsys):
+    """The reference's OWN active/active_train.py main() (config C4's driver, active_train.py:21-51) with its default
+    biased_sample=True branch (jax.random.choice -> the shim's weighted draw): loaders stubbed, everything else as
+    shipped -- including `from active.ActiveLearner import ActiveLearner` resolved from the reference tree."""
+    import importlib.util
+    import sys
+    import types
+    from pathlib import Path
+    from nngp_b200 import synth
+    compat = str(Path(__file__).resolve().parents[1] / "nngp-src_b200" / "compat")
+    x = synth.encodings(200, 8, 1)
+    y = synth.labels(x)[:, None]
+    util_stub = types.ModuleType("util")
+
+    class PredictionStatistics:
+        def get_prediction_details(self, *a, **k):
+            return None
+
+    def train_test_val_split(X, Y, train_frac=0.2, test_frac=0.6, all_query_infos=None):       # util.py:271-293
+        n = X.shape[0]
+        a, b = int(n * train_frac), int(n * (train_frac + test_frac))
+        return X[:a], Y[:a], None, X[a:b], Y[a:b], None, X[b:], Y[b:], None
+
+    util_stub.PredictionStatistics = PredictionStatistics
+    util_stub.train_test_val_split = train_test_val_split
+    schemas_stub = types.ModuleType("schemas")
+    schemas_stub.load_training_schema_data = lambda args: (x, y, None)
+    stubs = {"util": util_stub, "datasets": types.ModuleType("datasets"), "schemas": schemas_stub}
+    sys.path[:0] = [compat, "/root/reference"]
+    sys.modules.update(stubs)
+    try:
+        spec = importlib.util.spec_from_file_location("reference_active_train", REFERENCE_ACTIVE_TRAIN)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        args = types.SimpleNamespace(kernel_type="nngp", biased_sample=True, active_iters=3, budget=25)
+        mod.main(args)
+        out = capsys.readouterr().out
+        assert "# Initial Training samples: 40" in out
+        grown = [l for l in out.splitlines() if l.startswith("# Training samples:")]
+        assert grown == ["# Training samples: 65", "# Training samples: 90", "# Training samples: 115"]
+        assert out.count("Test MSE Loss:") == 4 and fake_engine.fits == 4
+    finally:
+        for p in (compat, "/root/reference"):
+            sys.path.remove(p)
+        for k in stubs:
+            sys.modules.pop(k, None)
+        for m in [k for k in sys.modules if k == "jax" or k.startswith("jax.") or k == "neural_tangents"
+                  or k == "active" or k.startswith("active.")]:
+            del sys.modules[m]
