@@ -1,0 +1,32 @@
+"""How the explicit 64 x 64 diagonal-block inverses of the solve behave when K + lambda*I is badly conditioned:
+CUDA path vs the CPU oracle (LAPACK substitution) for decreasing relative diag_reg.  GPU box only.
+    python tests/checks/illcond_report.py"""
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+for p in (ROOT, ROOT / "nngp-src_b200", ROOT / "oracle"):
+    sys.path.insert(0, str(p))
+import nngp_oracle as oracle  # noqa: E402
+from nngp_b200 import _lib, synth  # noqa: E402
+
+xtr, ytr, xte, _ = synth.make_problem(3000, 1000, 32)
+out = []
+for reg in (1e-3, 1e-5, 1e-7, 1e-9):
+    try:
+        h = _lib.Handle(diag_reg=reg)
+        h.fit(xtr, ytr)
+        m, v = h.predict(xte)
+        ref = oracle.Fit(xtr, ytr, diag_reg=reg)
+        rm, rv = ref.predict(xte)
+        k = oracle.kernel_fn(xtr)
+        ev = np.linalg.eigvalsh(k + ref.lam * np.eye(3000))
+        out.append({"diag_reg": reg, "cond": float(ev[-1] / ev[0]), "mean_rel": float(np.max(np.abs(m - rm)) / np.max(np.abs(rm))),
+                    "var_rel_to_kss": float(np.max(np.abs(v - rv)) / np.max(oracle.final_diag(oracle.layer0_diag(xte)))),
+                    "var_rel": float(np.max(np.abs(v - rv) / np.abs(rv))), "min_var_over_kss": float(np.min(rv) / np.max(rv))})
+    except Exception as e:  # noqa: BLE001
+        out.append({"diag_reg": reg, "error": repr(e)[:200]})
+print(json.dumps(out))
