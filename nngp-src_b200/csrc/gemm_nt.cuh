@@ -234,11 +234,14 @@ struct NoGate {  // default refill gate: operand tiles are always ready to be lo
 };
 // `gate(kt)` is called by thread 0 right before it issues the TMA loads of k-tile kt (refills only; the caller
 // gates its own prologue): the persistent solve uses it to wait until the producer of that k-tile's A operand
-// (another CTA) has published it.
+// (another CTA) has published it.  `active == false` (warp-uniform): this warp's 32-row slab lies entirely beyond
+// the valid rows -- it keeps the barrier protocol going but skips its fragment loads and DMMAs, which leaves the
+// FP64 pipe to the warps that have rows (a single query occupies 1 of the 4 slabs of a row tile).
 template <int STAGES, class Gate = NoGate>
 __device__ __forceinline__ void mma_mainloop(double (&acc)[4][4][2], const TileSrc& src, uint8_t* ringA, uint8_t* ringB,
                                              uint64_t* full_bar, uint64_t* empty_bar, int& stage, uint32_t& phase,
-                                             int ktiles, int wm, int wn, int lane, uint32_t zero, Gate gate = Gate()) {
+                                             int ktiles, int wm, int wn, int lane, uint32_t zero, Gate gate = Gate(),
+                                             bool active = true) {
   const int g = lane >> 2, t = lane & 3;
   // Which k does lane (g, t) feed into DMMA step s?  Any bijection (s, t) -> 0..15 is a valid GEMM as long as the A
   // and the B fragment use the same one.  We use  k = 8*(t>>1) + 2*s + (t&1):  logical 16-byte chunk 4*(t>>1) + s,
@@ -273,19 +276,23 @@ __device__ __forceinline__ void mma_mainloop(double (&acc)[4][4][2], const TileS
 #pragma unroll
     for (int k4 = 0; k4 < 4; ++k4) {
       double a[4], b[4];
+      if (active) {
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi) a[mi] = lds_f64((a_st ^ (uint32_t)(k4 << 4)) + mi * 1024);
+        for (int mi = 0; mi < 4; ++mi) a[mi] = lds_f64((a_st ^ (uint32_t)(k4 << 4)) + mi * 1024);
 #pragma unroll
-      for (int ni = 0; ni < 4; ++ni) b[ni] = lds_f64((b_st ^ (uint32_t)(k4 << 4)) + ni * 1024);
+        for (int ni = 0; ni < 4; ++ni) b[ni] = lds_f64((b_st ^ (uint32_t)(k4 << 4)) + ni * 1024);
+      }
       if (k4 == NNGP_RELEASE_AT && kt > 0)
         release(stage == 0 ? STAGES - 1 : stage - 1, stage == 0 ? phase ^ 1u : phase, seen_prev, kt - 1);
+      if (active) {
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
+        for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) dmma_884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
-      // folded after the DMMAs that consume the same registers: the values have landed, the XORs never stall
+          for (int ni = 0; ni < 4; ++ni) dmma_884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        // folded after the DMMAs that consume the same registers: the values have landed, the XORs never stall
 #pragma unroll
-      for (int i = 0; i < 4; ++i) seen ^= (uint32_t)__double2hiint(a[i]) ^ (uint32_t)__double2hiint(b[i]);
+        for (int i = 0; i < 4; ++i) seen ^= (uint32_t)__double2hiint(a[i]) ^ (uint32_t)__double2hiint(b[i]);
+      }
     }
 #if NNGP_RELEASE_AT >= 4
     release(stage, phase, seen, kt);

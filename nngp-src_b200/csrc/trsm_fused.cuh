@@ -104,8 +104,6 @@ trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
     if (tid == 0) {
       const int it = p.static_sched ? next_static : atomicAdd(p.counter, 1);
       s_item[0] = it;
-      // PIPE: how far is this item's row tile already solved?  (decides between the ungated and the gated main loop)
-      if (PIPE) s_item[1] = (it < total && it >= p.row_tiles) ? ld_acquire_gpu(p.progress + it % p.row_tiles) : 0;
     }
     next_static += gridDim.x;
     __syncthreads();  // publishes the item; also: nobody still uses the ring / the scratch of the last item
@@ -113,7 +111,6 @@ trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
     if (item >= total) break;
     const int J = item / p.row_tiles;
     const int r = item - J * p.row_tiles;
-    const bool all_ready = !PIPE || s_item[1] >= J;   // CTA-uniform: every column block this item consumes is published
     const int ktiles = J * (NB / GEMM_BK);
     const int col0 = J * NB;
     const int nb = min(NB, p.N - col0);
@@ -127,7 +124,7 @@ trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
     // acquire per newly needed block), so an item starts consuming the blocks that exist instead of waiting for all
     // of them -- with few row tiles the items of one row tile form a software pipeline along J across the CTAs.
     // Claims are handed out in J-major order, so whatever this CTA waits for is owned by a running CTA.
-    int known = PIPE ? s_item[1] : 0;   // progress[r] as last seen by thread 0
+    int known = 0;   // progress[r] as last seen by thread 0
     auto gate = [&](int kt) {
       const int need = kt / (NB / GEMM_BK) + 1;
       if (known < need) {
@@ -139,11 +136,10 @@ trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
       }
     };
     if (tid == 0) {
-      if (all_ready) {   // nothing (more) to wait for: plain prologue
-        if (!PIPE) { if (J > 0) gate(ktiles - 1); }   // the up-front wait for item (r, J-1) (+ proxy fence)
-        else if (J > 0) fence_proxy_async_all();
+      if (!PIPE) {   // one up-front wait for item (r, J-1) (+ proxy fence), then a plain prologue
+        if (J > 0) gate(ktiles - 1);
         ring_prologue<TF_STAGES>(src, ringA, ringB, full_bar, stage, ktiles);
-      } else {
+      } else {       // gated prologue: issue what exists, block by block
         const int n0 = ktiles < TF_STAGES ? ktiles : TF_STAGES;
         int st = stage;
         for (int i = 0; i < n0; ++i) {
@@ -176,10 +172,13 @@ trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
       }
     }
 
-    if (all_ready)   // (PIPE: two instantiations of the loop in one kernel)
-      mma_mainloop<TF_STAGES>(acc, src, ringA, ringB, full_bar, empty_bar, stage, phase, ktiles, wm, wn, lane, p.zero);
+    // PIPE (few rows): a 32-row slab entirely beyond the valid rows does no arithmetic (results are never stored)
+    const bool slab_active = !PIPE || row0 + wm * 32 < p.rows;
+    if (PIPE)
+      mma_mainloop<TF_STAGES>(acc, src, ringA, ringB, full_bar, empty_bar, stage, phase, ktiles, wm, wn, lane, p.zero,
+                              gate, slab_active);
     else
-      mma_mainloop<TF_STAGES>(acc, src, ringA, ringB, full_bar, empty_bar, stage, phase, ktiles, wm, wn, lane, p.zero, gate);
+      mma_mainloop<TF_STAGES>(acc, src, ringA, ringB, full_bar, empty_bar, stage, phase, ktiles, wm, wn, lane, p.zero);
 
     // ---- diagonal step: V[r, J] = R * W_J^T on the tensor pipe -------------------------------------------
     __syncthreads();  // every warp has left the ring (each warp's last release waited for its fragment loads)
@@ -209,7 +208,8 @@ trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
       }
     }
     __syncthreads();  // R is visible to every warp (generic proxy on both sides)
-    mma_mainloop<TF_STAGES>(acc, src, ringA, ringB, full_bar, empty_bar, stage, phase, TF_STAGES, wm, wn, lane, p.zero);
+    mma_mainloop<TF_STAGES>(acc, src, ringA, ringB, full_bar, empty_bar, stage, phase, TF_STAGES, wm, wn, lane, p.zero,
+                            NoGate(), slab_active);
     __syncthreads();  // ring drained again: its first 2 KiB are the row-sum scratch of the epilogue
     {
       DiagOut o;
