@@ -21,15 +21,20 @@ def rel(a, b):
 def main():
     out = {}
     f = np.load(ROOT / "tests" / "golden" / "forest_xy.npz")
+    import time
     h = _lib.Handle()
     h.fit(f["x_train"], f["y_train"])
     mean, var = h.predict(f["x_test"])
-    ref = oracle.Fit(f["x_train"], f["y_train"])
-    rm, rv = ref.predict(f["x_test"])
+    t0 = time.perf_counter(); h.fit(f["x_train"], f["y_train"]); t_fit = time.perf_counter() - t0
+    t0 = time.perf_counter(); mean, var = h.predict(f["x_test"]); t_pred = time.perf_counter() - t0
+    t0 = time.perf_counter(); ref = oracle.Fit(f["x_train"], f["y_train"]); t_ofit = time.perf_counter() - t0
+    t0 = time.perf_counter(); rm, rv = ref.predict(f["x_test"]); t_opred = time.perf_counter() - t0
     out["forest_c1"] = {"n_train": int(f["x_train"].shape[0]), "n_test": int(f["x_test"].shape[0]),
                         "mean_rel": rel(mean, rm), "var_rel": rel(var, rv), "std_rel": rel(np.sqrt(var), np.sqrt(rv)),
                         "alpha_rel": rel(h.get_state(x=False, l=False)["alpha"], ref.alpha),
-                        "lambda": h.dims()[2], "lambda_oracle": float(ref.lam)}
+                        "lambda": h.dims()[2], "lambda_oracle": float(ref.lam),
+                        "gpu_fit_s": t_fit, "gpu_predict_s": t_pred, "oracle_fit_s": t_ofit, "oracle_predict_s": t_opred,
+                        "host_cores": len(__import__("os").sched_getaffinity(0))}
     xtr, ytr, xte, _ = synth.make_problem(8192, 2048, 128)
     h.fit(xtr, ytr)
     mean, var = h.predict(xte)
