@@ -15,8 +15,13 @@
  *     are written into the caller's buffer in the memory space it lives in;
  *   - every call returns 0 on success or a negative nngp_status; the message is
  *     available from nngp_last_error(); nothing aborts, throws or prints;
- *   - a handle is bound to ONE GPU and is not re-entrant; distinct handles are
- *     independent; every call is complete (stream-synchronised) when it returns;
+ *   - a handle is not re-entrant; distinct handles are independent; every call is
+ *     complete (stream-synchronised) when it returns.  A handle owns ONE GPU, or -- with
+ *     cfg.n_gpus > 1 -- a fit GPU plus replicas of the fitted state on the other GPUs: the
+ *     fit runs on device_ids[0], its state is copied once per fit over NVLink (packed lower
+ *     triangle, peer-to-peer, no host staging) and nngp_predict splits the test rows
+ *     [g*T/G, (g+1)*T/G) over the G GPUs, one host worker thread per extra GPU (the
+ *     reference's callers are single-process: estimator.py:42-62, train.py:178);
  *   - there is NO CPU fallback: without a usable sm_100 device nngp_create fails.
  */
 #ifndef NNGP_B200_H
@@ -28,7 +33,8 @@
 extern "C" {
 #endif
 
-#define NNGP_B200_ABI_VERSION 4
+#define NNGP_B200_ABI_VERSION 5
+#define NNGP_MAX_GPUS 8
 
 #if defined(__GNUC__)
 #define NNGP_API __attribute__((visibility("default")))
@@ -69,6 +75,12 @@ typedef struct nngp_config {
   int64_t max_block_bytes;    /* cap of the test-row block buffer; 0 = default 16 GiB */
   int32_t stats_level;        /* 0 none, 1 per-stage events, 2 per-kernel-class events*/
   int32_t kernel_type;        /* 0 = 'nngp' (reference default), 1 = 'ntk' (train.py:254)  */
+  int32_t n_gpus;             /* 0 / 1: one GPU (`device`); G > 1: prediction rows are split over G GPUs   */
+  int32_t device_ids[NNGP_MAX_GPUS]; /* CUDA ordinals when n_gpus > 1 ([0] = fit GPU); all -1: 0..G-1   */
+  int32_t latency_mode;       /* 1: the fit also builds the explicit inverse factor L^-1 (N^3/3 more flop) and small
+                                 prediction batches (the serving case, estimator.py:42-62: a few query lines per
+                                 call) run as a dependency-free triangular GEMM on it instead of the substitution
+                                 chain.  Same posterior to rounding (not bitwise the substitution's); default 0.     */
 } nngp_config;
 
 /* Per-stage device timings (CUDA events on the handle's stream) and work counters,
@@ -88,6 +100,9 @@ typedef struct nngp_stats_t {
   int64_t kernel_launches; /* every kernel this library launched                       */
   int64_t h2d_bytes, d2h_bytes;
   int64_t queries;         /* test rows predicted                                      */
+  double replicate_ms;     /* n_gpus > 1: wall time of the last peer-to-peer replication of the fitted state */
+  int64_t replicate_bytes; /* bytes each replica received in it                        */
+  double inverse_ms;       /* latency_mode: device time of building L^-1 in the last fit */
 } nngp_stats_t;
 
 typedef struct nngp_handle nngp_handle;
@@ -201,6 +216,24 @@ NNGP_API int nngp_diag_gemm_probe(nngp_handle* h, int64_t M, int64_t N, int64_t 
 NNGP_API int nngp_diag_potrf(nngp_handle* h, double* a, int64_t N);
 
 NNGP_API int nngp_abi_version(void);
+/* Hash of the sources this binary was compiled from (csrc, include, build.sh -- nngp_b200/_build.py); the Python
+ * loader and __graft_entry__.build() rebuild when it does not match the tree they run in. */
+NNGP_API const char* nngp_build_id(void);
+/* Number of GPUs the handle predicts on (1 unless cfg.n_gpus > 1). */
+NNGP_API int nngp_num_gpus(const nngp_handle* h);
+
+/* Packed fitted state, for shipping a fit to other processes (one process per GPU, nngp_b200/dist.py) or to a
+ * file without a staging copy of the whole N x N factor.  The state is ONE logical array of doubles:
+ *     [ X (N*D, row-major) | alpha (N) | lower triangle of L by rows (N(N+1)/2) | 'ntk' only: M (N*N) ].
+ * nngp_state_packed_size reports its length; nngp_state_pack copies elements [offset, offset+count) into `dst`
+ * (host or device memory); on the receiving side nngp_state_import_begin sizes the buffers,
+ * nngp_state_unpack stores a range, nngp_state_import_end derives the rest (layer-0 diagonal, diagonal-block
+ * inverses, replicas) and marks the handle fitted.  Every call is complete when it returns. */
+NNGP_API int nngp_state_packed_size(nngp_handle* h, int64_t* n_doubles);
+NNGP_API int nngp_state_pack(nngp_handle* h, int64_t offset, int64_t count, double* dst);
+NNGP_API int nngp_state_import_begin(nngp_handle* h, int64_t N, int64_t D);
+NNGP_API int nngp_state_unpack(nngp_handle* h, int64_t offset, int64_t count, const double* src);
+NNGP_API int nngp_state_import_end(nngp_handle* h, double lambda);
 
 /*
  * Batch query-line encoder (host C++, multi-threaded) -- scope row f-1.

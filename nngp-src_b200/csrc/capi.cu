@@ -13,7 +13,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <chrono>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -54,6 +56,10 @@ inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 struct nngp_handle {
   nngp_config cfg;
   int device = 0;
+  // cfg.n_gpus > 1: replicas of the fitted state on the other GPUs (each a complete single-GPU handle with its own
+  // streams and workspace; nngp_predict runs them on one host thread each).  `owner` is set on a replica.
+  std::vector<nngp_handle*> peers;
+  nngp_handle* owner = nullptr;
   int sm_count = 148;
   cudaStream_t stream = nullptr;        // main stream (all stage timing events live here)
   cudaStream_t panel_stream = nullptr;  // high-priority stream: Cholesky panel look-ahead
@@ -76,6 +82,7 @@ struct nngp_handle {
   DevBuf zkeep;   // z = L^-1 y of the last fit (the backward substitution destroys its copy in the factor buffer)
   DevBuf L2;      // second factor buffer: target of the incremental (fixed-lambda) append, then swapped with L
   bool have_y = false;
+  bool importing = false;   // between nngp_state_import_begin and _end
   DevBuf flags;   // int[2]: {potrf info, non-finite input}
   DevBuf lam_d;   // double[4]: {lambda, sum log diag L, z^T z, spare}
 
@@ -124,7 +131,12 @@ int fail(nngp_handle* h, int code, const char* fmt, ...) {
 int ensure(nngp_handle* h, DevBuf& b, size_t bytes) {
   if (bytes <= b.cap && b.p) return NNGP_OK;
   const bool regrow = b.p != nullptr;
-  if (b.p) { CK(cudaStreamSynchronize(h->stream)); CK(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+  if (b.p) {  // every stream of the handle may still touch the old buffer (uploads run ahead on copy_stream)
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->copy_stream) CK(cudaStreamSynchronize(h->copy_stream));
+    if (h->panel_stream) CK(cudaStreamSynchronize(h->panel_stream));
+    CK(cudaFree(b.p)); b.p = nullptr; b.cap = 0;
+  }
   if (bytes == 0) bytes = 256;
   // A buffer that grows again (the active-learning loop: N += budget every round) gets 25 % head-room, so that
   // multi-GB cudaFree / cudaMalloc pairs do not recur every round; exact size if that does not fit.
@@ -513,10 +525,20 @@ int run_trsv_bwd(nngp_handle* h, const double* L, int64_t ld, int64_t N, double*
       CKR(ensure(h, h->sync_ints, (size_t)(nblk + 1) * sizeof(int)));
       CK(cudaMemsetAsync(h->sync_ints.p, 0, (size_t)nblk * sizeof(int), h->stream));
       CK(cudaFuncSetAttribute(trsv_bwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      trsv_bwd_persistent_kernel<<<grid, TRSVP_THREADS, smem, h->stream>>>(L, ld, (int)N, (int)sw, z, out, h->sync_ints.as<int>());
-      h->st.kernel_launches++;
-      CK(cudaGetLastError());
-      return NNGP_OK;
+      // The kernel's CTAs wait on each other's flags, so they must all be resident: a cooperative launch makes the
+      // driver guarantee that (it waits for room when another handle or process holds SMs) instead of relying on
+      // the dispatch order; if the grid cannot be co-resident at all the stepwise kernels below take over.
+      int Ni = (int)N, swi = (int)sw;
+      const double* zc = z;
+      int* fl = h->sync_ints.as<int>();
+      void* args[] = {(void*)&L, (void*)&ld, (void*)&Ni, (void*)&swi, (void*)&zc, (void*)&out, (void*)&fl};
+      cudaError_t le = cudaLaunchCooperativeKernel((const void*)trsv_bwd_persistent_kernel, dim3((unsigned)grid),
+                                                   dim3(TRSVP_THREADS), args, smem, h->stream);
+      if (le == cudaSuccess) {
+        h->st.kernel_launches++;
+        return NNGP_OK;
+      }
+      cudaGetLastError();   // not co-schedulable here: fall through to one launch per block
     }
   }
   for (int64_t jb = nblk - 1; jb >= 0; --jb) {
@@ -535,16 +557,16 @@ int upload_matrix(nngp_handle* h, const double* src, int64_t rows, int64_t cols,
                   cudaStream_t stream = nullptr) {
   if (!stream) stream = h->stream;
   if (ld != cols) CK(cudaMemsetAsync(dst, 0, (size_t)rows * ld * sizeof(double), stream));
-  const bool dev = is_device_ptr(src);
+  const bool dev = is_device_ptr(src);   // (possibly memory of another GPU: the kind is resolved through UVA)
   CK(cudaMemcpy2DAsync(dst, ld * sizeof(double), src, cols * sizeof(double), cols * sizeof(double), rows,
-                       dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
+                       cudaMemcpyDefault, stream));
   if (!dev) h->st.h2d_bytes += rows * cols * (int64_t)sizeof(double);
   return NNGP_OK;
 }
 int download(nngp_handle* h, const double* dsrc, int64_t rows, int64_t cols, int64_t ld, double* dst) {
   const bool dev = is_device_ptr(dst);
   CK(cudaMemcpy2DAsync(dst, cols * sizeof(double), dsrc, ld * sizeof(double), cols * sizeof(double), rows,
-                       dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+                       cudaMemcpyDefault, h->stream));
   if (!dev) h->st.d2h_bytes += rows * cols * (int64_t)sizeof(double);
   return NNGP_OK;
 }
@@ -563,7 +585,7 @@ int bind_device(nngp_handle* h) {
   return NNGP_OK;
 }
 
-void drop_fit(nngp_handle* h) { h->fitted = false; h->have_lml = false; h->have_y = false; h->have_M = false; }
+void drop_fit(nngp_handle* h) { h->importing = false; h->fitted = false; h->have_lml = false; h->have_y = false; h->have_M = false; }
 
 int alloc_state(nngp_handle* h, int64_t N, int64_t D) {
   h->N = N; h->D = D;
@@ -583,6 +605,94 @@ int run_trtri_diag(nngp_handle* h) {
   trtri_diag_kernel<<<nblk, NB, 0, h->stream>>>(h->L.as<double>(), h->ldl, (int)h->N, h->Linv.as<double>());
   h->st.kernel_launches++;
   CK(cudaGetLastError());
+  return NNGP_OK;
+}
+
+
+// ---- replicas (cfg.n_gpus > 1) ------------------------------------------------------------------
+// After every successful fit / append / import the fitted state {X, q, alpha, inv(L_JJ), lower triangle of L
+// (+ M in 'ntk' mode)} is copied to the replicas, device to device over NVLink (peer access is enabled at
+// nngp_create), as a pipelined chain  d0 -> d1 -> ... -> d(G-1):  the factor travels in row panels
+// [r0, r1) x [0, r1) -- only the lower trapezoid, half the bytes of the square -- and hop g forwards panel c as soon
+// as it has arrived (event), so every link carries a different panel at the same time and the whole replication
+// costs about one transfer of the packed factor, independent of G (NVSwitch gives every hop full bandwidth).
+// Copies are pushed from the source GPU's copy stream.  No host staging, no extra device buffers.
+int replicate_state(nngp_handle* h) {
+  if (h->peers.empty() || !h->fitted) return NNGP_OK;
+  const int64_t N = h->N, D = h->D, ldx = h->ldx, ldl = h->ldl;
+  const bool ntk = h->cfg.kernel_type == 1;
+  const auto t_begin = std::chrono::steady_clock::now();
+  std::vector<nngp_handle*> chain;
+  chain.push_back(h);
+  for (auto* p : h->peers) chain.push_back(p);
+  const int G = (int)chain.size();
+  for (int g = 1; g < G; ++g) {
+    nngp_handle* p = chain[g];
+    CK(cudaSetDevice(p->device));
+    drop_fit(p);
+    int rc = alloc_state(p, N, D);
+    if (rc == NNGP_OK && ntk && h->have_M) rc = ensure(p, p->Mmat, (size_t)N * ldl * sizeof(double));
+    if (rc != NNGP_OK) { h->err = "replica on device " + std::to_string(p->device) + ": " + p->err; cudaSetDevice(h->device); return rc; }
+  }
+  const int64_t RP = 512;                       // rows per panel
+  const int npanel = (int)((N + RP - 1) / RP);
+  // items in chain order: 0 = small vectors (X, q, alpha, Linv), 1..npanel = factor panels, then M panels
+  const int nM = (ntk && h->have_M) ? npanel : 0;
+  const int nitems = 1 + npanel + nM;
+  std::vector<std::vector<cudaEvent_t>> ev((size_t)G);   // ev[g][i]: item i has arrived on chain[g]
+  cudaError_t ce = cudaSuccess;
+  auto copy_item = [&](nngp_handle* src, nngp_handle* dst, int item, cudaStream_t st) -> cudaError_t {
+    cudaError_t e = cudaSuccess;
+    if (item == 0) {
+      e = cudaMemcpyAsync(dst->X.p, src->X.p, (size_t)N * ldx * 8, cudaMemcpyDefault, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(dst->q.p, src->q.p, (size_t)N * 8, cudaMemcpyDefault, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(dst->alpha.p, src->alpha.p, (size_t)N * 8, cudaMemcpyDefault, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(dst->Linv.p, src->Linv.p, (size_t)round_up(N, NB) * NB * 8, cudaMemcpyDefault, st);
+      return e;
+    }
+    const bool isM = item > npanel;
+    const int64_t r0 = (int64_t)(isM ? item - npanel - 1 : item - 1) * RP;
+    const int64_t r1 = std::min<int64_t>(r0 + RP, N);
+    const double* sp = (isM ? src->Mmat.as<double>() : src->L.as<double>()) + r0 * ldl;
+    double* dp = (isM ? dst->Mmat.as<double>() : dst->L.as<double>()) + r0 * ldl;
+    const int64_t width = isM ? N : r1;        // the factor: columns [0, r1) of these rows; M: whole rows
+    return cudaMemcpy2DAsync(dp, ldl * 8, sp, ldl * 8, (size_t)width * 8, (size_t)(r1 - r0), cudaMemcpyDefault, st);
+  };
+  for (int g = 0; g + 1 < G && ce == cudaSuccess; ++g) {
+    nngp_handle* src = chain[g];
+    nngp_handle* dst = chain[g + 1];
+    ce = cudaSetDevice(src->device);
+    cudaStream_t st = src->copy_stream;
+    ev[(size_t)g + 1].resize((size_t)nitems);
+    for (int i = 0; i < nitems && ce == cudaSuccess; ++i) {
+      if (g > 0) ce = cudaStreamWaitEvent(st, ev[(size_t)g][(size_t)i], 0);   // item i has reached src
+      if (ce == cudaSuccess) ce = copy_item(src, dst, i, st);
+      cudaEvent_t e = nullptr;
+      if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+      if (ce == cudaSuccess) { ev[(size_t)g + 1][(size_t)i] = e; ce = cudaEventRecord(e, st); }
+    }
+  }
+  for (int g = 0; g + 1 < G; ++g) {
+    cudaSetDevice(chain[g]->device);
+    cudaError_t e2 = cudaStreamSynchronize(chain[g]->copy_stream);
+    if (ce == cudaSuccess) ce = e2;
+  }
+  for (auto& v : ev) for (auto e : v) if (e) cudaEventDestroy(e);
+  cudaSetDevice(h->device);
+  if (ce != cudaSuccess) return fail(h, NNGP_ECUDA, "replicating the fitted state to the other GPUs failed: %s", cudaGetErrorString(ce));
+  for (int g = 1; g < G; ++g) {
+    nngp_handle* p = chain[g];
+    p->lambda = h->lambda; p->fitted = true; p->have_M = ntk && h->have_M;
+    p->have_lml = false; p->have_y = false;
+  }
+  h->st.replicate_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+  int64_t bytes = (int64_t)N * ldx * 8 + 2 * N * 8 + round_up(N, NB) * NB * 8;
+  for (int c = 0; c < npanel; ++c) {
+    const int64_t r0 = (int64_t)c * RP, r1 = std::min<int64_t>(r0 + RP, N);
+    bytes += (r1 - r0) * r1 * 8;
+  }
+  if (nM) bytes += N * N * 8;
+  h->st.replicate_bytes = bytes;
   return NNGP_OK;
 }
 
@@ -609,7 +719,7 @@ void nngp_default_config(nngp_config* cfg) {
 
 const char* nngp_last_error(const nngp_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
-int nngp_create(const nngp_config* cfg, nngp_handle** out) {
+static int create_single(const nngp_config* cfg, nngp_handle** out) {
   nngp_handle* h = nullptr;
   if (!cfg || !out) return fail(h, NNGP_EINVAL, "nngp_create: null argument");
   *out = nullptr;
@@ -634,7 +744,7 @@ int nngp_create(const nngp_config* cfg, nngp_handle** out) {
                 prop.major, prop.minor);
   nngp_handle* nh = new nngp_handle();
   nh->cfg = *cfg;
-  if (nh->cfg.max_block_bytes <= 0) nh->cfg.max_block_bytes = (int64_t)16 << 30;
+  if (nh->cfg.max_block_bytes <= 0) nh->cfg.max_block_bytes = (int64_t)32 << 30;
   nh->device = dev;
   nh->sm_count = prop.multiProcessorCount;
   memset(&nh->st, 0, sizeof nh->st);
@@ -686,8 +796,76 @@ int nngp_create(const nngp_config* cfg, nngp_handle** out) {
   return NNGP_OK;
 }
 
+int nngp_create(const nngp_config* cfg, nngp_handle** out) {
+  nngp_handle* h = nullptr;
+  if (!cfg || !out) return fail(h, NNGP_EINVAL, "nngp_create: null argument");
+  *out = nullptr;
+  const int G = cfg->n_gpus <= 1 ? 1 : cfg->n_gpus;
+  if (G > NNGP_MAX_GPUS) return fail(h, NNGP_EINVAL, "nngp_create: n_gpus=%d exceeds NNGP_MAX_GPUS=%d", G, NNGP_MAX_GPUS);
+  nngp_config c0 = *cfg;
+  c0.n_gpus = 1;
+  if (G == 1) return create_single(&c0, out);
+  int ids[NNGP_MAX_GPUS];
+  bool any = false;
+  for (int g = 0; g < G; ++g) any = any || cfg->device_ids[g] >= 0;
+  for (int g = 0; g < G; ++g) ids[g] = any ? cfg->device_ids[g] : g;
+  for (int g = 0; g < G; ++g)
+    for (int k = 0; k < g; ++k)
+      if (ids[g] == ids[k] || ids[g] < 0)
+        return fail(h, NNGP_EINVAL, "nngp_create: device_ids must be %d distinct CUDA ordinals", G);
+  c0.device = ids[0];
+  CKR(create_single(&c0, &h));
+  for (int g = 1; g < G; ++g) {
+    nngp_config cg = c0;
+    cg.device = ids[g];
+    nngp_handle* p = nullptr;
+    const int rc = create_single(&cg, &p);
+    if (rc != NNGP_OK) { nngp_destroy(h); return rc; }   // g_create_error holds the message
+    p->owner = h;
+    h->peers.push_back(p);
+  }
+  h->cfg.n_gpus = G;
+  for (int g = 0; g < G; ++g) h->cfg.device_ids[g] = ids[g];
+  // peer access both ways between every pair: the replication chain pushes over NVLink, and a replica may read test
+  // rows from / write results to device memory of the first GPU
+  for (int a = 0; a < G; ++a) {
+    for (int b = 0; b < G; ++b) {
+      if (a == b) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, ids[a], ids[b]);
+      if (!can) {
+        fail(nullptr, NNGP_ENODEV, "nngp_create: GPU %d cannot access GPU %d peer-to-peer", ids[a], ids[b]);
+        nngp_destroy(h);
+        return NNGP_ENODEV;
+      }
+      cudaSetDevice(ids[a]);
+      cudaError_t e = cudaDeviceEnablePeerAccess(ids[b], 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+        fail(nullptr, NNGP_ECUDA, "cudaDeviceEnablePeerAccess(%d -> %d) failed: %s", ids[a], ids[b], cudaGetErrorString(e));
+        nngp_destroy(h);
+        return NNGP_ECUDA;
+      }
+      cudaGetLastError();
+    }
+  }
+  cudaSetDevice(ids[0]);
+  *out = h;
+  return NNGP_OK;
+}
+
+int nngp_num_gpus(const nngp_handle* h) { return h ? 1 + (int)h->peers.size() : 0; }
+
+#ifndef NNGP_BUILD_ID
+#define NNGP_BUILD_ID "unknown"
+#endif
+// "nngp-build-id:<16 hex>" is also what the Python loader scans the file for before loading it
+static const char g_build_marker[] = "nngp-build-id:" NNGP_BUILD_ID;
+const char* nngp_build_id(void) { return g_build_marker + 14; }
+
 void nngp_destroy(nngp_handle* h) {
   if (!h) return;
+  for (auto* p : h->peers) nngp_destroy(p);
+  h->peers.clear();
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->X, &h->q, &h->L, &h->alpha, &h->flags, &h->lam_d, &h->xt, &h->qt, &h->kss,
@@ -706,12 +884,20 @@ void* nngp_get_stream(nngp_handle* h) { return h ? (void*)h->stream : nullptr; }
 
 int nngp_stats(nngp_handle* h, nngp_stats_t* out) {
   if (!h || !out) return NNGP_EINVAL;
-  *out = h->st;
+  *out = h->st;   // stage / kernel-class times: the first GPU's; counters: summed over the handle's GPUs
+  for (auto* p : h->peers) {
+    out->kernel_launches += p->st.kernel_launches;
+    out->h2d_bytes += p->st.h2d_bytes;
+    out->d2h_bytes += p->st.d2h_bytes;
+    out->gemm_launches += p->st.gemm_launches;
+    out->gram_launches += p->st.gram_launches;
+  }
   return NNGP_OK;
 }
 int nngp_stats_reset(nngp_handle* h) {
   if (!h) return NNGP_EINVAL;
   memset(&h->st, 0, sizeof h->st);
+  for (auto* p : h->peers) memset(&p->st, 0, sizeof p->st);
   return NNGP_OK;
 }
 
@@ -757,8 +943,15 @@ int nngp_kernel(nngp_handle* h, const double* x1, int64_t M, const double* x2, i
 }
 
 // -------------------------------------------------------------------------------------------------
+static int fit_impl(nngp_handle* h, const double* x_train, const double* y_train, int64_t N, int64_t D);
 int nngp_fit(nngp_handle* h, const double* x_train, const double* y_train, int64_t N, int64_t D) {
   if (!h) return NNGP_EINVAL;
+  for (auto* p : h->peers) drop_fit(p);
+  CKR(fit_impl(h, x_train, y_train, N, D));
+  return replicate_state(h);
+}
+
+static int fit_impl(nngp_handle* h, const double* x_train, const double* y_train, int64_t N, int64_t D) {
   if (!x_train || !y_train || N <= 0 || D <= 0)
     return fail(h, NNGP_EINVAL, "nngp_fit: bad argument (N=%lld D=%lld)", (long long)N, (long long)D);
   if (N > 65535LL * GEMM_BM || D > 0x7fffffffLL) return fail(h, NNGP_EINVAL, "nngp_fit: N=%lld too large", (long long)N);
@@ -928,11 +1121,10 @@ int nngp_reserve(nngp_handle* h, int64_t n_train_max, int64_t dim, int64_t n_tes
   if (h->cfg.diag_reg_absolute && h->cfg.kernel_type == 0)   // the incremental append ping-pongs between two factors
     CKR(ensure(h, h->L2, (size_t)(N + 1) * ldl * 8));
   if (T > 0) {   // the row-block workspace of nngp_predict / nngp_active_select at (N, T)
-    const int64_t wave_rows = 2LL * h->sm_count * GEMM_BM;
     int64_t cap_rows = h->cfg.max_block_bytes / (ldl * 8);
-    if (cap_rows >= wave_rows) cap_rows = cap_rows / wave_rows * wave_rows;
     cap_rows = std::min<int64_t>(std::max<int64_t>(cap_rows, GEMM_BM), 65535LL * GEMM_BM);
-    const int64_t TB = std::min<int64_t>(round_up(T, 2), cap_rows);
+    const int64_t nblocks = (T + cap_rows - 1) / cap_rows;   // as nngp_predict sizes its row blocks
+    const int64_t TB = std::min<int64_t>(round_up(T, 2), round_up((T + nblocks - 1) / nblocks, GEMM_BM));
     const int64_t col_tiles = (N + GEMM_BN - 1) / GEMM_BN;
     CKR(ensure(h, h->xt, (size_t)TB * ldx * 8));
     CKR(ensure(h, h->qt, (size_t)TB * 8));
@@ -1056,15 +1248,49 @@ int nngp_append_fit(nngp_handle* h, const double* x_new, const double* y_new, in
       if (r != NNGP_OK) drop_fit(h);   // a half-extended model is not a model
       return r;
     }
-    return nngp_fit(h, xc.as<double>(), yc.as<double>(), N + M, D);
+    return fit_impl(h, xc.as<double>(), yc.as<double>(), N + M, D);
   };
+  for (auto* p : h->peers) drop_fit(p);
   if (rc == NNGP_OK) rc = body();
+  if (rc == NNGP_OK) rc = replicate_state(h);
   return rc;
 }
 
 // -------------------------------------------------------------------------------------------------
+static int predict_impl(nngp_handle* h, const double* x_test, int64_t T, double* mean_out, double* var_out);
+
+// cfg.n_gpus > 1: rows [g*T/G, (g+1)*T/G) go to GPU g; the replicas run on one host thread each while the
+// calling thread drives the first GPU.  Rows are independent and every reduction has a fixed order, so the result
+// is bitwise the single-GPU result.  Small batches (fewer than one 128-row tile per GPU) stay on the first GPU.
 int nngp_predict(nngp_handle* h, const double* x_test, int64_t T, double* mean_out, double* var_out) {
   if (!h) return NNGP_EINVAL;
+  const int G = 1 + (int)h->peers.size();
+  if (G == 1 || T < (int64_t)G * GEMM_BM) return predict_impl(h, x_test, T, mean_out, var_out);
+  if (!h->fitted) return fail(h, NNGP_ESTATE, "nngp_predict: no fitted model (call nngp_fit or nngp_set_state)");
+  if (!x_test || !mean_out || T <= 0) return fail(h, NNGP_EINVAL, "nngp_predict: bad argument (T=%lld)", (long long)T);
+  const int64_t D = h->D;
+  std::vector<int> rcs((size_t)G, NNGP_OK);
+  std::vector<std::thread> workers;
+  auto shard = [&](int g) {
+    nngp_handle* hg = g == 0 ? h : h->peers[(size_t)g - 1];
+    const int64_t lo = (int64_t)g * T / G, hi = (int64_t)(g + 1) * T / G;
+    rcs[(size_t)g] = predict_impl(hg, x_test + lo * D, hi - lo, mean_out + lo, var_out ? var_out + lo : nullptr);
+  };
+  for (int g = 1; g < G; ++g) workers.emplace_back(shard, g);
+  shard(0);
+  for (auto& w : workers) w.join();
+  cudaSetDevice(h->device);
+  for (int g = 1; g < G; ++g)
+    if (rcs[(size_t)g] != NNGP_OK) {
+      h->err = "GPU " + std::to_string(h->peers[(size_t)g - 1]->device) + ": " + h->peers[(size_t)g - 1]->err;
+      return rcs[(size_t)g];
+    }
+  if (rcs[0] != NNGP_OK) return rcs[0];
+  for (auto* p : h->peers) { h->st.queries += p->st.queries; p->st.queries = 0; }
+  return NNGP_OK;
+}
+
+static int predict_impl(nngp_handle* h, const double* x_test, int64_t T, double* mean_out, double* var_out) {
   if (!h->fitted) return fail(h, NNGP_ESTATE, "nngp_predict: no fitted model (call nngp_fit or nngp_set_state)");
   if (!x_test || !mean_out || T <= 0) return fail(h, NNGP_EINVAL, "nngp_predict: bad argument (T=%lld)", (long long)T);
   if (h->cfg.kernel_type == 1 && var_out && !h->have_M)
@@ -1073,14 +1299,15 @@ int nngp_predict(nngp_handle* h, const double* x_test, int64_t T, double* mean_o
   const int64_t N = h->N, D = h->D, ldx = h->ldx, ldl = h->ldl;
   const double sw2 = h->cfg.sigma_w * h->cfg.sigma_w, sb2 = h->cfg.sigma_b * h->cfg.sigma_b;
 
-  // Row-block size: a whole number of full DMMA waves (2 CTAs/SM x 128 rows) that fits the buffer cap.
-  const int64_t wave_rows = 2LL * h->sm_count * GEMM_BM;
+  // Row-block size: what fits the buffer cap, in equal blocks of whole 128-row tiles.
   const bool ntk = h->cfg.kernel_type == 1;
   int64_t cap_rows = h->cfg.max_block_bytes / (ldl * 8) / (ntk && var_out ? 2 : 1);  // NTK variance needs two row blocks
-  if (cap_rows >= wave_rows) cap_rows = cap_rows / wave_rows * wave_rows;
   cap_rows = std::max<int64_t>(cap_rows, GEMM_BM);
   cap_rows = std::min<int64_t>(cap_rows, 65535LL * GEMM_BM);
-  const int64_t TB = std::min<int64_t>(round_up(T, 2), cap_rows);
+  // equal blocks (whole 128-row tiles) instead of full blocks plus a short tail: the persistent solve keeps every SM
+  // busy with any tile count, what hurts is a last block with too few row tiles to fill the GPU
+  const int64_t nblocks = (T + cap_rows - 1) / cap_rows;
+  const int64_t TB = std::min<int64_t>(round_up(T, 2), round_up((T + nblocks - 1) / nblocks, GEMM_BM));
 
   CKR(ensure(h, h->xt, (size_t)TB * ldx * 8));
   CKR(ensure(h, h->qt, (size_t)TB * 8));
@@ -1239,7 +1466,7 @@ int nngp_set_state(nngp_handle* h, const double* x, const double* l, const doubl
   CK(cudaGetLastError());
   h->lambda = lambda;
   h->fitted = true;
-  return NNGP_OK;
+  return replicate_state(h);
 }
 
 // NTK mode: the fitted state also holds M = L^-1 K_dd L^-T (N x N, symmetric, dense), needed by the posterior variance.
@@ -1262,7 +1489,92 @@ int nngp_set_state_ntk_m(nngp_handle* h, const double* m) {
   CKR(upload_matrix(h, m, h->N, h->N, h->Mmat.as<double>(), h->ldl));
   CK(cudaStreamSynchronize(h->stream));
   h->have_M = true;
+  return replicate_state(h);
+}
+
+// -------------------------------------------------------------------------------------------------
+// Packed state (see the header): [ X (N*D) | alpha (N) | tril(L) by rows (N(N+1)/2) | ntk: M (N*N) ]
+static int64_t packed_size(const nngp_handle* h) {
+  const int64_t N = h->N, D = h->D;
+  return N * D + N + N * (N + 1) / 2 + ((h->cfg.kernel_type == 1) ? N * N : 0);
+}
+static StatePackView pack_view(nngp_handle* h) {
+  StatePackView v;
+  v.X = h->X.as<double>(); v.alpha = h->alpha.as<double>(); v.L = h->L.as<double>(); v.M = h->Mmat.as<double>();
+  v.N = h->N; v.D = h->D; v.ldx = h->ldx; v.ldl = h->ldl;
+  return v;
+}
+static int pack_range(nngp_handle* h, int64_t offset, int64_t count, double* ext, bool unpack, const char* who) {
+  if (!ext || offset < 0 || count <= 0 || offset + count > packed_size(h))
+    return fail(h, NNGP_EINVAL, "%s: range [%lld, +%lld) outside the packed state (%lld doubles)", who,
+                (long long)offset, (long long)count, (long long)packed_size(h));
+  CKR(bind_device(h));
+  double* dptr = ext;
+  const bool dev = is_device_ptr(ext);
+  if (!dev) {   // host memory on the other side: stage the range through a device buffer
+    CKR(ensure(h, h->kout, (size_t)count * 8));
+    dptr = h->kout.as<double>();
+    if (unpack) { CK(cudaMemcpyAsync(dptr, ext, (size_t)count * 8, cudaMemcpyHostToDevice, h->stream)); h->st.h2d_bytes += count * 8; }
+  }
+  const int grid = (int)std::min<int64_t>((count + 255) / 256, 16LL * h->sm_count);
+  if (unpack) state_pack_kernel<true><<<grid, 256, 0, h->stream>>>(pack_view(h), offset, count, dptr);
+  else state_pack_kernel<false><<<grid, 256, 0, h->stream>>>(pack_view(h), offset, count, dptr);
+  h->st.kernel_launches++;
+  if (!dev && !unpack) { CK(cudaMemcpyAsync(ext, dptr, (size_t)count * 8, cudaMemcpyDeviceToHost, h->stream)); h->st.d2h_bytes += count * 8; }
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
   return NNGP_OK;
+}
+
+int nngp_state_packed_size(nngp_handle* h, int64_t* n_doubles) {
+  if (!h || !n_doubles) return NNGP_EINVAL;
+  if (!h->fitted && !h->importing) return fail(h, NNGP_ESTATE, "nngp_state_packed_size: no fitted model and no import in progress");
+  *n_doubles = packed_size(h);
+  return NNGP_OK;
+}
+
+int nngp_state_pack(nngp_handle* h, int64_t offset, int64_t count, double* dst) {
+  if (!h) return NNGP_EINVAL;
+  if (!h->fitted) return fail(h, NNGP_ESTATE, "nngp_state_pack: no fitted model");
+  if (h->cfg.kernel_type == 1 && !h->have_M) return fail(h, NNGP_ESTATE, "nngp_state_pack: this 'ntk' state holds no M");
+  return pack_range(h, offset, count, dst, false, "nngp_state_pack");
+}
+
+int nngp_state_import_begin(nngp_handle* h, int64_t N, int64_t D) {
+  if (!h) return NNGP_EINVAL;
+  if (N <= 0 || D <= 0 || N > 65535LL * GEMM_BM) return fail(h, NNGP_EINVAL, "nngp_state_import_begin: bad shape (N=%lld D=%lld)", (long long)N, (long long)D);
+  CKR(bind_device(h));
+  drop_fit(h);
+  for (auto* p : h->peers) drop_fit(p);
+  CKR(alloc_state(h, N, D));
+  if (h->ldx != D) CK(cudaMemsetAsync(h->X.p, 0, (size_t)N * h->ldx * 8, h->stream));   // the pad column stays zero
+  if (h->cfg.kernel_type == 1) CKR(ensure(h, h->Mmat, (size_t)N * h->ldl * 8));
+  CK(cudaStreamSynchronize(h->stream));
+  h->importing = true;
+  return NNGP_OK;
+}
+
+int nngp_state_unpack(nngp_handle* h, int64_t offset, int64_t count, const double* src) {
+  if (!h) return NNGP_EINVAL;
+  if (!h->importing) return fail(h, NNGP_ESTATE, "nngp_state_unpack: call nngp_state_import_begin first");
+  return pack_range(h, offset, count, const_cast<double*>(src), true, "nngp_state_unpack");
+}
+
+int nngp_state_import_end(nngp_handle* h, double lambda) {
+  if (!h) return NNGP_EINVAL;
+  if (!h->importing) return fail(h, NNGP_ESTATE, "nngp_state_import_end: no import in progress");
+  CKR(bind_device(h));
+  h->importing = false;
+  const double sw2 = h->cfg.sigma_w * h->cfg.sigma_w, sb2 = h->cfg.sigma_b * h->cfg.sigma_b;
+  row_sqnorm_kernel<<<(unsigned)((h->N * 32 + 255) / 256), 256, 0, h->stream>>>(h->X.as<double>(), h->ldx, (int)h->N, (int)h->D, sw2, sb2, h->q.as<double>());
+  h->st.kernel_launches++;
+  CKR(run_trtri_diag(h));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  h->lambda = lambda;
+  h->fitted = true;
+  h->have_M = h->cfg.kernel_type == 1;
+  return replicate_state(h);
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -535,6 +535,39 @@ __global__ void zero_upper_kernel(double* __restrict__ A, long long ld, int N) {
   for (long long i = blockIdx.y; i < N && i < j; i += gridDim.y) A[i * ld + j] = 0.0;
 }
 
+// Packed fitted state <-> the handle's padded device buffers (include/nngp_b200.h, nngp_state_pack / _unpack):
+//   [ X (N*D, row-major) | alpha (N) | lower triangle of L by rows (N(N+1)/2) | 'ntk' only: M (N*N) ]
+// element g = offset + i of the packed array <-> its home; UNPACK = true stores ext[i] there, false loads it.
+struct StatePackView {
+  double* X; double* alpha; double* L; double* M;
+  long long N, D, ldx, ldl;
+};
+template <bool UNPACK>
+__global__ void state_pack_kernel(StatePackView v, long long offset, long long count, double* __restrict__ ext) {
+  const long long nx = v.N * v.D, ntri = v.N * (v.N + 1) / 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    long long g = offset + i;
+    double* home;
+    if (g < nx) {
+      const long long r = g / v.D;
+      home = v.X + r * v.ldx + (g - r * v.D);
+    } else if (g < nx + v.N) {
+      home = v.alpha + (g - nx);
+    } else if (g < nx + v.N + ntri) {
+      const long long t = g - nx - v.N;                       // t = r (r + 1) / 2 + c, 0 <= c <= r
+      long long r = (long long)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+      while (r * (r + 1) / 2 > t) --r;                        // the sqrt may be off by one either way
+      while ((r + 1) * (r + 2) / 2 <= t) ++r;
+      home = v.L + r * v.ldl + (t - r * (r + 1) / 2);
+    } else {
+      const long long t = g - nx - v.N - ntri;
+      const long long r = t / v.N;
+      home = v.M + r * v.ldl + (t - r * v.N);
+    }
+    if (UNPACK) *home = ext[i]; else ext[i] = *home;
+  }
+}
+
 // finite check: *flag |= any non-finite in x (rows x cols, ld)
 __global__ void finite_check_kernel(const double* __restrict__ x, long long ld, long long rows, int cols,
                                     int* __restrict__ flag) {

@@ -12,6 +12,8 @@ from pathlib import Path
 
 import numpy as np
 
+from . import _build
+
 _PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("NNGP_B200_LIB", _PKG_DIR.parent / "libnngp_b200.so"))
 
@@ -29,6 +31,9 @@ class NngpConfig(C.Structure):
         ("max_block_bytes", C.c_int64),
         ("stats_level", C.c_int32),
         ("kernel_type", C.c_int32),
+        ("n_gpus", C.c_int32),
+        ("device_ids", C.c_int32 * 8),
+        ("latency_mode", C.c_int32),
     ]
 
 
@@ -41,6 +46,7 @@ class NngpStats(C.Structure):
         + [("gemm_launches", C.c_int64)]
         + [(n, C.c_double) for n in ("gram_ms", "gram_flops", "gram_evals")]
         + [(n, C.c_int64) for n in ("gram_launches", "kernel_launches", "h2d_bytes", "d2h_bytes", "queries")]
+        + [("replicate_ms", C.c_double), ("replicate_bytes", C.c_int64), ("inverse_ms", C.c_double)]
     )
 
     def as_dict(self) -> dict:
@@ -53,6 +59,13 @@ _I64 = C.c_int64
 _DP = C.POINTER(C.c_double)
 EXPORTS = {
     "nngp_abi_version": (C.c_int, []),
+    "nngp_build_id": (C.c_char_p, []),
+    "nngp_num_gpus": (C.c_int, [_P]),
+    "nngp_state_packed_size": (C.c_int, [_P, C.POINTER(_I64)]),
+    "nngp_state_pack": (C.c_int, [_P, _I64, _I64, _P]),
+    "nngp_state_import_begin": (C.c_int, [_P, _I64, _I64]),
+    "nngp_state_unpack": (C.c_int, [_P, _I64, _I64, _P]),
+    "nngp_state_import_end": (C.c_int, [_P, C.c_double]),
     "nngp_default_config": (None, [C.POINTER(NngpConfig)]),
     "nngp_create": (C.c_int, [C.POINTER(NngpConfig), C.POINTER(_P)]),
     "nngp_destroy": (None, [_P]),
@@ -96,10 +109,13 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    custom = "NNGP_B200_LIB" in os.environ          # an explicitly chosen build is taken as it is
+    if not custom and (not LIB_PATH.exists() or built_id(LIB_PATH) != _build.source_hash()):
+        # missing, or compiled from other sources than the tree we run in (the .so is not tracked by git: it travels
+        # to the GPU box as a built file) -> rebuild in-tree; without nvcc this raises, there is no CPU fallback
+        _build.build()
     if not LIB_PATH.exists():
-        raise ImportError(
-            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-            "(nngp_b200 has no CPU fallback)")
+        raise ImportError(f"{LIB_PATH} not found (nngp_b200 has no CPU fallback)")
     lib = C.CDLL(str(LIB_PATH))
     for name, (res, args) in EXPORTS.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
@@ -107,6 +123,21 @@ def load() -> C.CDLL:
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def built_id(path=None) -> str | None:
+    """nngp_build_id() of a library file, read without loading it into this process (it is scanned for the
+    marker the build embeds), or None."""
+    try:
+        data = Path(path or LIB_PATH).read_bytes()
+    except OSError:
+        return None
+    i = data.find(b"nngp-build-id:")
+    return data[i + 14:i + 30].decode("ascii", "replace") if i >= 0 else None
+
+
+def build_id() -> str:
+    return load().nngp_build_id().decode()
 
 
 def _raise(lib, handle, code: int):
@@ -120,7 +151,8 @@ def _raise(lib, handle, code: int):
 
 
 def _ptr(a):
-    """(pointer, keepalive) for a numpy array (host) or a torch CUDA/CPU tensor (device/host)."""
+    """(pointer, keepalive) for an INPUT: a numpy array (host) or a torch CUDA/CPU tensor (device/host).
+    Inputs of another dtype / layout are converted into a temporary (kept alive by the caller)."""
     if a is None:
         return None, None
     if isinstance(a, np.ndarray):
@@ -131,16 +163,51 @@ def _ptr(a):
         import torch
         if a.dtype != torch.float64 or not a.is_contiguous():
             a = a.to(torch.float64).contiguous()
+        if a.is_cuda:
+            # the library reads on its own non-blocking stream, which is not ordered with torch's streams: whatever
+            # produced (or converted) this tensor on torch's current stream must have finished before the C call
+            torch.cuda.current_stream(a.device).synchronize()
         return C.c_void_p(a.data_ptr()), a
     a = np.ascontiguousarray(a, dtype=np.float64)
     return C.c_void_p(a.ctypes.data), a
+
+
+def _out_ptr(a, shape, name):
+    """Pointer of an OUTPUT buffer.  The library writes float64 values straight into it, so it must already be
+    float64, C-contiguous, writeable and of the right size -- anything else raises (a silent temporary would leave
+    the caller's buffer unfilled)."""
+    n = int(np.prod(shape))
+    if isinstance(a, np.ndarray):
+        if a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"] or not a.flags["WRITEABLE"]:
+            raise ValueError(f"nngp_b200: output buffer {name} must be a writeable C-contiguous float64 array "
+                             f"(got dtype {a.dtype}, contiguous={a.flags['C_CONTIGUOUS']})")
+        if a.size != n:
+            raise ValueError(f"nngp_b200: output buffer {name} has {a.size} elements, {n} are needed {tuple(shape)}")
+        return C.c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):
+        import torch
+        if a.dtype != torch.float64 or not a.is_contiguous():
+            raise ValueError(f"nngp_b200: output buffer {name} must be a contiguous float64 tensor (got {a.dtype})")
+        if a.numel() != n:
+            raise ValueError(f"nngp_b200: output buffer {name} has {a.numel()} elements, {n} are needed {tuple(shape)}")
+        if a.is_cuda:
+            torch.cuda.current_stream(a.device).synchronize()   # earlier users of the buffer on torch's stream
+        return C.c_void_p(a.data_ptr())
+    raise ValueError(f"nngp_b200: output buffer {name} must be a numpy array or a torch tensor, got {type(a).__name__}")
+
+
+def _npz_path(path):
+    """np.savez appends '.npz' to a name without it; save() and load() agree on the final name."""
+    p = os.fspath(path)
+    return p if p.endswith(".npz") else p + ".npz"
 
 
 class Handle:
     """RAII wrapper of ``nngp_handle*`` (one GPU, not re-entrant)."""
 
     def __init__(self, depth=2, sigma_w=1.0, sigma_b=0.0, diag_reg=1e-3, diag_reg_absolute=False,
-                 device=-1, max_block_bytes=0, stats_level=1, kernel_type="nngp"):
+                 device=-1, max_block_bytes=0, stats_level=1, kernel_type="nngp", n_gpus=1, device_ids=None,
+                 latency_mode=False):
         self._lib = load()
         cfg = NngpConfig()
         self._lib.nngp_default_config(C.byref(cfg))
@@ -150,6 +217,14 @@ class Handle:
         if kernel_type not in ("nngp", "ntk"):
             raise NotImplementedError(f"kernel_type {kernel_type!r}: only 'nngp' and 'ntk' exist")
         cfg.kernel_type = 1 if kernel_type == "ntk" else 0
+        ids = list(device_ids) if device_ids is not None else []
+        n_gpus = len(ids) if ids else int(n_gpus)
+        if n_gpus > 8 or n_gpus < 0:
+            raise ValueError(f"nngp_b200: n_gpus={n_gpus}: 1..8 GPUs per handle")
+        cfg.n_gpus = n_gpus
+        for i in range(8):
+            cfg.device_ids[i] = int(ids[i]) if i < len(ids) else -1
+        cfg.latency_mode = int(bool(latency_mode))
         self.cfg = cfg
         h = C.c_void_p()
         rc = self._lib.nngp_create(C.byref(cfg), C.byref(h))
@@ -181,7 +256,7 @@ class Handle:
             raise ValueError(f"nngp_b200: x1 has {D} features but x2 has {k2.shape[1]}")
         if out is None:
             out = np.empty((M, N2), dtype=np.float64)
-        op, _ko = _ptr(out)
+        op = _out_ptr(out, (M, N2), "out")
         self._ck(self._lib.nngp_kernel(self._h, x1p, M, x2p, N2, D, op))
         return out
 
@@ -206,8 +281,8 @@ class Handle:
             mean_out = np.empty(T, dtype=np.float64)
         if want_var and var_out is None:
             var_out = np.empty(T, dtype=np.float64)
-        mp, _km = _ptr(mean_out)
-        vp, _kv = _ptr(var_out) if want_var else (None, None)
+        mp = _out_ptr(mean_out, (T,), "mean_out")
+        vp = _out_ptr(var_out, (T,), "var_out") if want_var else None
         self._ck(self._lib.nngp_predict(self._h, xp, T, mp, vp))
         return mean_out, (var_out if want_var else None)
 
@@ -215,6 +290,31 @@ class Handle:
         n, d, lam = _I64(), _I64(), C.c_double()
         self._ck(self._lib.nngp_get_dims(self._h, C.byref(n), C.byref(d), C.byref(lam)))
         return n.value, d.value, lam.value
+
+    @property
+    def n_gpus(self) -> int:
+        return int(self._lib.nngp_num_gpus(self._h))
+
+    # ---- packed state streaming (see include/nngp_b200.h; used by nngp_b200.dist.broadcast_fit) ----
+    def packed_size(self) -> int:
+        n = _I64()
+        self._ck(self._lib.nngp_state_packed_size(self._h, C.byref(n)))
+        return n.value
+
+    def state_pack(self, offset: int, count: int, dst) -> None:
+        self._ck(self._lib.nngp_state_pack(self._h, int(offset), int(count), _out_ptr(dst, (count,), "dst")))
+
+    def state_import_begin(self, n: int, d: int) -> None:
+        self._ck(self._lib.nngp_state_import_begin(self._h, int(n), int(d)))
+
+    def state_unpack(self, offset: int, count: int, src) -> None:
+        sp, keep = _ptr(src)
+        if int(np.prod(keep.shape)) != int(count):
+            raise ValueError(f"nngp_b200: src has {int(np.prod(keep.shape))} elements, count is {count}")
+        self._ck(self._lib.nngp_state_unpack(self._h, int(offset), int(count), sp))
+
+    def state_import_end(self, lam: float) -> None:
+        self._ck(self._lib.nngp_state_import_end(self._h, float(lam)))
 
     @property
     def is_ntk(self) -> bool:
@@ -230,7 +330,7 @@ class Handle:
         if m:
             if "m" not in out:
                 out["m"] = np.empty((n, n))
-            mp, _m = _ptr(out["m"])
+            mp = _out_ptr(out["m"], (n, n), "m")
             self._ck(self._lib.nngp_get_state_ntk_m(self._h, mp))
         if x and "x" not in out:
             out["x"] = np.empty((n, d))
@@ -238,9 +338,9 @@ class Handle:
             out["l"] = np.empty((n, n))
         if alpha and "alpha" not in out:
             out["alpha"] = np.empty(n)
-        xp, _a = _ptr(out.get("x") if x else None)
-        lp, _b = _ptr(out.get("l") if l else None)
-        ap, _c = _ptr(out.get("alpha") if alpha else None)
+        xp = _out_ptr(out["x"], (n, d), "x") if x else None
+        lp = _out_ptr(out["l"], (n, n), "l") if l else None
+        ap = _out_ptr(out["alpha"], (n,), "alpha") if alpha else None
         self._ck(self._lib.nngp_get_state(self._h, xp, lp, ap))
         out["lambda"] = lam
         return out
@@ -299,13 +399,13 @@ class Handle:
         neuroestimator/README.md:28-29; its ``load_model`` is a warm-up, estimator.py:37-40)."""
         st = self.get_state()
         extra = {"m": st["m"]} if self.is_ntk else {}
-        np.savez(path, x=st["x"], l=st["l"], alpha=st["alpha"], lam=st["lambda"], depth=self.cfg.depth,
+        np.savez(_npz_path(path), x=st["x"], l=st["l"], alpha=st["alpha"], lam=st["lambda"], depth=self.cfg.depth,
                  sigma_w=self.cfg.sigma_w, sigma_b=self.cfg.sigma_b, diag_reg=self.cfg.diag_reg,
                  diag_reg_absolute=self.cfg.diag_reg_absolute, kernel_type="ntk" if self.is_ntk else "nngp", **extra)
 
     @classmethod
     def load(cls, path, **kw) -> "Handle":
-        z = np.load(path)
+        z = np.load(_npz_path(path))
         kt = str(z["kernel_type"]) if "kernel_type" in z.files else "nngp"
         h = cls(depth=int(z["depth"]), sigma_w=float(z["sigma_w"]), sigma_b=float(z["sigma_b"]),
                 diag_reg=float(z["diag_reg"]), diag_reg_absolute=bool(z["diag_reg_absolute"]), kernel_type=kt, **kw)

@@ -36,11 +36,22 @@ def _comm_device(group=None):
     return torch.device("cpu")
 
 
-def broadcast_fit(engine, src: int = 0, group=None):
+# doubles per broadcast chunk of the packed state (256 MB): large enough for NCCL to run at NVLink bandwidth, small
+# enough that the two staging buffers cost 0.5 GB instead of a second copy of the factor
+CHUNK = 32 * 1024 * 1024
+
+
+def broadcast_fit(engine, src: int = 0, group=None, chunk: int = CHUNK):
     """Rank ``src`` holds a fitted engine; on return every rank's engine holds the same state.
 
-    Traffic: 8*(N*N + N*D + N) bytes per receiving rank, once per fit (twice the N*N part in 'ntk' mode, whose state
-    also holds M = L^-1 K_dd L^-T).  Returns (N, D, lambda)."""
+    The state travels PACKED -- X, alpha, the lower triangle of L by rows (N(N+1)/2, half of the square), plus M in
+    'ntk' mode -- in chunks: ``nngp_state_pack`` fills a staging chunk straight from the handle's buffers,
+    ``dist.broadcast`` ships it, ``nngp_state_unpack`` stores it into the receiving handle's buffers; the layer-0
+    diagonal and the diagonal-block inverses are recomputed on arrival.  Two staging chunks alternate so that the
+    packing / unpacking of one overlaps the broadcast of the other.  Every hand-over between the library's stream and
+    torch's communication stream is a host-side wait (the C calls are complete on return; the broadcast handle is
+    waited for and the device synchronised before a chunk is unpacked or reused) -- there is no ordering between the
+    two streams to rely on.  Traffic per receiving rank: 8*(N*D + N + N(N+1)/2) bytes.  Returns (N, D, lambda)."""
     import torch
     dist = _dist()
     rank = dist.get_rank(group)
@@ -50,7 +61,56 @@ def broadcast_fit(engine, src: int = 0, group=None):
         n, d, lam = engine.dims()
         hdr[0], hdr[1], hdr[2], hdr[3] = n, d, lam, float(bool(getattr(engine, "is_ntk", False)))
     dist.broadcast(hdr, src=src, group=group)
-    n, d, lam, ntk = int(hdr[0].item()), int(hdr[1].item()), float(hdr[2].item()), bool(hdr[3].item())
+    hdr_h = hdr.cpu()
+    n, d, lam, ntk = int(hdr_h[0]), int(hdr_h[1]), float(hdr_h[2]), bool(hdr_h[3])
+    if not hasattr(engine, "state_pack"):          # engines without the packed interface (test doubles)
+        return _broadcast_fit_dense(engine, src, group, n, d, lam, ntk)
+    if rank != src:
+        engine.state_import_begin(n, d)
+    total = engine.packed_size()
+    chunk = max(1, min(int(chunk), total))
+    stage = [torch.empty(chunk, dtype=torch.float64, device=dev) for _ in range(2 if total > chunk else 1)]
+    sync = (lambda: torch.cuda.synchronize(dev)) if dev.type == "cuda" else (lambda: None)
+    offs = list(range(0, total, chunk))
+    pending = None                                  # (work, buffer index, offset, count) of the chunk in flight
+    for i, off in enumerate(offs):
+        cnt = min(chunk, total - off)
+        buf = stage[i % len(stage)][:cnt]
+        if rank == src:
+            engine.state_pack(off, cnt, buf)        # complete on return (library stream synchronised)
+        work = dist.broadcast(buf, src=src, group=group, async_op=True)
+        if pending is not None:                     # finish the previous chunk while this one travels
+            pw, pbuf, poff, pcnt = pending
+            pw.wait()
+            sync()
+            if rank != src:
+                engine.state_unpack(poff, pcnt, pbuf)
+        if len(stage) == 1:
+            work.wait()
+            sync()
+            if rank != src:
+                engine.state_unpack(off, cnt, buf)
+            pending = None
+        else:
+            pending = (work, buf, off, cnt)
+    if pending is not None:
+        pw, pbuf, poff, pcnt = pending
+        pw.wait()
+        sync()
+        if rank != src:
+            engine.state_unpack(poff, pcnt, pbuf)
+    if rank != src:
+        engine.state_import_end(lam)
+    del stage
+    return n, d, lam
+
+
+def _broadcast_fit_dense(engine, src, group, n, d, lam, ntk):
+    """Dense variant over get_state / set_state (full N x N factor)."""
+    import torch
+    dist = _dist()
+    rank = dist.get_rank(group)
+    dev = _comm_device(group)
     x = torch.empty((n, d), dtype=torch.float64, device=dev)
     l = torch.empty((n, n), dtype=torch.float64, device=dev)
     alpha = torch.empty(n, dtype=torch.float64, device=dev)
@@ -59,6 +119,11 @@ def broadcast_fit(engine, src: int = 0, group=None):
         engine.get_state(out={"x": x, "l": l, "alpha": alpha, **({"m": m} if ntk else {})})
     for t in (x, l, alpha) + ((m,) if ntk else ()):
         dist.broadcast(t, src=src, group=group)
+    if dev.type == "cuda":
+        # NCCL broadcasts are only ENQUEUED on torch's communication stream; the handle copies these buffers on its
+        # own non-blocking stream, which has no ordering with torch's streams -> the host must wait here, or a
+        # receiving rank could import a partially received state.
+        torch.cuda.synchronize(dev)
     if rank != src:
         if ntk:
             engine.set_state(x, l, alpha, lam, m=m)
@@ -66,7 +131,6 @@ def broadcast_fit(engine, src: int = 0, group=None):
             engine.set_state(x, l, alpha, lam)
     if dev.type == "cuda":
         torch.cuda.synchronize(dev)
-    del x, l, alpha, m
     return n, d, lam
 
 

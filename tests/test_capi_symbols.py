@@ -33,13 +33,26 @@ def test_library_exports_every_declared_symbol(lib):
     cdll = ctypes.CDLL(str(lib.LIB_PATH))
     for name in declared_functions():
         assert hasattr(cdll, name), f"{name} declared in include/nngp_b200.h but not exported"
-    assert cdll.nngp_abi_version() == 4
+    assert cdll.nngp_abi_version() == 5
+    cdll.nngp_build_id.restype = ctypes.c_char_p
+    from nngp_b200 import _build
+    assert cdll.nngp_build_id().decode() == _build.source_hash() == lib.built_id()
+
+
+def test_build_id_tracks_every_source_file(lib):
+    """The staleness check is by content and covers the C++ encoder and the header too (an mtime / *.cu-only check
+    would ship a stale binary for those)."""
+    from nngp_b200 import _build
+    names = {f.name for f in _build.source_files()}
+    assert {"capi.cu", "encoder.cc", "gemm_nt.cuh", "nngp_b200.h", "build.sh"} <= names
 
 
 def test_struct_layouts_match_header(lib):
-    # nngp_config: int32, 3 doubles, 2 int32, int64, int32 -> 56 bytes with natural alignment
-    assert ctypes.sizeof(lib.NngpConfig) == 56
-    assert ctypes.sizeof(lib.NngpStats) == 8 * 22
+    # nngp_config: int32, 3 doubles, 2 int32, int64, 2 int32 (56 bytes) + n_gpus, device_ids[8], latency_mode
+    assert ctypes.sizeof(lib.NngpConfig) == 56 + 4 * 10
+    assert lib.NngpConfig.n_gpus.offset == 56 and lib.NngpConfig.device_ids.offset == 60
+    assert lib.NngpConfig.latency_mode.offset == 92
+    assert ctypes.sizeof(lib.NngpStats) == 8 * 25
 
 
 def test_no_cpu_fallback_without_gpu(lib):
@@ -78,14 +91,16 @@ def test_stage_release_carries_a_dependence_on_the_fragment_loads(lib):
     sass = subprocess.run([tool, "-sass", str(lib.LIB_PATH)], capture_output=True, text=True).stdout
     instrs = [m.group(1).strip() for m in re.finditer(r"/\*[0-9a-f]{4,}\*/\s+(.*?);", sass)]
     arrives = [i for i, t in enumerate(instrs) if "SYNCS.ARRIVE.TRANS64.A1T0" in t]
-    assert len(arrives) >= 10, "expected the consumer releases of gemm_nt_kernel<0..3> and trsm_fused_kernel"
+    nvcc = subprocess.run(["/usr/local/cuda/bin/nvcc", "--version"], capture_output=True, text=True).stdout.strip().splitlines()
+    where = f" [compiler: {nvcc[-2] if len(nvcc) > 1 else nvcc}; the guard is tied to this ptxas' code generation]"
+    assert len(arrives) >= 10, "expected the consumer releases of gemm_nt_kernel<0..3> and trsm_fused_kernel" + where
     for i in arrives:
         reg = re.search(r"\[(R\d+)\+", instrs[i]).group(1)
         add = next((j for j in range(i - 1, max(i - 16, 0), -1)
                     if re.search(r"IADD\w*(\.\w+)* %s," % reg, instrs[j])), None)
-        assert add is not None, f"arrive address {reg} is not computed by an add: {instrs[max(i - 4, 0):i + 1]}"
+        assert add is not None, f"arrive address {reg} is not computed by an add: {instrs[max(i - 4, 0):i + 1]}" + where
         srcs = set(re.findall(r"R\d+", instrs[add].split(",", 1)[1]))
         masked = [j for j in range(add - 1, max(add - 60, 0), -1)
                   if "LOP3.LUT" in instrs[j] and "0xc0" in instrs[j]
                   and (re.search(r"LOP3\.LUT (?:P\d+, )?(R\d+|RZ),", instrs[j]) or [None, None])[1] in srcs]
-        assert masked, f"no `seen & zero` feeding the arrive address: {instrs[max(add - 6, 0):i + 1]}"
+        assert masked, f"no `seen & zero` feeding the arrive address: {instrs[max(add - 6, 0):i + 1]}" + where
