@@ -31,10 +31,40 @@ Reference call sites restated (file:line under the reference tree):
 """
 from __future__ import annotations
 
+import os
+from concurrent.futures import ThreadPoolExecutor
+
 import numpy as np
 import scipy.linalg as sla
 
 TWO_PI = 2.0 * np.pi
+# threads for the elementwise arc-cosine recursion (the BLAS calls use OpenBLAS' own pool)
+THREADS = int(os.environ.get("NNGP_ORACLE_THREADS", "0")) or len(os.sched_getaffinity(0))
+_POOL = None
+
+
+def _pool():
+    global _POOL
+    if _POOL is None:
+        _POOL = ThreadPoolExecutor(max_workers=THREADS)
+    return _POOL
+
+
+def _relu_layers(k, ntk, q1, q2, depth, sw2, sb2):
+    """depth-1 ReLU arc-cosine steps on the block k (rows: q1, columns: q2), in place (Appendix A.1 / A.5)."""
+    factor = 1.0 / TWO_PI
+    q1, q2l = q1.copy(), q2.copy()
+    for _ in range(depth - 1):
+        prod = q1[:, None] * q2l[None, :]
+        s = np.sqrt(np.maximum(prod - k * k, 0.0))
+        theta = np.arctan2(s, k)
+        theta[(s == 0.0) & (k == 0.0)] = np.pi / 2
+        dot_sigma = 0.5 - factor * theta
+        k[...] = sw2 * (factor * s + dot_sigma * k) + sb2
+        if ntk is not None:
+            ntk[...] = k + sw2 * (ntk * dot_sigma)
+        q1 = sw2 * (0.5 * q1) + sb2
+        q2l = sw2 * (0.5 * q2l) + sb2
 
 
 def layer0_diag(x: np.ndarray, sigma_w: float = 1.0, sigma_b: float = 0.0) -> np.ndarray:
@@ -69,23 +99,25 @@ def kernel_fn(x1: np.ndarray, x2: np.ndarray | None = None, depth: int = 2, sigm
     q1_all, q2 = layer0_diag(x1, sigma_w, sigma_b), layer0_diag(x2, sigma_w, sigma_b)
     out = np.empty((x1.shape[0], x2.shape[0]), dtype=np.float64)
     out_ntk = np.empty_like(out) if get in ("ntk", "both") else None
-    factor = 1.0 / TWO_PI
     for r0 in range(0, x1.shape[0], chunk):
         r1 = min(r0 + chunk, x1.shape[0])
-        k = sw2 * ((x1[r0:r1] @ x2.T) / D) + sb2
+        k = sw2 * ((x1[r0:r1] @ x2.T) / D) + sb2          # BLAS dgemm (all cores)
         ntk = k.copy() if out_ntk is not None else None
-        q1, q2l = q1_all[r0:r1].copy(), q2.copy()
-        for _ in range(depth - 1):
-            prod = q1[:, None] * q2l[None, :]
-            s = np.sqrt(np.maximum(prod - k * k, 0.0))
-            theta = np.arctan2(s, k)
-            theta[(s == 0.0) & (k == 0.0)] = np.pi / 2
-            dot_sigma = 0.5 - factor * theta
-            k = sw2 * (factor * s + dot_sigma * k) + sb2
-            if ntk is not None:
-                ntk = k + sw2 * (ntk * dot_sigma)
-            q1 = sw2 * (0.5 * q1) + sb2
-            q2l = sw2 * (0.5 * q2l) + sb2
+        # The elementwise recursion is one fused, multi-threaded loop in XLA:CPU (the reference's backend); numpy's
+        # ufuncs are single-threaded but release the GIL, so row slices of the chunk run on a thread pool.  Every
+        # entry sees exactly the same operations as in a single pass: results do not depend on the thread count.
+        nthr = max(1, min(THREADS, (r1 - r0 + 63) // 64))
+        bounds = [(r1 - r0) * i // nthr for i in range(nthr + 1)]
+
+        def work(i, k=k, ntk=ntk, r0=r0):
+            a, b = bounds[i], bounds[i + 1]
+            if b > a:
+                _relu_layers(k[a:b], None if ntk is None else ntk[a:b], q1_all[r0 + a:r0 + b], q2, depth, sw2, sb2)
+
+        if nthr == 1:
+            work(0)
+        else:
+            list(_pool().map(work, range(nthr)))
         out[r0:r1] = k
         if out_ntk is not None:
             out_ntk[r0:r1] = ntk
@@ -116,8 +148,21 @@ class Fit:
         reg = max(diag_reg, 0.0)
         self.lam = reg if diag_reg_absolute else reg * (np.trace(k) / n)   # [nt: _add_diagonal_regularizer]
         k[np.diag_indices(n)] += self.lam
-        self.c = sla.cholesky(k, lower=True, overwrite_a=True, check_finite=False)  # [nt: cho_factor]
+        # [nt: cho_factor]  k is symmetric, so its transpose view (Fortran order) is the same matrix: LAPACK dpotrf
+        # then factors in place instead of scipy first copying the 8*N^2 bytes into column-major order
+        self.c = sla.cholesky(k.T, lower=True, overwrite_a=True, check_finite=False)
         self.alpha = sla.cho_solve((self.c, True), self.y, check_finite=False)      # [nt: cho_solve]
+
+    @classmethod
+    def from_state(cls, x, y, c, alpha, lam, depth=2, sigma_w=1.0, sigma_b=0.0):
+        """A Fit around an existing factorisation (lower factor c, alpha, lambda) -- bench.py's bounded CPU sample
+        times predict() against a model of the full size without paying the CPU fit again."""
+        self = cls.__new__(cls)
+        self.x = np.asarray(x, dtype=np.float64)
+        self.y = np.asarray(y, dtype=np.float64).reshape(-1)
+        self.depth, self.sigma_w, self.sigma_b = depth, sigma_w, sigma_b
+        self.c, self.alpha, self.lam = np.asarray(c), np.asarray(alpha).reshape(-1), float(lam)
+        return self
 
     def log_marginal_likelihood(self):
         """-1/2 y^T (K+lam I)^-1 y - sum log C_ii - N/2 log 2 pi  (standard GP evidence; cf. train.py:86-103)."""

@@ -67,6 +67,39 @@ class FakeNtkEngine(FakeEngine):
                       "m": m.numpy().copy()}
 
 
+class FakePackedEngine(FakeEngine):
+    """FakeEngine + the packed-state interface of _lib.Handle (nngp_state_pack / _unpack; include/nngp_b200.h):
+    [ X (N*D) | alpha (N) | tril(L) by rows | ntk: M (N*N) ] -- so broadcast_fit's chunked pipeline runs on CPU."""
+
+    def _flat(self):
+        st = self.state
+        n = st["x"].shape[0]
+        parts = [st["x"].ravel(), st["alpha"].ravel(), st["l"][np.tril_indices(n)]]
+        return np.concatenate(parts)
+
+    def packed_size(self):
+        n, d = (self.state["x"].shape if self.state else self._shape)
+        return n * d + n + n * (n + 1) // 2
+
+    def state_pack(self, off, cnt, dst):
+        import torch
+        dst.copy_(torch.from_numpy(self._flat()[off:off + cnt]))
+
+    def state_import_begin(self, n, d):
+        self.state, self._shape = None, (n, d)
+        self._buf = np.full(n * d + n + n * (n + 1) // 2, np.nan)
+
+    def state_unpack(self, off, cnt, src):
+        self._buf[off:off + cnt] = src.numpy()
+
+    def state_import_end(self, lam):
+        n, d = self._shape
+        l = np.zeros((n, n))
+        l[np.tril_indices(n)] = self._buf[n * d + n:]
+        self.state = {"x": self._buf[:n * d].reshape(n, d).copy(), "alpha": self._buf[n * d:n * d + n].copy(), "l": l,
+                      "lambda": lam}
+
+
 def _worker(rank, world, port, q):
     sys.path[:0] = [str(ROOT), str(ROOT / "nngp-src_b200"), str(ROOT / "oracle"), str(ROOT / "tests")]
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -89,6 +122,14 @@ def _worker(rank, world, port, q):
     ndist.broadcast_fit(ntk_eng, src=0)
     ntk_ok = bool(np.array_equal(ntk_eng.state["m"], np.arange(96.0 * 96.0).reshape(96, 96))
                   and ntk_eng.state["lambda"] == 0.25 and np.array_equal(ntk_eng.state["alpha"], ytr))
+    # the packed, chunked path (what the real handle uses): odd chunk sizes, one chunk, chunk > total
+    for chunk in (1000, 777, 10 ** 9):
+        pk = FakePackedEngine()
+        if rank == 0:
+            pk.state = dict(eng.state)
+        ndist.broadcast_fit(pk, src=0, chunk=chunk)
+        ntk_ok = ntk_ok and all(np.array_equal(pk.state[k], eng.state[k]) for k in ("x", "l", "alpha"))
+        ntk_ok = ntk_ok and pk.state["lambda"] == eng.state["lambda"]
     q.put((rank, n, d, lam, mean, var, own_m, m_only, (none is None) and ntk_ok))
     dist.barrier()
     dist.destroy_process_group()
