@@ -79,7 +79,10 @@ struct nngp_handle {
   DevBuf Linv;    // inv(L_JJ) of every 64 x 64 diagonal block of L (trtri_diag_kernel), operand of the solves' diagonal step
   DevBuf y;       // raw labels of the last nngp_fit (kept for nngp_append_fit)
   DevBuf app_x, app_y;  // nngp_append_fit staging: [X; X_new], [y; y_new]
+  DevBuf panel_inv;  // scratch inverses of a factorisation that is not the handle's own factor (Schur block, nngp_diag_potrf)
   DevBuf zkeep;   // z = L^-1 y of the last fit (the backward substitution destroys its copy in the factor buffer)
+  DevBuf Linvfull;  // latency mode: the explicit inverse factor L^-1 (N x N, lower, row-major, ld = ldl)
+  bool have_inv = false;
   DevBuf L2;      // second factor buffer: target of the incremental (fixed-lambda) append, then swapped with L
   bool have_y = false;
   bool importing = false;   // between nngp_state_import_begin and _end
@@ -344,21 +347,40 @@ int chol_outer_width(int64_t N) {
 }
 
 // `R` = N + extra rows riding along below the matrix (see run_potrf).
-int potrf_panel(nngp_handle* h, double* A, int64_t ld, int64_t N, int64_t R, int64_t j0, int64_t w) {
+// Per 64-wide sub-panel: (1) left-looking update from the panel's earlier columns (DMMA), (2) potf2_64: Cholesky of
+// the diagonal block AND its inverse W = inv(L_JJ) in one one-CTA launch, (3) the block column below it,
+// X L_JJ^T = B  ->  X = B W^T, as a K = 64 product on the tensor pipe (gemm_nt_kernel<EPI_DIAG>, in place: a CTA reads
+// its own 128 x 64 tile completely before it stores it).  Step (3) used to be a one-thread-per-row substitution on
+// the FP64 CUDA cores (23 us per sub-panel on the critical path of the panel chain; NNGP_PANEL_SOLVE=fma brings
+// it back for A/B runs).  `Winv` receives the inverses, block J at rows [64 J, 64 J + 64) of a 64-wide matrix.
+bool panel_solve_fma() {
+  static const bool v = [] { const char* e = getenv("NNGP_PANEL_SOLVE"); return e && !strcmp(e, "fma"); }();
+  return v;
+}
+
+int potrf_panel(nngp_handle* h, double* A, int64_t ld, int64_t N, int64_t R, int64_t j0, int64_t w, double* Winv) {
   int* info = h->flags.as<int>();
-  MatView Av{A, R, N, ld};
+  MatView Av{A, R, N, ld}, Wv{Winv, round_up(N, NB), NB, NB};
   for (int64_t s0 = j0; s0 < j0 + w; s0 += NB) {
     const int64_t nb = std::min<int64_t>(NB, N - s0);
     if (s0 > j0)  // A[s0:R, s0:s0+nb] -= A[s0:R, j0:s0] * A[s0:s0+nb, j0:s0]^T
       CKR(run_gemm_sub(h, Av, s0, j0, Av, s0, j0, R - s0, nb, s0 - j0, A + s0 * ld + s0, ld, 0));
-    potf2_64_kernel<<<1, POTF2_THREADS, 0, h->cur>>>(A + s0 * ld + s0, ld, (int)nb, (int)s0, info);
+    potf2_64_kernel<<<1, POTF2_THREADS, 0, h->cur>>>(A + s0 * ld + s0, ld, (int)nb, (int)s0, info, Winv + s0 * NB);
     h->st.kernel_launches++;
     const int64_t below = R - s0 - nb;
     if (below > 0) {
-      const int grid = (int)((below + TRSM_ROWS - 1) / TRSM_ROWS);
-      trsm_rows_64_kernel<<<grid, TRSM_ROWS, TRSM_SMEM_BYTES, h->cur>>>(A + (s0 + nb) * ld + s0, ld, (int)below,
-                                                                       A + s0 * ld + s0, ld, (int)nb);
-      h->st.kernel_launches++;
+      if (panel_solve_fma()) {
+        const int grid = (int)((below + TRSM_ROWS - 1) / TRSM_ROWS);
+        trsm_rows_64_kernel<<<grid, TRSM_ROWS, TRSM_SMEM_BYTES, h->cur>>>(A + (s0 + nb) * ld + s0, ld, (int)below,
+                                                                         A + s0 * ld + s0, ld, (int)nb);
+        h->st.kernel_launches++;
+      } else {
+        GemmParams p{};
+        p.M = (int)below; p.N = (int)nb; p.ktiles = NB / GEMM_BK;
+        p.C = A + (s0 + nb) * ld + s0; p.ldc = ld;
+        p.var = nullptr; p.J = 0; p.col_blocks = 1;
+        CKR(launch_gemm<EPI_DIAG>(h, Av, (int)(s0 + nb), (int)s0, Wv, (int)s0, 0, p));
+      }
     }
   }
   return NNGP_OK;
@@ -374,7 +396,7 @@ int potrf_panel(nngp_handle* h, double* A, int64_t ld, int64_t N, int64_t R, int
 // `extra` rows stored below the matrix (rows N..N+extra-1, N columns each) are carried through every
 // panel solve and trailing update: on exit they hold  E L^-T.  The fit puts y^T there, so the forward
 // substitution z = L^-1 y of the alpha solve costs nothing extra (one more row in GEMMs already running).
-int run_potrf(nngp_handle* h, double* A, int64_t ld, int64_t N, int64_t extra = 0) {
+int run_potrf(nngp_handle* h, double* A, int64_t ld, int64_t N, int64_t extra, double* Winv) {
   const int W = chol_outer_width(N);
   const int64_t R = N + extra;
   MatView Av{A, R, N, ld};
@@ -393,7 +415,7 @@ int run_potrf(nngp_handle* h, double* A, int64_t ld, int64_t N, int64_t extra = 
     const int64_t w = std::min<int64_t>(W, N - j0);
     const int64_t t0 = j0 + w;
     h->cur = lookahead ? h->panel_stream : h->stream;
-    rc = potrf_panel(h, A, ld, N, R, j0, w);
+    rc = potrf_panel(h, A, ld, N, R, j0, w, Winv);
     if (rc != NNGP_OK || t0 >= N) break;
     if (lookahead) ce = edge(ev_panel, h->panel_stream, h->stream);
     h->cur = h->stream;
@@ -420,8 +442,9 @@ int run_potrf(nngp_handle* h, double* A, int64_t ld, int64_t N, int64_t extra = 
 // B (rows x N, ldb) <- B * L^-T  (solve X L^T = B; L lower N x N row-major) plus, optionally, the posterior
 // variance of every row, as ONE persistent kernel (trsm_fused.cuh).
 int run_trsm_fused(nngp_handle* h, double* B, int64_t ldb, int64_t rows, const double* L, int64_t ldl, int64_t N,
-                   const double* Linv, const double* kss, double* var) {
+                   const double* Linv, const double* kss, double* var, int upper_start = 0) {
   TrsmFusedParams p{};
+  p.upper_start = upper_start;
   p.B = B; p.ldb = ldb; p.rows = (int)rows; p.L = L; p.ldl = ldl; p.N = (int)N;
   p.row_tiles = (int)((rows + GEMM_BM - 1) / GEMM_BM);
   p.col_blocks = (int)((N + NB - 1) / NB);
@@ -453,7 +476,7 @@ int run_trsm_fused(nngp_handle* h, double* B, int64_t ldb, int64_t rows, const d
   CK(cudaGetLastError());
   h->st.kernel_launches++;
   h->st.gemm_launches++;
-  h->st.gemm_flops += (double)rows * (double)N * (double)N;  // N^2 flop per test row
+  h->st.gemm_flops += (double)rows * (double)N * (double)N * (upper_start ? 1.0 / 3.0 : 1.0);  // N^2 flop per test row
   return NNGP_OK;
 }
 
@@ -510,6 +533,63 @@ int run_predict_solve(nngp_handle* h, double* B, int64_t ldb, int64_t rows, cons
   const int64_t row_tiles = (rows + GEMM_BM - 1) / GEMM_BM;
   if (row_tiles <= small_batch_row_tiles(h)) return run_trsm_right(h, B, ldb, rows, L, ldl, N, Linv, kss, var);
   return run_trsm_fused(h, B, ldb, rows, L, ldl, N, Linv, kss, var);
+}
+
+// ---- latency mode (cfg.latency_mode): explicit inverse factor ---------------------------------------
+// Serving a handful of query lines per call (estimator.py:42-62) is latency-bound on the substitution chain of
+// V = K_* L^-T: N/64 dependent steps of ~10 us.  With W = L^-1 held explicitly the same V is a plain product
+// K_* W^T -- no dependencies, every column tile independent -- whose cost for a few rows is one pass over W.
+// W is built once per fit on the same DMMA kernels: X L^T = I solved by the persistent kernel (upper-triangular
+// right-hand side: N^3/3 flop), X = L^-T, then W = X^T.  inv(L) is as benign as inv(L_JJ) in the diagonal step:
+// the error of K_* W^T is eps * cond(L) = eps * sqrt(cond(K + lambda I)) (tests/checks/illcond_report.py).
+int build_inverse(nngp_handle* h) {
+  const int64_t N = h->N, ldl = h->ldl;
+  CKR(ensure(h, h->Linvfull, (size_t)N * ldl * sizeof(double)));
+  CKR(ensure(h, h->Kdd, (size_t)N * ldl * sizeof(double)));     // scratch for L^-T (otherwise the 'ntk' K_dd buffer)
+  double* X = h->Kdd.as<double>();
+  cudaEvent_t a = get_event(h), b = get_event(h);
+  cudaEventRecord(a, h->stream);
+  set_identity_kernel<<<4 * h->sm_count, 256, 0, h->stream>>>(X, ldl, (int)N);
+  h->st.kernel_launches++;
+  CKR(run_trsm_fused(h, X, ldl, N, h->L.as<double>(), ldl, N, h->Linv.as<double>(), nullptr, nullptr, 1));
+  dim3 tg((unsigned)((N + 31) / 32), (unsigned)((N + 31) / 32));
+  transpose_kernel<<<tg, dim3(32, 8), 0, h->stream>>>(X, h->Linvfull.as<double>(), ldl, (int)N);
+  h->st.kernel_launches++;
+  cudaEventRecord(b, h->stream);
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, a, b) == cudaSuccess) h->st.inverse_ms = ms;
+  h->ev_pool.push_back(a); h->ev_pool.push_back(b);
+  flush_class_events(h);
+  h->have_inv = true;
+  return NNGP_OK;
+}
+
+// Row count up to which nngp_predict uses the explicit inverse (NNGP_LATENCY_ROWS overrides; read per call).
+int64_t latency_rows(const nngp_handle* h) {
+  if (!h->have_inv) return 0;
+  const char* e = getenv("NNGP_LATENCY_ROWS");
+  return e ? atoll(e) : 4096;
+}
+
+// var[r] = kss[r] - |K_*[r,:] W^T|^2 through the explicit inverse: one triangular GEMM whose epilogue reduces the
+// squares of each 64-column tile (V itself is never written), then a fixed-order sum over the tiles.
+int run_inverse_variance(nngp_handle* h, const double* B, int64_t ldb, int64_t rows, const double* kss, double* var) {
+  const int64_t N = h->N;
+  const int col_tiles = (int)((N + GEMM_BN - 1) / GEMM_BN);
+  CKR(ensure(h, h->partial, (size_t)rows * col_tiles * 8));
+  GemmParams p{};
+  p.M = (int)rows; p.N = (int)N; p.ktiles = (int)((N + GEMM_BK - 1) / GEMM_BK);
+  p.ldc = ldb; p.W = nullptr; p.partial = h->partial.as<double>(); p.tri_k = 1;
+  MatView a{B, rows, N, ldb}, b{h->Linvfull.as<double>(), N, N, h->ldl};
+  CKR(launch_gemm<EPI_ROWDOT>(h, a, 0, 0, b, 0, 0, p));
+  // launch_gemm counted 2*M*N*K for the full square; the triangular product is half of it: N^2 flop per row
+  h->st.gemm_flops -= (double)rows * (double)N * (double)p.ktiles * GEMM_BK;
+  var_from_partial_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, h->stream>>>(kss, h->partial.as<double>(), col_tiles, (int)rows, var);
+  h->st.kernel_launches++;
+  CK(cudaGetLastError());
+  return NNGP_OK;
 }
 
 // out <- L^-T z  (blocked backward substitution; z is destroyed; reads L exactly once)
@@ -585,7 +665,7 @@ int bind_device(nngp_handle* h) {
   return NNGP_OK;
 }
 
-void drop_fit(nngp_handle* h) { h->importing = false; h->fitted = false; h->have_lml = false; h->have_y = false; h->have_M = false; }
+void drop_fit(nngp_handle* h) { h->importing = false; h->have_inv = false; h->fitted = false; h->have_lml = false; h->have_y = false; h->have_M = false; }
 
 int alloc_state(nngp_handle* h, int64_t N, int64_t D) {
   h->N = N; h->D = D;
@@ -632,13 +712,15 @@ int replicate_state(nngp_handle* h) {
     drop_fit(p);
     int rc = alloc_state(p, N, D);
     if (rc == NNGP_OK && ntk && h->have_M) rc = ensure(p, p->Mmat, (size_t)N * ldl * sizeof(double));
+    if (rc == NNGP_OK && h->have_inv) rc = ensure(p, p->Linvfull, (size_t)N * ldl * sizeof(double));
     if (rc != NNGP_OK) { h->err = "replica on device " + std::to_string(p->device) + ": " + p->err; cudaSetDevice(h->device); return rc; }
   }
   const int64_t RP = 512;                       // rows per panel
   const int npanel = (int)((N + RP - 1) / RP);
   // items in chain order: 0 = small vectors (X, q, alpha, Linv), 1..npanel = factor panels, then M panels
   const int nM = (ntk && h->have_M) ? npanel : 0;
-  const int nitems = 1 + npanel + nM;
+  const int nI = h->have_inv ? npanel : 0;          // latency mode: the explicit inverse (lower trapezoids, like L)
+  const int nitems = 1 + npanel + nM + nI;
   std::vector<std::vector<cudaEvent_t>> ev((size_t)G);   // ev[g][i]: item i has arrived on chain[g]
   cudaError_t ce = cudaSuccess;
   auto copy_item = [&](nngp_handle* src, nngp_handle* dst, int item, cudaStream_t st) -> cudaError_t {
@@ -650,12 +732,15 @@ int replicate_state(nngp_handle* h) {
       if (e == cudaSuccess) e = cudaMemcpyAsync(dst->Linv.p, src->Linv.p, (size_t)round_up(N, NB) * NB * 8, cudaMemcpyDefault, st);
       return e;
     }
-    const bool isM = item > npanel;
-    const int64_t r0 = (int64_t)(isM ? item - npanel - 1 : item - 1) * RP;
+    const int which = item <= npanel ? 0 : (item <= npanel + nM ? 1 : 2);     // 0: L, 1: M, 2: L^-1
+    const bool isM = which == 1;
+    const int64_t r0 = (int64_t)((item - 1) % npanel) * RP;
     const int64_t r1 = std::min<int64_t>(r0 + RP, N);
-    const double* sp = (isM ? src->Mmat.as<double>() : src->L.as<double>()) + r0 * ldl;
-    double* dp = (isM ? dst->Mmat.as<double>() : dst->L.as<double>()) + r0 * ldl;
-    const int64_t width = isM ? N : r1;        // the factor: columns [0, r1) of these rows; M: whole rows
+    const DevBuf& sb = which == 0 ? src->L : (which == 1 ? src->Mmat : src->Linvfull);
+    const DevBuf& db = which == 0 ? dst->L : (which == 1 ? dst->Mmat : dst->Linvfull);
+    const double* sp = sb.as<double>() + r0 * ldl;
+    double* dp = db.as<double>() + r0 * ldl;
+    const int64_t width = isM ? N : r1;        // the factors: columns [0, r1) of these rows; M: whole rows
     return cudaMemcpy2DAsync(dp, ldl * 8, sp, ldl * 8, (size_t)width * 8, (size_t)(r1 - r0), cudaMemcpyDefault, st);
   };
   for (int g = 0; g + 1 < G && ce == cudaSuccess; ++g) {
@@ -683,15 +768,18 @@ int replicate_state(nngp_handle* h) {
   for (int g = 1; g < G; ++g) {
     nngp_handle* p = chain[g];
     p->lambda = h->lambda; p->fitted = true; p->have_M = ntk && h->have_M;
-    p->have_lml = false; p->have_y = false;
+    p->have_lml = false; p->have_y = false; p->have_inv = h->have_inv;
   }
   h->st.replicate_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
   int64_t bytes = (int64_t)N * ldx * 8 + 2 * N * 8 + round_up(N, NB) * NB * 8;
+  int64_t bytes_tri = 0;
   for (int c = 0; c < npanel; ++c) {
     const int64_t r0 = (int64_t)c * RP, r1 = std::min<int64_t>(r0 + RP, N);
-    bytes += (r1 - r0) * r1 * 8;
+    bytes_tri += (r1 - r0) * r1 * 8;
   }
+  bytes += bytes_tri;
   if (nM) bytes += N * N * 8;
+  if (nI) bytes += bytes_tri;
   h->st.replicate_bytes = bytes;
   return NNGP_OK;
 }
@@ -869,7 +957,7 @@ void nngp_destroy(nngp_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->X, &h->q, &h->L, &h->alpha, &h->flags, &h->lam_d, &h->xt, &h->qt, &h->kss,
-                    &h->blk, &h->mean_d, &h->var_d, &h->ssq, &h->sync_ints, &h->Mmat, &h->Kdd, &h->blk2, &h->cross, &h->partial, &h->mean_partial, &h->ka, &h->kb, &h->kqa, &h->kqb, &h->kout, &h->Linv, &h->zkeep, &h->L2, &h->y, &h->app_x, &h->app_y, &h->sel_mean, &h->sel_var, &h->sel_score, &h->sel_key,
+                    &h->blk, &h->mean_d, &h->var_d, &h->ssq, &h->sync_ints, &h->Mmat, &h->Kdd, &h->blk2, &h->cross, &h->partial, &h->mean_partial, &h->ka, &h->kb, &h->kqa, &h->kqb, &h->kout, &h->Linv, &h->Linvfull, &h->panel_inv, &h->zkeep, &h->L2, &h->y, &h->app_x, &h->app_y, &h->sel_mean, &h->sel_var, &h->sel_score, &h->sel_key,
                     &h->sel_state, &h->sel_okey, &h->sel_oidx, &h->sel_max})
     release(*b);
   for (auto& r : h->pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -992,8 +1080,7 @@ static int fit_impl(nngp_handle* h, const double* x_train, const double* y_train
   StageTimer t_chol(h, &h->st.fit_chol_ms);
   // y^T goes into row N of the factor buffer: the factorisation turns it into z^T = (L^-1 y)^T
   CK(cudaMemcpyAsync(L + N * h->ldl, alpha, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-  CKR(run_potrf(h, L, h->ldl, N, 1));
-  CKR(run_trtri_diag(h));
+  CKR(run_potrf(h, L, h->ldl, N, 1, h->Linv.as<double>()));   // also leaves inv(L_JJ) of every diagonal block in Linv
   t_chol.stop();
 
   StageTimer t_solve(h, &h->st.fit_solve_ms);
@@ -1029,6 +1116,7 @@ static int fit_impl(nngp_handle* h, const double* x_train, const double* y_train
   h->have_lml = true;
   h->have_y = true;
   h->have_M = ntk;
+  if (h->cfg.latency_mode && !ntk) CKR(build_inverse(h));
   return NNGP_OK;
 }
 
@@ -1148,6 +1236,7 @@ int nngp_reserve(nngp_handle* h, int64_t n_train_max, int64_t dim, int64_t n_tes
 static int append_incremental(nngp_handle* h, int64_t M) {
   const int64_t N = h->N, D = h->D, Nn = N + M;
   const int64_t ldo = h->ldl, ldn = round_up(Nn, 16);
+  h->have_inv = false;    // (latency mode: rebuilt by nngp_append_fit once the factor is extended)
   const double sw2 = h->cfg.sigma_w * h->cfg.sigma_w, sb2 = h->cfg.sigma_b * h->cfg.sigma_b;
   StageTimer t_total(h, &h->st.fit_total_ms);
   CKR(ensure(h, h->L2, (size_t)(Nn + 1) * ldn * sizeof(double)));
@@ -1189,7 +1278,8 @@ static int append_incremental(nngp_handle* h, int64_t M) {
     MatView Av{Ln, Nn + 1, N, ldn};
     CKR(run_gemm_sub(h, Av, N, 0, Av, N, 0, M + 1, M, round_up(N, GEMM_BK), S, ldn, 1));
   }
-  CKR(run_potrf(h, S, ldn, M, 1));                                                                         // L22, z_new
+  CKR(ensure(h, h->panel_inv, (size_t)round_up(M, NB) * NB * sizeof(double)));   // inverses on the Schur block's own 64-grid
+  CKR(run_potrf(h, S, ldn, M, 1, h->panel_inv.as<double>()));                                              // L22, z_new
   // from here on the handle describes the extended model
   std::swap(h->L, h->L2);
   h->N = Nn; h->ldl = ldn;
@@ -1252,6 +1342,7 @@ int nngp_append_fit(nngp_handle* h, const double* x_new, const double* y_new, in
   };
   for (auto* p : h->peers) drop_fit(p);
   if (rc == NNGP_OK) rc = body();
+  if (rc == NNGP_OK && h->cfg.latency_mode && h->cfg.kernel_type == 0 && !h->have_inv) rc = build_inverse(h);
   if (rc == NNGP_OK) rc = replicate_state(h);
   return rc;
 }
@@ -1384,8 +1475,11 @@ static int predict_impl(nngp_handle* h, const double* x_test, int64_t T, double*
         h->st.kernel_launches += 2;
         timers.back().stop();
       } else {
-        timers.emplace_back(h, &h->st.pred_trsm_ms);   // solve + variance in one persistent kernel
-        CKR(run_predict_solve(h, blk, ldl, rows, h->L.as<double>(), ldl, N, h->kss.as<double>(), h->var_d.as<double>() + t0));
+        timers.emplace_back(h, &h->st.pred_trsm_ms);
+        if (T <= latency_rows(h))                      // latency mode, small batch: dependency-free product with L^-1
+          CKR(run_inverse_variance(h, blk, ldl, rows, h->kss.as<double>(), h->var_d.as<double>() + t0));
+        else                                           // solve + variance in one persistent kernel
+          CKR(run_predict_solve(h, blk, ldl, rows, h->L.as<double>(), ldl, N, h->kss.as<double>(), h->var_d.as<double>() + t0));
         timers.back().stop();
       }
     }
@@ -1466,6 +1560,7 @@ int nngp_set_state(nngp_handle* h, const double* x, const double* l, const doubl
   CK(cudaGetLastError());
   h->lambda = lambda;
   h->fitted = true;
+  if (h->cfg.latency_mode && h->cfg.kernel_type == 0) CKR(build_inverse(h));
   return replicate_state(h);
 }
 
@@ -1574,6 +1669,7 @@ int nngp_state_import_end(nngp_handle* h, double lambda) {
   h->lambda = lambda;
   h->fitted = true;
   h->have_M = h->cfg.kernel_type == 1;
+  if (h->cfg.latency_mode && h->cfg.kernel_type == 0) CKR(build_inverse(h));
   return replicate_state(h);
 }
 
@@ -1655,7 +1751,8 @@ int nngp_diag_potrf(nngp_handle* h, double* a, int64_t N) {
     cudaMemcpyAsync(A.as<double>() + N * ld, ones.data(), N * sizeof(double), cudaMemcpyHostToDevice, h->stream);
     cudaStreamSynchronize(h->stream);
   }
-  if (rc == NNGP_OK) rc = run_potrf(h, A.as<double>(), ld, N, extra);
+  if (rc == NNGP_OK) rc = ensure(h, h->panel_inv, (size_t)round_up(N, NB) * NB * sizeof(double));
+  if (rc == NNGP_OK) rc = run_potrf(h, A.as<double>(), ld, N, extra, h->panel_inv.as<double>());
   if (rc == NNGP_OK) rc = download(h, A.as<double>(), N, N, ld, a);
   int flags[2] = {0, 0};
   cudaMemcpyAsync(flags, h->flags.p, sizeof flags, cudaMemcpyDeviceToHost, h->stream);

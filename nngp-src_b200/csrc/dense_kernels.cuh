@@ -86,8 +86,40 @@ __global__ void diag_reg_kernel(double* __restrict__ K, long long ld, int N, dou
 // factor is bitwise that of the one-column-per-step version this replaces (34 us -> 10 us per block).
 // On a non-positive pivot: *info = global pivot index + 1 (first failure wins), block left as is.
 constexpr int POTF2_THREADS = 256;
+// Inverse of the lower-triangular 64 x 64 block in Ls (identity padded), by all 256 threads of the CTA: column c of
+// W = L^-1 is the forward substitution L w = e_c; four adjacent lanes share a column (lane part p owns w[i], i = p mod 4,
+// in registers) and split every dot product  sum_{k<i} L[i][k] w[k]  four ways, joined by two shuffles -- 64 dependent
+// steps of ~4 FMAs + 2 shuffles instead of the 2016-FMA chain of one thread per column.  Output: row-major 64 x 64.
+__device__ __forceinline__ void invert_lower_64(const double (*Ls)[NB + 1], double* __restrict__ Wout) {
+  const int tid = threadIdx.x;
+  const int c = tid >> 2, p = tid & 3;
+  double w[NB / 4];
+#pragma unroll
+  for (int j = 0; j < NB / 4; ++j) w[j] = 0.0;
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < NB / 4; ++j) {
+      if (4 * j < i) {                      // (entries with 4 j + p >= i are not set yet: w[j] == 0 there)
+        const double l = Ls[i][4 * j + p];
+        if (j & 1) a1 = fma(l, w[j], a1); else a0 = fma(l, w[j], a0);
+      }
+    }
+    double sacc = a0 + a1;
+    sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+    sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+    const double wi = (((i == c) ? 1.0 : 0.0) - sacc) / Ls[i][i];
+    if ((i & 3) == p) w[i >> 2] = wi;
+  }
+#pragma unroll
+  for (int j = 0; j < NB / 4; ++j) Wout[(long long)(4 * j + p) * NB + c] = w[j];
+}
+
+// `Winv` (optional): also write inv(L_JJ) (64 x 64 row-major, identity padded) -- the operand of the DMMA panel solve
+// below the block (potrf_panel) and of the prediction solves' diagonal step.
 __global__ void __launch_bounds__(POTF2_THREADS) potf2_64_kernel(double* __restrict__ A, long long ld, int n, int pivot0,
-                                                                 int* __restrict__ info) {
+                                                                 int* __restrict__ info, double* __restrict__ Winv) {
   __shared__ double Ld[2][4][4];     // factored diagonal 4 x 4 block (lower), double-buffered by micro-panel parity
   __shared__ double Rinv[2][4];      // reciprocal pivots of its 4 columns
   __shared__ double P[2][NB][4];     // the finished micro-panel: P[.][r][ja] = L[r][4 jb + ja]
@@ -184,6 +216,18 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_64_kernel(double* __restr
       const int r = ty * 4 + a, c = tx * 4 + b;
       if (r < n && c <= r) A[(long long)r * ld + c] = v[a][b];
     }
+  if (Winv != nullptr) {
+    __shared__ double Ls[NB][NB + 1];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int r = ty * 4 + a, c = tx * 4 + b;
+        Ls[r][c] = (r < n && c <= r) ? v[a][b] : ((r == c) ? 1.0 : 0.0);
+      }
+    __syncthreads();
+    invert_lower_64(Ls, Winv);
+  }
 }
 
 // X * Ljj^T = B in place, for `rows` rows of B (row-major, ldb) and the n x n (n <= 64) lower block
@@ -511,6 +555,25 @@ __global__ void ntk_var_kernel(const double* __restrict__ kss, const double* __r
   double q = 0.0;
   for (int t = 0; t < tiles; ++t) q += partial[(long long)t * rows + r];
   var[r] = kss[r] + q - 2.0 * cross[r];
+}
+
+// latency mode: var[r] = kss[r] - sum_t partial[t][r]   (tiles summed in index order: deterministic)
+__global__ void var_from_partial_kernel(const double* __restrict__ kss, const double* __restrict__ partial, int tiles,
+                                        int rows, double* __restrict__ var) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  double q = 0.0;
+  for (int t = 0; t < tiles; ++t) q += partial[(long long)t * rows + r];
+  var[r] = kss[r] - q;
+}
+
+// A <- I (n x n, leading dimension ld)
+__global__ void set_identity_kernel(double* __restrict__ A, long long ld, int n) {
+  const long long total = (long long)n * ld;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / ld, c = i - r * ld;
+    A[i] = (r == c) ? 1.0 : 0.0;
+  }
 }
 
 // out = in^T for an n x n row-major matrix (both with leading dimension ld); 32 x 32 smem tiles.

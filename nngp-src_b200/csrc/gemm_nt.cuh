@@ -60,8 +60,10 @@ struct GemmParams {
                        //   mean_partial[(2 * tile_n + wn) * M + r] = sum over that warp's 32 columns of K[r][c] alpha[c]
   double* mean_partial;
   // EPI_ROWDOT only: partial[tile_n * M + r] = sum_{c in tile} acc[r][c] * W[r][c]
-  const double* W;     // M x N, leading dimension ldc (reuses ldc)
+  const double* W;     // M x N, leading dimension ldc (reuses ldc); nullptr: W = acc (row sums of squares)
   double* partial;
+  int tri_k;           // 1: B is lower triangular (row j is zero beyond column j): column tile n only needs the k-tiles
+                       //    up to its own last column -- the latency-mode product V = K_* L^-T against the explicit inverse
   uint32_t zero;       // always 0 (value-initialised): opaque run-time zero for mma_mainloop's release dependence
   // EPI_DIAG only (diagonal step of the row-wise triangular solve, see diag_epilogue): C <- A * Winv^T, K = 64
   double* ssq;         // [M] running sum of squares of the solved row (cross-launch carry)
@@ -337,7 +339,10 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   __syncthreads();
 
-  const int ktiles = p.ktiles;
+  int ktiles = p.ktiles;
+  if constexpr (EPI == EPI_ROWDOT) {
+    if (p.tri_k) ktiles = min(ktiles, (tile_n + 1) * (GEMM_BN / GEMM_BK));
+  }
   TileSrc src;
   src.tmA = &tmA; src.tmB = &tmB;
   src.a_col0 = p.a_col0; src.a_row = p.a_row0 + tile_m * GEMM_BM;
@@ -428,7 +433,9 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int ni = 0; ni < 4; ++ni) {
         const int c = col_base_e + 8 * ni;
         double w0 = 0.0, w1 = 0.0;
-        if (r < p.M) {
+        if (p.W == nullptr) {                 // squares: columns beyond N hold exact zeros (zero-filled operand rows)
+          w0 = acc[mi][ni][0]; w1 = acc[mi][ni][1];
+        } else if (r < p.M) {
           const double* src = p.W + (long long)r * p.ldc + c;
           if (c + 1 < p.N) {
             const double2 v = *reinterpret_cast<const double2*>(src);

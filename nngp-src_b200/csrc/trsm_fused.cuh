@@ -48,6 +48,9 @@ struct TrsmFusedParams {
   const double* kss;    // [rows] K(x,x)
   double* var;          // [rows] output; nullptr: plain solve, no variance bookkeeping
   uint32_t zero;        // always 0 (value-initialised): see mma_mainloop's release dependence
+  int upper_start;      // 1: B is upper triangular on entry (the identity, when the fit builds L^-T for latency mode), so
+                        //    V[r, 0:128 r] stays zero: items left of the diagonal are skipped and every k loop starts at
+                        //    column 128 r -- N^3/3 flop instead of N^3
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
@@ -111,14 +114,18 @@ trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
     if (item >= total) break;
     const int J = item / p.row_tiles;
     const int r = item - J * p.row_tiles;
-    const int ktiles = J * (NB / GEMM_BK);
     const int col0 = J * NB;
     const int nb = min(NB, p.N - col0);
     const int row0 = r * GEMM_BM;
+    // upper-triangular right-hand side: nothing to do left of the diagonal, and the k loop starts at the row tile's
+    // own first column (block-uniform branch; a skipped item publishes nothing -- nobody ever waits for it)
+    if (p.upper_start && col0 + NB <= row0) { __syncthreads(); continue; }   // (everyone has read s_item)
+    const int kt0 = p.upper_start ? r * (GEMM_BM / GEMM_BK) : 0;
+    const int ktiles = J * (NB / GEMM_BK) - kt0;
 
     TileSrc src;
     src.tmA = &tmB; src.tmB = &tmL;
-    src.a_col0 = 0; src.a_row = row0; src.b_col0 = 0; src.b_row = col0;
+    src.a_col0 = kt0 * GEMM_BK; src.a_row = row0; src.b_col0 = kt0 * GEMM_BK; src.b_row = col0;
     // The V operand of k-tile kt is column block kt/4 of this row tile, produced by item (r, kt/4): possibly by
     // another CTA, possibly still in flight.  Thread 0 gates every TMA issue on progress[r] > kt/4 (cached: one
     // acquire per newly needed block), so an item starts consuming the blocks that exist instead of waiting for all
@@ -126,7 +133,7 @@ trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
     // Claims are handed out in J-major order, so whatever this CTA waits for is owned by a running CTA.
     int known = 0;   // progress[r] as last seen by thread 0
     auto gate = [&](int kt) {
-      const int need = kt / (NB / GEMM_BK) + 1;
+      const int need = (kt + kt0) / (NB / GEMM_BK) + 1;
       if (known < need) {
         for (unsigned spin = 0; (known = ld_acquire_gpu(p.progress + r)) < need; ++spin) {
           __nanosleep(64);
@@ -137,7 +144,7 @@ trsm_fused_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant
     };
     if (tid == 0) {
       if (!PIPE) {   // one up-front wait for item (r, J-1) (+ proxy fence), then a plain prologue
-        if (J > 0) gate(ktiles - 1);
+        if (ktiles > 0) gate(ktiles - 1);
         ring_prologue<TF_STAGES>(src, ringA, ringB, full_bar, stage, ktiles);
       } else {       // gated prologue: issue what exists, block by block
         const int n0 = ktiles < TF_STAGES ? ktiles : TF_STAGES;
