@@ -257,13 +257,13 @@ struct MatView {  // a whole device matrix a tensor map is built over
 // ---- GEMM launches ----------------------------------------------------------------------------
 template <int EPI>
 int launch_gemm(nngp_handle* h, const MatView& A, int a_row0, int a_col0, const MatView& B, int b_row0, int b_col0,
-                GemmParams p) {
+                GemmParams p, int grid_z = 1) {
   if (p.M <= 0 || p.N <= 0) return NNGP_OK;
   CUtensorMap tmA, tmB;
   CKR(get_tmap(h, A.base, A.rows, A.cols, A.ld, GEMM_BM, &tmA));
   CKR(get_tmap(h, B.base, B.rows, B.cols, B.ld, GEMM_BN, &tmB));
   p.a_row0 = a_row0; p.a_col0 = a_col0; p.b_row0 = b_row0; p.b_col0 = b_col0;
-  dim3 grid((p.N + GEMM_BN - 1) / GEMM_BN, (p.M + GEMM_BM - 1) / GEMM_BM, 1);
+  dim3 grid((p.N + GEMM_BN - 1) / GEMM_BN, (p.M + GEMM_BM - 1) / GEMM_BM, grid_z);
   if (grid.y > 65535) return fail(h, NNGP_EINVAL, "internal: GEMM row range too large (%d rows)", p.M);
   cudaEvent_t ev;
   const int cls = (EPI == EPI_GRAM) ? EV_GRAM : EV_GEMM;  // ROWDOT counts as a GEMM-class launch
@@ -303,7 +303,28 @@ int run_gram(nngp_handle* h, const double* A, int64_t lda, int64_t M, const doub
   MatView a{A, M, D, lda}, b{B, N, D, ldb};
   // the flop counter must use the true D, not the padded k extent
   const double before = h->st.gram_flops;
-  CKR(launch_gemm<EPI_GRAM>(h, a, 0, 0, b, 0, 0, p));
+  static const bool one_tile_per_cta = [] { const char* e = getenv("NNGP_GRAM"); return e && !strcmp(e, "tiles"); }();
+  if (one_tile_per_cta) {
+    CKR(launch_gemm<EPI_GRAM>(h, a, 0, 0, b, 0, 0, p));
+  } else {   // persistent tile loop: the next tile's operands load while this tile's arc-cosine epilogue runs
+    if (M <= 0 || N <= 0) return NNGP_OK;
+    CUtensorMap tmA, tmB;
+    CKR(get_tmap(h, a.base, a.rows, a.cols, a.ld, GEMM_BM, &tmA));
+    CKR(get_tmap(h, b.base, b.rows, b.cols, b.ld, GEMM_BN, &tmB));
+    p.a_row0 = p.a_col0 = p.b_row0 = p.b_col0 = 0;
+    const int64_t tiles_m = (M + GEMM_BM - 1) / GEMM_BM, tiles_n = (N + GEMM_BN - 1) / GEMM_BN;
+    const int64_t ntiles = lower ? tiles_m * (tiles_m + 1) : tiles_m * tiles_n;
+    if (ntiles > 0x7fffffffLL) return fail(h, NNGP_EINVAL, "internal: Gram tile count too large");
+    const int grid = (int)std::min<int64_t>(ntiles, 2LL * h->sm_count);
+    cudaEvent_t ev;
+    class_begin(h, EV_GRAM, &ev);
+    gram_persistent_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->cur>>>(tmA, tmB, p, (int)tiles_n, (int)ntiles);
+    class_end(h, EV_GRAM, ev);
+    CK(cudaGetLastError());
+    h->st.kernel_launches++;
+    h->st.gram_launches++;
+    h->st.gram_evals += (double)M * (double)N * (lower ? 0.5 : 1.0) * p.steps;
+  }
   h->st.gram_flops = before + 2.0 * (double)M * (double)N * (double)D * (lower ? 0.5 : 1.0);
   return NNGP_OK;
 }
@@ -578,15 +599,31 @@ int64_t latency_rows(const nngp_handle* h) {
 int run_inverse_variance(nngp_handle* h, const double* B, int64_t ldb, int64_t rows, const double* kss, double* var) {
   const int64_t N = h->N;
   const int col_tiles = (int)((N + GEMM_BN - 1) / GEMM_BN);
-  CKR(ensure(h, h->partial, (size_t)rows * col_tiles * 8));
   GemmParams p{};
   p.M = (int)rows; p.N = (int)N; p.ktiles = (int)((N + GEMM_BK - 1) / GEMM_BK);
-  p.ldc = ldb; p.W = nullptr; p.partial = h->partial.as<double>(); p.tri_k = 1;
+  p.ldc = ldb; p.W = nullptr; p.tri_k = 1;
   MatView a{B, rows, N, ldb}, b{h->Linvfull.as<double>(), N, N, h->ldl};
-  CKR(launch_gemm<EPI_ROWDOT>(h, a, 0, 0, b, 0, 0, p));
-  // launch_gemm counted 2*M*N*K for the full square; the triangular product is half of it: N^2 flop per row
-  h->st.gemm_flops -= (double)rows * (double)N * (double)p.ktiles * GEMM_BK;
-  var_from_partial_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, h->stream>>>(kss, h->partial.as<double>(), col_tiles, (int)rows, var);
+  const int64_t row_tiles = (rows + GEMM_BM - 1) / GEMM_BM;
+  if (row_tiles * col_tiles < 4LL * h->sm_count) {
+    // Few rows: a column tile near the end of the triangular product is one serial loop of up to N/16 k-tiles on ONE
+    // SM while most of the GPU idles.  Split K into <= 8 chunks (grid z), keep the partial products of the valid rows
+    // (rows x N x chunks doubles) and square / reduce them in a second, fixed-order kernel.
+    int kchunk = 64;
+    while ((p.ktiles + kchunk - 1) / kchunk > 8) kchunk *= 2;
+    const int nz = (p.ktiles + kchunk - 1) / kchunk;
+    CKR(ensure(h, h->partial, (size_t)nz * rows * N * 8));
+    p.kchunk = kchunk; p.vpart = h->partial.as<double>();
+    CKR(launch_gemm<EPI_ROWDOT>(h, a, 0, 0, b, 0, 0, p, nz));
+    h->st.gemm_flops -= (double)rows * (double)N * (double)p.ktiles * GEMM_BK;
+    var_from_split_kernel<<<(unsigned)rows, 256, 0, h->stream>>>(kss, h->partial.as<double>(), (int)rows, (int)N, p.ktiles, kchunk, var);
+  } else {
+    CKR(ensure(h, h->partial, (size_t)rows * col_tiles * 8));
+    p.partial = h->partial.as<double>();
+    CKR(launch_gemm<EPI_ROWDOT>(h, a, 0, 0, b, 0, 0, p));
+    // launch_gemm counted 2*M*N*K for the full square; the triangular product is half of it: N^2 flop per row
+    h->st.gemm_flops -= (double)rows * (double)N * (double)p.ktiles * GEMM_BK;
+    var_from_partial_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, h->stream>>>(kss, h->partial.as<double>(), col_tiles, (int)rows, var);
+  }
   h->st.kernel_launches++;
   CK(cudaGetLastError());
   return NNGP_OK;
@@ -682,7 +719,7 @@ int alloc_state(nngp_handle* h, int64_t N, int64_t D) {
 // inv(L_JJ) for all diagonal blocks of the factor in h->L (after a factorisation or an imported state)
 int run_trtri_diag(nngp_handle* h) {
   const int nblk = (int)((h->N + NB - 1) / NB);
-  trtri_diag_kernel<<<nblk, NB, 0, h->stream>>>(h->L.as<double>(), h->ldl, (int)h->N, h->Linv.as<double>());
+  trtri_diag_kernel<<<nblk, POTF2_THREADS, 0, h->stream>>>(h->L.as<double>(), h->ldl, (int)h->N, h->Linv.as<double>());
   h->st.kernel_launches++;
   CK(cudaGetLastError());
   return NNGP_OK;
@@ -865,6 +902,7 @@ static int create_single(const nngp_config* cfg, nngp_handle** out) {
   }
   h->encode = reinterpret_cast<PFN_encodeTiled>(fn);
   cudaError_t e1 = cudaFuncSetAttribute(gemm_nt_kernel<EPI_GRAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+  if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(gram_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
   cudaError_t e2 = cudaFuncSetAttribute(gemm_nt_kernel<EPI_SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
   if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(gemm_nt_kernel<EPI_ROWDOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
   cudaError_t e3 = cudaFuncSetAttribute(trsm_rows_64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM_BYTES);

@@ -300,30 +300,21 @@ __global__ void __launch_bounds__(TRSM_ROWS) trsm_rows_64_kernel(double* __restr
 }
 
 // W_J = inv(L_JJ) for every 64 x 64 diagonal block of the factor (identity padded when the last block is short):
-// one CTA per block, thread c solves L_JJ w = e_c by forward substitution (column c of the inverse).  Output: row-major
-// 64 x 64 blocks stacked along the rows (block J at rows [64 J, 64 J + 64)), the B operand of the diagonal step of
-// the row-wise triangular solves (trsm_fused.cuh / gemm_nt_kernel<EPI_DIAG>).  Runs once per fit; N/64 tiny CTAs.
-__global__ void __launch_bounds__(NB) trtri_diag_kernel(const double* __restrict__ L, long long ldl, int N,
-                                                        double* __restrict__ Winv) {
+// one CTA per block, the SAME routine (invert_lower_64) the factorisation's potf2_64_kernel runs on the block it has
+// just factored -- so a state that was imported (nngp_set_state / nngp_state_import_end) predicts with bitwise the
+// inverses of the handle that fitted it.  Output: row-major 64 x 64 blocks stacked along the rows (block J at rows
+// [64 J, 64 J + 64)), the B operand of the diagonal step of the row-wise triangular solves.
+__global__ void __launch_bounds__(POTF2_THREADS) trtri_diag_kernel(const double* __restrict__ L, long long ldl, int N,
+                                                                   double* __restrict__ Winv) {
   __shared__ double Ls[NB][NB + 1];
   const int J = blockIdx.x;
   const int j0 = J * NB;
   const int n = min(NB, N - j0);
-  const int c = threadIdx.x;
-  for (int r = 0; r < NB; ++r)
+  const int c = threadIdx.x & 63, rsub = threadIdx.x >> 6;
+  for (int r = rsub; r < NB; r += 4)
     Ls[r][c] = (r < n && c <= r) ? L[(long long)(j0 + r) * ldl + j0 + c] : ((r == c) ? 1.0 : 0.0);
   __syncthreads();
-  double w[NB];
-#pragma unroll
-  for (int i = 0; i < NB; ++i) {
-    double sacc = (i == c) ? 1.0 : 0.0;
-#pragma unroll
-    for (int k = 0; k < i; ++k) sacc = fma(-Ls[i][k], w[k], sacc);
-    w[i] = (i >= c) ? sacc / Ls[i][i] : 0.0;
-  }
-  double* out = Winv + (long long)j0 * NB;
-#pragma unroll
-  for (int i = 0; i < NB; ++i) out[(long long)i * NB + c] = w[i];
+  invert_lower_64(Ls, Winv + (long long)j0 * NB);
 }
 
 // Shared helper: load the n x n lower block Ljj into Ls (identity padded), 8 loads in flight per thread,
@@ -565,6 +556,31 @@ __global__ void var_from_partial_kernel(const double* __restrict__ kss, const do
   double q = 0.0;
   for (int t = 0; t < tiles; ++t) q += partial[(long long)t * rows + r];
   var[r] = kss[r] - q;
+}
+
+// latency mode, split-K variant (few rows): var[r] = kss[r] - sum_c ( sum_z vpart[z][r][c] )^2, one CTA per row.
+// Column c lies in column tile c / 64, whose triangular product spans 4 (c / 64 + 1) k-tiles, i.e.
+// ceil(that / kchunk) chunks were written.  Fixed summation order: deterministic.
+__global__ void __launch_bounds__(256) var_from_split_kernel(const double* __restrict__ kss, const double* __restrict__ vpart,
+                                                             int rows, int N, int ktiles_total, int kchunk,
+                                                             double* __restrict__ var) {
+  __shared__ double red[256];
+  const int r = blockIdx.x;
+  double sacc = 0.0;
+  for (int c = threadIdx.x; c < N; c += 256) {
+    const int kt = min(ktiles_total, (c / 64 + 1) * 4);
+    const int nz = (kt + kchunk - 1) / kchunk;
+    double v = 0.0;
+    for (int z = 0; z < nz; ++z) v += vpart[((long long)z * rows + r) * N + c];
+    sacc = fma(v, v, sacc);
+  }
+  red[threadIdx.x] = sacc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) var[r] = kss[r] - red[0];
 }
 
 // A <- I (n x n, leading dimension ld)

@@ -62,6 +62,9 @@ struct GemmParams {
   // EPI_ROWDOT only: partial[tile_n * M + r] = sum_{c in tile} acc[r][c] * W[r][c]
   const double* W;     // M x N, leading dimension ldc (reuses ldc); nullptr: W = acc (row sums of squares)
   double* partial;
+  int kchunk;          // > 0: split-K over blockIdx.z in chunks of kchunk k-tiles; the epilogue then stores the partial
+  double* vpart;       //      products to vpart[(z * M + r) * N + c] instead of reducing them (few-row batches: the
+                       //      column tiles near the end of a triangular product would otherwise be one long serial loop)
   int tri_k;           // 1: B is lower triangular (row j is zero beyond column j): column tile n only needs the k-tiles
                        //    up to its own last column -- the latency-mode product V = K_* L^-T against the explicit inverse
   uint32_t zero;       // always 0 (value-initialised): opaque run-time zero for mma_mainloop's release dependence
@@ -121,12 +124,24 @@ __device__ __forceinline__ void diag_epilogue(const double (&acc)[4][4][2], cons
   }
 }
 
-// theta = atan2(s, k) for s >= 0 (theta in [0, pi]), pi/2 at s == k == 0 [nt: _arctan2(fill_zero = pi/2)].
-// One division + a degree-20 polynomial: atan(t) = t P(t^2) on t = min(s,|k|)/max(s,|k|) in [0,1] (interpolant of
-// atan(sqrt u)/sqrt u at the Chebyshev nodes, fitted in 40-digit mpmath; FP64 Horner error <= 2.3e-16 relative,
-// i.e. the same <= 1 ulp as libm's atan2 against a 40-digit reference -- tests/test_oracle.py checks the identical
-// algorithm in numpy).  About half the FP64 instructions of libdevice's sqrt + atan2 pair in this epilogue.
-__device__ __forceinline__ double atan2_pos(double s, double k) {
+// theta = atan2(s, k) for s = sqrt(s2) >= 0 (theta in [0, pi]), pi/2 at s == k == 0 [nt: _arctan2(fill_zero = pi/2)].
+// atan(t) = t P(t^2) on t = min(s,|k|)/max(s,|k|) in [0,1], P of degree 20 (interpolant of atan(sqrt u)/sqrt u at the
+// Chebyshev nodes, fitted in 40-digit mpmath; FP64 evaluation error <= 2.3e-16 relative).  Two things keep the FP64
+// pipe -- which this epilogue shares with the co-resident CTA's DMMAs -- and the dependency chain short:
+//   * no division:  min/max = s |k| / max(s^2, k^2);  the reciprocal of max(s^2, k^2) (MUFU.RCP64H seed + two Newton
+//     steps, 1 ulp) does not depend on the square root, so the two run side by side instead of back to back;
+//   * P is evaluated as  Pe(w) + u Po(w),  w = u^2: two independent Horner chains of 10 instead of one of 20.
+// Total error of theta <= 2 ulp (tests/test_oracle.py restates the identical algorithm in numpy against mpmath).
+__device__ __forceinline__ double rcp_newton(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));   // ~20 good bits
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+
+__device__ __forceinline__ double atan2_pos(double s, double s2, double k) {
   constexpr double C[21] = {
     1.0,
     -0.3333333333333286,
@@ -152,16 +167,20 @@ __device__ __forceinline__ double atan2_pos(double s, double k) {
   const double half_pi = 1.57079632679489661923;
   const double pi = 3.14159265358979323846;
   const double a = fabs(k);
-  const double mx = fmax(s, a), mn = fmin(s, a);
-  const double t = mn / mx;
+  const double a2 = k * k;
+  const double mx2 = fmax(s2, a2);
+  const double t = (s * a) * rcp_newton(mx2);
   const double u = t * t;
-  double p = C[20];
+  const double w = u * u;
+  double pe = C[20], po = C[19];
 #pragma unroll
-  for (int i = 19; i >= 0; --i) p = fma(p, u, C[i]);
-  const double at = t * p;
-  const double th0 = (s > a) ? (half_pi - at) : at;
+  for (int i = 18; i >= 0; i -= 2) pe = fma(pe, w, C[i]);
+#pragma unroll
+  for (int i = 17; i >= 1; i -= 2) po = fma(po, w, C[i]);
+  const double at = t * fma(u, po, pe);
+  const double th0 = (s2 > a2) ? (half_pi - at) : at;
   const double th = (k < 0.0) ? (pi - th0) : th0;
-  return (mx == 0.0) ? half_pi : th;
+  return (mx2 == 0.0) ? half_pi : th;
 }
 
 // One ReLU arc-cosine step followed by the next Dense layer's affine map
@@ -170,9 +189,9 @@ __device__ __forceinline__ double atan2_pos(double s, double k) {
 //   k' = sw2 * ( s/(2 pi) + (1/2 - theta/(2 pi)) k ) + sb2
 __device__ __forceinline__ double arccos_step(double k, double q1, double q2, double sw2, double sb2) {
   const double inv_2pi = 0.15915494309189533577;
-  double s2 = q1 * q2 - k * k;
-  double s = sqrt(fmax(s2, 0.0));
-  double theta = atan2_pos(s, k);
+  double s2 = fmax(q1 * q2 - k * k, 0.0);
+  double s = sqrt(s2);
+  double theta = atan2_pos(s, s2, k);
   double dot_sigma = 0.5 - inv_2pi * theta;
   double r = inv_2pi * s + dot_sigma * k;
   return sw2 * r + sb2;
@@ -183,9 +202,9 @@ __device__ __forceinline__ double arccos_step(double k, double q1, double q2, do
 // ([nt: Relu `ntk *= dot_sigma`, Dense `ntk = nngp + W_std^2 * ntk`]).
 __device__ __forceinline__ void arccos_step_ntk(double& k, double& ntk, double q1, double q2, double sw2, double sb2) {
   const double inv_2pi = 0.15915494309189533577;
-  double s2 = q1 * q2 - k * k;
-  double s = sqrt(fmax(s2, 0.0));
-  double theta = atan2_pos(s, k);
+  double s2 = fmax(q1 * q2 - k * k, 0.0);
+  double s = sqrt(s2);
+  double theta = atan2_pos(s, s2, k);
   double dot_sigma = 0.5 - inv_2pi * theta;
   double r = inv_2pi * s + dot_sigma * k;
   k = sw2 * r + sb2;
@@ -234,6 +253,14 @@ __device__ __forceinline__ void ring_prologue(const TileSrc& src, uint8_t* ringA
 struct NoGate {  // default refill gate: operand tiles are always ready to be loaded
   __device__ __forceinline__ void operator()(int) const {}
 };
+// Persistent kernels: the tile this CTA works on next.  When `valid`, the stages released by the last STAGES k-tiles
+// of the current tile are refilled with the FIRST k-tiles of the next one, so its operands are in flight while this
+// tile's epilogue runs (the next mma_mainloop call is then told that its prologue has been issued).
+struct NextTile {
+  bool valid = false;
+  TileSrc src;
+  int ktiles = 0;
+};
 // `gate(kt)` is called by thread 0 right before it issues the TMA loads of k-tile kt (refills only; the caller
 // gates its own prologue): the persistent solve uses it to wait until the producer of that k-tile's A operand
 // (another CTA) has published it.  `active == false` (warp-uniform): this warp's 32-row slab lies entirely beyond
@@ -243,7 +270,7 @@ template <int STAGES, class Gate = NoGate>
 __device__ __forceinline__ void mma_mainloop(double (&acc)[4][4][2], const TileSrc& src, uint8_t* ringA, uint8_t* ringB,
                                              uint64_t* full_bar, uint64_t* empty_bar, int& stage, uint32_t& phase,
                                              int ktiles, int wm, int wn, int lane, uint32_t zero, Gate gate = Gate(),
-                                             bool active = true) {
+                                             bool active = true, const NextTile* next = nullptr) {
   const int g = lane >> 2, t = lane & 3;
   // Which k does lane (g, t) feed into DMMA step s?  Any bijection (s, t) -> 0..15 is a valid GEMM as long as the A
   // and the B fragment use the same one.  We use  k = 8*(t>>1) + 2*s + (t&1):  logical 16-byte chunk 4*(t>>1) + s,
@@ -262,10 +289,15 @@ __device__ __forceinline__ void mma_mainloop(double (&acc)[4][4][2], const TileS
   auto release = [&](int s, uint32_t ph, uint32_t seen, int kdone) {
     __syncwarp();
     if (lane == 0) mbar_arrive_addr(smem_u32(&empty_bar[s]) + (seen & zero));
-    if (threadIdx.x == 0 && kdone + STAGES < ktiles) {
-      mbar_wait(&empty_bar[s], ph);  // all 8 warps are done with this stage in this round
-      gate(kdone + STAGES);
-      ring_issue<STAGES>(src, ringA, ringB, full_bar, s, kdone + STAGES);
+    if (threadIdx.x == 0) {
+      if (kdone + STAGES < ktiles) {
+        mbar_wait(&empty_bar[s], ph);  // all 8 warps are done with this stage in this round
+        gate(kdone + STAGES);
+        ring_issue<STAGES>(src, ringA, ringB, full_bar, s, kdone + STAGES);
+      } else if (next != nullptr && next->valid && kdone + STAGES - ktiles < next->ktiles) {
+        mbar_wait(&empty_bar[s], ph);
+        ring_issue<STAGES>(next->src, ringA, ringB, full_bar, s, kdone + STAGES - ktiles);
+      }
     }
     __syncwarp();
   };
@@ -305,6 +337,95 @@ __device__ __forceinline__ void mma_mainloop(double (&acc)[4][4][2], const TileS
   if (NNGP_RELEASE_AT < 4 && ktiles > 0) release(stage == 0 ? STAGES - 1 : stage - 1, stage == 0 ? phase ^ 1u : phase, seen_prev, ktiles - 1);
 }
 
+// Gram epilogue (K1 + K2 + K3 (+ K8)): k = scale * acc + sb2, depth-1 arc-cosine steps in registers, store, and
+// (optionally) the fused posterior-mean GEMV partial of this warp's 32 columns.  Shared by the one-tile-per-CTA
+// kernel and the persistent kernel.
+#ifndef NNGP_GRAM_ILP
+#define NNGP_GRAM_ILP 4   // entries advanced through the layers together (2, 4 or 8): independent dependency chains
+#endif                    // (sqrt, reciprocal, two Horner halves each) for the scheduler to interleave; 8 spills
+__device__ __forceinline__ void gram_epilogue(const double (&acc)[4][4][2], const GemmParams& p, int tile_n, int row_base,
+                                              int col_base, int wn, int t) {
+  constexpr int W = NNGP_GRAM_ILP;          // entries per group
+  constexpr int NG = W / 2;                 // fragments (ni) per group
+  double msum[4] = {0.0, 0.0, 0.0, 0.0};  // fused GEMV partial sums (this thread's 8 columns of 4 rows)
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi) {
+    const int r = row_base + 8 * mi;
+    if (r < p.M) {
+      const double q1r = p.q1[r];
+#pragma unroll
+      for (int n0 = 0; n0 < 4; n0 += NG) {
+        double k[W], qb[W];
+#pragma unroll
+        for (int j = 0; j < NG; ++j) {
+          const int c = col_base + 8 * (n0 + j);
+          k[2 * j] = p.scale * acc[mi][n0 + j][0] + p.sb2;
+          k[2 * j + 1] = p.scale * acc[mi][n0 + j][1] + p.sb2;
+          qb[2 * j] = (c < p.N) ? __ldg(p.q2 + c) : 0.0;          // re-read per row (L1 hit): keeps registers free
+          qb[2 * j + 1] = (c + 1 < p.N) ? __ldg(p.q2 + c + 1) : 0.0;
+        }
+        double qa = q1r;
+        if (!p.ntk) {
+          for (int s = 0; s < p.steps; ++s) {
+#pragma unroll
+            for (int j = 0; j < W; ++j) {
+              k[j] = arccos_step(k[j], qa, qb[j], p.sw2, p.sb2);
+              qb[j] = p.sw2 * (0.5 * qb[j]) + p.sb2;
+            }
+            qa = p.sw2 * (0.5 * qa) + p.sb2;
+          }
+        } else {
+          double n[W];
+#pragma unroll
+          for (int j = 0; j < W; ++j) n[j] = k[j];
+          for (int s = 0; s < p.steps; ++s) {
+#pragma unroll
+            for (int j = 0; j < W; ++j) {
+              arccos_step_ntk(k[j], n[j], qa, qb[j], p.sw2, p.sb2);
+              qb[j] = p.sw2 * (0.5 * qb[j]) + p.sb2;
+            }
+            qa = p.sw2 * (0.5 * qa) + p.sb2;
+          }
+          if (p.C2) {
+#pragma unroll
+            for (int j = 0; j < NG; ++j) {
+              const int c = col_base + 8 * (n0 + j);
+              double* dst2 = p.C2 + (long long)r * p.ldc + c;
+              if (c + 1 < p.N) *reinterpret_cast<double2*>(dst2) = make_double2(k[2 * j], k[2 * j + 1]);
+              else if (c < p.N) dst2[0] = k[2 * j];
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < W; ++j) k[j] = n[j];
+        }
+#pragma unroll
+        for (int j = 0; j < NG; ++j) {
+          const int c = col_base + 8 * (n0 + j);
+          double* dst = p.C + (long long)r * p.ldc + c;
+          if (c + 1 < p.N) {
+            *reinterpret_cast<double2*>(dst) = make_double2(k[2 * j], k[2 * j + 1]);
+          } else if (c < p.N) {
+            dst[0] = k[2 * j];
+          }
+          if (p.alpha != nullptr) {  // K_* alpha (Theta_* alpha in NTK mode), columns in ascending order
+            if (c < p.N) msum[mi] = fma(k[2 * j], __ldg(p.alpha + c), msum[mi]);
+            if (c + 1 < p.N) msum[mi] = fma(k[2 * j + 1], __ldg(p.alpha + c + 1), msum[mi]);
+          }
+        }
+      }
+    }
+  }
+  if (p.alpha != nullptr) {  // fixed-order reduction inside the quad, then one partial per (tile, warp column)
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+      msum[mi] += __shfl_xor_sync(0xffffffffu, msum[mi], 1);
+      msum[mi] += __shfl_xor_sync(0xffffffffu, msum[mi], 2);
+      const int r = row_base + 8 * mi;
+      if (t == 0 && r < p.M) p.mean_partial[(long long)(2 * tile_n + wn) * p.M + r] = msum[mi];
+    }
+  }
+}
+
 #ifndef NNGP_GEMM_MINBLOCKS
 #define NNGP_GEMM_MINBLOCKS 2
 #endif
@@ -340,13 +461,19 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
 
   int ktiles = p.ktiles;
+  int k0 = 0;
   if constexpr (EPI == EPI_ROWDOT) {
     if (p.tri_k) ktiles = min(ktiles, (tile_n + 1) * (GEMM_BN / GEMM_BK));
+    if (p.kchunk > 0) {                       // split-K: this CTA owns k-tiles [k0, k0 + ktiles)
+      k0 = (int)blockIdx.z * p.kchunk;
+      if (k0 >= ktiles) return;               // (before any barrier: the whole CTA leaves)
+      ktiles = min(p.kchunk, ktiles - k0);
+    }
   }
   TileSrc src;
   src.tmA = &tmA; src.tmB = &tmB;
-  src.a_col0 = p.a_col0; src.a_row = p.a_row0 + tile_m * GEMM_BM;
-  src.b_col0 = p.b_col0; src.b_row = p.b_row0 + tile_n * GEMM_BN;
+  src.a_col0 = p.a_col0 + k0 * GEMM_BK; src.a_row = p.a_row0 + tile_m * GEMM_BM;
+  src.b_col0 = p.b_col0 + k0 * GEMM_BK; src.b_row = p.b_row0 + tile_n * GEMM_BN;
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -423,6 +550,21 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     o.B = p.C; o.ldb = p.ldc; o.rows = p.M; o.ssq = p.ssq; o.kss = p.kss; o.var = p.var; o.J = p.J; o.col_blocks = p.col_blocks;
     diag_epilogue(acc, o, tile_m * GEMM_BM, p.N, wm, wn, g, t, reinterpret_cast<double*>(ringA));
   } else if constexpr (EPI == EPI_ROWDOT) {
+    if (p.kchunk > 0) {   // split-K: hand the partial products to the reduction kernel
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) {
+        const int r = row_base_e + 8 * mi;
+        if (r >= p.M) continue;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+          const int c = col_base_e + 8 * ni;
+          double* dst = p.vpart + ((long long)blockIdx.z * p.M + r) * p.N + c;
+          if (c < p.N) dst[0] = acc[mi][ni][0];
+          if (c + 1 < p.N) dst[1] = acc[mi][ni][1];
+        }
+      }
+      return;
+    }
     // quad[r] contribution of this 64-column tile: sum_c acc[r][c] * W[r][c]  (fixed order => deterministic)
     double part[4];
 #pragma unroll
@@ -463,66 +605,95 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (r < p.M) p.partial[(long long)tile_n * p.M + r] = red[threadIdx.x] + red[GEMM_BM + threadIdx.x];
     }
   } else {
-    double msum[4] = {0.0, 0.0, 0.0, 0.0};  // fused GEMV partial sums (this thread's 8 columns of 4 rows)
+    gram_epilogue(acc, p, tile_n, row_base_e, col_base_e, wn, t);
+  }
+}
+
+// Persistent Gram kernel: one CTA per slot (2 per SM) walks the output tiles  idx = blockIdx.x, + gridDim.x, ...
+// (row-major over (tile_m, tile_n); only the tiles at or below the diagonal when p.lower).  While a tile's
+// arc-cosine epilogue runs on the FP64 pipe, the TMA loads of the CTA's NEXT tile are already in flight: the ring
+// stages released by the last k-tiles of a tile are refilled with the first k-tiles of the next one (NextTile), so a
+// tile neither pays a launch / barrier-init / pipeline-fill bubble nor leaves the copy engine idle during the
+// epilogue.  With D = 128 a tile is only 8 k-tiles: in the one-tile-per-CTA kernel that bubble is a third of the tile.
+__device__ __forceinline__ void gram_tile_coords(const GemmParams& p, int tiles_n, int idx, int& tile_m, int& tile_n) {
+  if (!p.lower) {
+    tile_m = idx / tiles_n;
+    tile_n = idx - tile_m * tiles_n;
+  } else {   // row tile m holds the column tiles 0 .. min(2 m + 1, tiles_n - 1): m (m + 1) tiles lie above it
+    int m = (int)((sqrt(4.0 * (double)idx + 1.0) - 1.0) * 0.5);
+    while (m * (m + 1) > idx) --m;
+    while ((m + 1) * (m + 2) <= idx) ++m;
+    tile_m = m;
+    tile_n = idx - m * (m + 1);
+  }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, NNGP_GEMM_MINBLOCKS)
+gram_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const GemmParams p, int tiles_n, int ntiles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+  uint8_t* ring = smem_raw + pad;
+  uint8_t* ringA = ring;
+  uint8_t* ringB = ring + GEMM_STAGES * GEMM_A_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ringB + GEMM_STAGES * GEMM_B_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + GEMM_STAGES;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
 #pragma unroll
-    for (int mi = 0; mi < 4; ++mi) {
-      const int r = row_base_e + 8 * mi;
-      if (r < p.M) {
-        const double q1r = p.q1[r];
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-          const int c = col_base_e + 8 * ni;
-          double k0 = p.scale * acc[mi][ni][0] + p.sb2;
-          double k1 = p.scale * acc[mi][ni][1] + p.sb2;
-          double qa = q1r;
-          double qb0 = (c < p.N) ? __ldg(p.q2 + c) : 0.0;          // re-read per fragment (L1 hit): keeps 16 registers free
-          double qb1 = (c + 1 < p.N) ? __ldg(p.q2 + c + 1) : 0.0;
-          double* dst = p.C + (long long)r * p.ldc + c;
-          if (!p.ntk) {
-            for (int s = 0; s < p.steps; ++s) {
-              k0 = arccos_step(k0, qa, qb0, p.sw2, p.sb2);
-              k1 = arccos_step(k1, qa, qb1, p.sw2, p.sb2);
-              qa = p.sw2 * (0.5 * qa) + p.sb2;
-              qb0 = p.sw2 * (0.5 * qb0) + p.sb2;
-              qb1 = p.sw2 * (0.5 * qb1) + p.sb2;
-            }
-          } else {
-            double n0 = k0, n1 = k1;
-            for (int s = 0; s < p.steps; ++s) {
-              arccos_step_ntk(k0, n0, qa, qb0, p.sw2, p.sb2);
-              arccos_step_ntk(k1, n1, qa, qb1, p.sw2, p.sb2);
-              qa = p.sw2 * (0.5 * qa) + p.sb2;
-              qb0 = p.sw2 * (0.5 * qb0) + p.sb2;
-              qb1 = p.sw2 * (0.5 * qb1) + p.sb2;
-            }
-            if (p.C2) {
-              double* dst2 = p.C2 + (long long)r * p.ldc + c;
-              if (c + 1 < p.N) *reinterpret_cast<double2*>(dst2) = make_double2(k0, k1);
-              else if (c < p.N) dst2[0] = k0;
-            }
-            k0 = n0; k1 = n1;
-          }
-          if (c + 1 < p.N) {
-            *reinterpret_cast<double2*>(dst) = make_double2(k0, k1);
-          } else if (c < p.N) {
-            dst[0] = k0;
-          }
-          if (p.alpha != nullptr) {  // K_* alpha (Theta_* alpha in NTK mode), columns in ascending order
-            if (c < p.N) msum[mi] = fma(k0, __ldg(p.alpha + c), msum[mi]);
-            if (c + 1 < p.N) msum[mi] = fma(k1, __ldg(p.alpha + c + 1), msum[mi]);
-          }
-        }
-      }
+    for (int s = 0; s < GEMM_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], GEMM_CONSUMER_WARPS);
     }
-    if (p.alpha != nullptr) {  // fixed-order reduction inside the quad, then one partial per (tile, warp column)
-#pragma unroll
-      for (int mi = 0; mi < 4; ++mi) {
-        msum[mi] += __shfl_xor_sync(0xffffffffu, msum[mi], 1);
-        msum[mi] += __shfl_xor_sync(0xffffffffu, msum[mi], 2);
-        const int r = row_base_e + 8 * mi;
-        if (t == 0 && r < p.M) p.mean_partial[(long long)(2 * tile_n + wn) * p.M + r] = msum[mi];
-      }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  __syncthreads();
+  const int ktiles = p.ktiles;
+  const int wm = warp >> 1, wn = warp & 1;
+  const int g = lane >> 2, t = lane & 3;
+  int idx = blockIdx.x;
+  if (idx >= ntiles) return;
+  int tile_m, tile_n;
+  gram_tile_coords(p, tiles_n, idx, tile_m, tile_n);
+  TileSrc src;
+  src.tmA = &tmA; src.tmB = &tmB;
+  src.a_col0 = p.a_col0; src.a_row = p.a_row0 + tile_m * GEMM_BM;
+  src.b_col0 = p.b_col0; src.b_row = p.b_row0 + tile_n * GEMM_BN;
+  int stage = 0;
+  uint32_t phase = 0;
+  if (threadIdx.x == 0) ring_prologue<GEMM_STAGES>(src, ringA, ringB, full_bar, stage, ktiles);
+  const bool chain = ktiles >= GEMM_STAGES;   // fewer k-tiles than stages: plain per-tile prologue (tiny D)
+  for (;;) {
+    NextTile next;
+    const int idx2 = idx + (int)gridDim.x;
+    int tm2 = 0, tn2 = 0;
+    if (idx2 < ntiles) {
+      gram_tile_coords(p, tiles_n, idx2, tm2, tn2);
+      next.valid = chain;
+      next.src = src;
+      next.src.a_row = p.a_row0 + tm2 * GEMM_BM;
+      next.src.b_row = p.b_row0 + tn2 * GEMM_BN;
+      next.ktiles = ktiles;
     }
+    double acc[4][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+    mma_mainloop<GEMM_STAGES>(acc, src, ringA, ringB, full_bar, empty_bar, stage, phase, ktiles, wm, wn, lane, p.zero,
+                              NoGate(), true, &next);
+    gram_epilogue(acc, p, tile_n, tile_m * GEMM_BM + wm * 32 + g, tile_n * GEMM_BN + wn * 32 + 2 * t, wn, t);
+    if (idx2 >= ntiles) break;
+    if (!chain) {
+      __syncthreads();   // every warp has left the ring
+      if (threadIdx.x == 0) ring_prologue<GEMM_STAGES>(next.src, ringA, ringB, full_bar, stage, ktiles);
+    }
+    idx = idx2; tile_m = tm2; tile_n = tn2;
+    src = next.src;
   }
 }
 
