@@ -5,7 +5,7 @@ set -euo pipefail
 here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 PY="${PYTHON:-python3}"
-out="$here/libnngp_b200.so"
+out="${OUT:-$here/libnngp_b200.so}"
 id="$("$PY" "$here/nngp_b200/_build.py" --hash)"
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
   -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -Xcompiler -pthread -shared -cudart static \

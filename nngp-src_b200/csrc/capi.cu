@@ -303,28 +303,7 @@ int run_gram(nngp_handle* h, const double* A, int64_t lda, int64_t M, const doub
   MatView a{A, M, D, lda}, b{B, N, D, ldb};
   // the flop counter must use the true D, not the padded k extent
   const double before = h->st.gram_flops;
-  static const bool one_tile_per_cta = [] { const char* e = getenv("NNGP_GRAM"); return e && !strcmp(e, "tiles"); }();
-  if (one_tile_per_cta) {
-    CKR(launch_gemm<EPI_GRAM>(h, a, 0, 0, b, 0, 0, p));
-  } else {   // persistent tile loop: the next tile's operands load while this tile's arc-cosine epilogue runs
-    if (M <= 0 || N <= 0) return NNGP_OK;
-    CUtensorMap tmA, tmB;
-    CKR(get_tmap(h, a.base, a.rows, a.cols, a.ld, GEMM_BM, &tmA));
-    CKR(get_tmap(h, b.base, b.rows, b.cols, b.ld, GEMM_BN, &tmB));
-    p.a_row0 = p.a_col0 = p.b_row0 = p.b_col0 = 0;
-    const int64_t tiles_m = (M + GEMM_BM - 1) / GEMM_BM, tiles_n = (N + GEMM_BN - 1) / GEMM_BN;
-    const int64_t ntiles = lower ? tiles_m * (tiles_m + 1) : tiles_m * tiles_n;
-    if (ntiles > 0x7fffffffLL) return fail(h, NNGP_EINVAL, "internal: Gram tile count too large");
-    const int grid = (int)std::min<int64_t>(ntiles, 2LL * h->sm_count);
-    cudaEvent_t ev;
-    class_begin(h, EV_GRAM, &ev);
-    gram_persistent_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->cur>>>(tmA, tmB, p, (int)tiles_n, (int)ntiles);
-    class_end(h, EV_GRAM, ev);
-    CK(cudaGetLastError());
-    h->st.kernel_launches++;
-    h->st.gram_launches++;
-    h->st.gram_evals += (double)M * (double)N * (lower ? 0.5 : 1.0) * p.steps;
-  }
+  CKR(launch_gemm<EPI_GRAM>(h, a, 0, 0, b, 0, 0, p));
   h->st.gram_flops = before + 2.0 * (double)M * (double)N * (double)D * (lower ? 0.5 : 1.0);
   return NNGP_OK;
 }
@@ -902,7 +881,6 @@ static int create_single(const nngp_config* cfg, nngp_handle** out) {
   }
   h->encode = reinterpret_cast<PFN_encodeTiled>(fn);
   cudaError_t e1 = cudaFuncSetAttribute(gemm_nt_kernel<EPI_GRAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
-  if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(gram_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
   cudaError_t e2 = cudaFuncSetAttribute(gemm_nt_kernel<EPI_SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
   if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(gemm_nt_kernel<EPI_ROWDOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
   cudaError_t e3 = cudaFuncSetAttribute(trsm_rows_64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM_BYTES);

@@ -86,39 +86,67 @@ __global__ void diag_reg_kernel(double* __restrict__ K, long long ld, int N, dou
 // factor is bitwise that of the one-column-per-step version this replaces (34 us -> 10 us per block).
 // On a non-positive pivot: *info = global pivot index + 1 (first failure wins), block left as is.
 constexpr int POTF2_THREADS = 256;
-// Inverse of the lower-triangular 64 x 64 block in Ls (identity padded), by all 256 threads of the CTA: column c of
-// W = L^-1 is the forward substitution L w = e_c; four adjacent lanes share a column (lane part p owns w[i], i = p mod 4,
-// in registers) and split every dot product  sum_{k<i} L[i][k] w[k]  four ways, joined by two shuffles -- 64 dependent
-// steps of ~4 FMAs + 2 shuffles instead of the 2016-FMA chain of one thread per column.  Output: row-major 64 x 64.
-__device__ __forceinline__ void invert_lower_64(const double (*Ls)[NB + 1], double* __restrict__ Wout) {
+// In-place inverse of the lower-triangular 64 x 64 block in Ls (identity padded), by all 256 threads of the CTA, as a
+// recursive block inversion:  inv [[A, 0], [B, C]] = [[A^-1, 0], [-C^-1 B A^-1, C^-1]].  Level 0 inverts the sixteen
+// 4 x 4 diagonal blocks (one thread each); levels m = 4, 8, 16, 32 fill the off-diagonal m x m blocks of every
+// 2m x 2m diagonal super-block with two small products (T = B A^-1 into the scratch `T`, then -C^-1 T over B: the
+// region that held B is exactly where the result belongs, so no second matrix is needed).  9 barriers and ~350
+// multiply-adds per thread -- ~2 us, where a column-wise forward substitution is a 64-step chain of divisions and
+// shuffles (~20 us measured, on the critical path of the Cholesky panel chain).  `T`: 1024 doubles.
+// The same routine serves the factorisation (potf2_64_kernel) and imported states (trtri_diag_kernel): same bits.
+__device__ __forceinline__ void invert_lower_64_inplace(double (*Ls)[NB + 1], double* __restrict__ T) {
   const int tid = threadIdx.x;
-  const int c = tid >> 2, p = tid & 3;
-  double w[NB / 4];
-#pragma unroll
-  for (int j = 0; j < NB / 4; ++j) w[j] = 0.0;
-#pragma unroll
-  for (int i = 0; i < NB; ++i) {
-    double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-    for (int j = 0; j < NB / 4; ++j) {
-      if (4 * j < i) {                      // (entries with 4 j + p >= i are not set yet: w[j] == 0 there)
-        const double l = Ls[i][4 * j + p];
-        if (j & 1) a1 = fma(l, w[j], a1); else a0 = fma(l, w[j], a0);
-      }
-    }
-    double sacc = a0 + a1;
-    sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
-    sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
-    const double wi = (((i == c) ? 1.0 : 0.0) - sacc) / Ls[i][i];
-    if ((i & 3) == p) w[i >> 2] = wi;
+  if (tid < NB / 4) {
+    const int o = 4 * tid;
+    const double l10 = Ls[o + 1][o], l20 = Ls[o + 2][o], l21 = Ls[o + 2][o + 1];
+    const double l30 = Ls[o + 3][o], l31 = Ls[o + 3][o + 1], l32 = Ls[o + 3][o + 2];
+    const double r0 = 1.0 / Ls[o][o], r1 = 1.0 / Ls[o + 1][o + 1], r2 = 1.0 / Ls[o + 2][o + 2], r3 = 1.0 / Ls[o + 3][o + 3];
+    const double w10 = -(l10 * r0) * r1;
+    const double w21 = -(l21 * r1) * r2;
+    const double w32 = -(l32 * r2) * r3;
+    const double w20 = -fma(l21, w10, l20 * r0) * r2;
+    const double w31 = -fma(l32, w21, l31 * r1) * r3;
+    const double w30 = -fma(l32, w20, fma(l31, w10, l30 * r0)) * r3;
+    Ls[o][o] = r0; Ls[o + 1][o + 1] = r1; Ls[o + 2][o + 2] = r2; Ls[o + 3][o + 3] = r3;
+    Ls[o + 1][o] = w10; Ls[o + 2][o] = w20; Ls[o + 2][o + 1] = w21;
+    Ls[o + 3][o] = w30; Ls[o + 3][o + 1] = w31; Ls[o + 3][o + 2] = w32;
   }
-#pragma unroll
-  for (int j = 0; j < NB / 4; ++j) Wout[(long long)(4 * j + p) * NB + c] = w[j];
+  __syncthreads();
+  for (int m = 4; m < NB; m *= 2) {
+    const int mm = m * m, elems = (NB / (2 * m)) * mm;      // = 32 m outputs per product
+    // T = B A^-1:  T[i][j] = sum_{k >= j} B[i][k] Ainv[k][j]   (A^-1 is lower triangular)
+    for (int e = tid; e < elems; e += blockDim.x) {
+      const int pr = e / mm, ij = e - pr * mm, i = ij / m, j = ij - i * m;
+      const int a0 = pr * 2 * m, c0 = a0 + m;
+      double acc = 0.0;
+      for (int k = j; k < m; ++k) acc = fma(Ls[c0 + i][a0 + k], Ls[a0 + k][a0 + j], acc);
+      T[e] = acc;
+    }
+    __syncthreads();
+    // B <- -C^-1 T:  X[i][j] = -sum_{k <= i} Cinv[i][k] T[k][j]   (C^-1 is lower triangular)
+    for (int e = tid; e < elems; e += blockDim.x) {
+      const int pr = e / mm, ij = e - pr * mm, i = ij / m, j = ij - i * m;
+      const int a0 = pr * 2 * m, c0 = a0 + m;
+      const double* Tp = T + pr * mm;
+      double acc = 0.0;
+      for (int k = 0; k <= i; ++k) acc = fma(Ls[c0 + i][c0 + k], Tp[k * m + j], acc);
+      Ls[c0 + i][a0 + j] = -acc;
+    }
+    __syncthreads();
+  }
+}
+
+// Ls (inverse, lower) -> global row-major 64 x 64 block (upper part written as zeros), coalesced.
+__device__ __forceinline__ void store_inverse_64(const double (*Ls)[NB + 1], double* __restrict__ Wout) {
+  for (int idx = threadIdx.x; idx < NB * NB; idx += blockDim.x) {
+    const int r = idx >> 6, c = idx & 63;
+    Wout[idx] = (c <= r) ? Ls[r][c] : 0.0;
+  }
 }
 
 // `Winv` (optional): also write inv(L_JJ) (64 x 64 row-major, identity padded) -- the operand of the DMMA panel solve
 // below the block (potrf_panel) and of the prediction solves' diagonal step.
-__global__ void __launch_bounds__(POTF2_THREADS) potf2_64_kernel(double* __restrict__ A, long long ld, int n, int pivot0,
+__global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_64_kernel(double* __restrict__ A, long long ld, int n, int pivot0,
                                                                  int* __restrict__ info, double* __restrict__ Winv) {
   __shared__ double Ld[2][4][4];     // factored diagonal 4 x 4 block (lower), double-buffered by micro-panel parity
   __shared__ double Rinv[2][4];      // reciprocal pivots of its 4 columns
@@ -218,6 +246,7 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_64_kernel(double* __restr
     }
   if (Winv != nullptr) {
     __shared__ double Ls[NB][NB + 1];
+    __shared__ double Tscratch[16 * NB];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -226,7 +255,8 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_64_kernel(double* __restr
         Ls[r][c] = (r < n && c <= r) ? v[a][b] : ((r == c) ? 1.0 : 0.0);
       }
     __syncthreads();
-    invert_lower_64(Ls, Winv);
+    invert_lower_64_inplace(Ls, Tscratch);
+    store_inverse_64(Ls, Winv);
   }
 }
 
@@ -300,13 +330,14 @@ __global__ void __launch_bounds__(TRSM_ROWS) trsm_rows_64_kernel(double* __restr
 }
 
 // W_J = inv(L_JJ) for every 64 x 64 diagonal block of the factor (identity padded when the last block is short):
-// one CTA per block, the SAME routine (invert_lower_64) the factorisation's potf2_64_kernel runs on the block it has
+// one CTA per block, the SAME routine (invert_lower_64_inplace) the factorisation's potf2_64_kernel runs on the block it has
 // just factored -- so a state that was imported (nngp_set_state / nngp_state_import_end) predicts with bitwise the
 // inverses of the handle that fitted it.  Output: row-major 64 x 64 blocks stacked along the rows (block J at rows
 // [64 J, 64 J + 64)), the B operand of the diagonal step of the row-wise triangular solves.
 __global__ void __launch_bounds__(POTF2_THREADS) trtri_diag_kernel(const double* __restrict__ L, long long ldl, int N,
                                                                    double* __restrict__ Winv) {
   __shared__ double Ls[NB][NB + 1];
+  __shared__ double Tscratch[16 * NB];
   const int J = blockIdx.x;
   const int j0 = J * NB;
   const int n = min(NB, N - j0);
@@ -314,7 +345,8 @@ __global__ void __launch_bounds__(POTF2_THREADS) trtri_diag_kernel(const double*
   for (int r = rsub; r < NB; r += 4)
     Ls[r][c] = (r < n && c <= r) ? L[(long long)(j0 + r) * ldl + j0 + c] : ((r == c) ? 1.0 : 0.0);
   __syncthreads();
-  invert_lower_64(Ls, Winv + (long long)j0 * NB);
+  invert_lower_64_inplace(Ls, Tscratch);
+  store_inverse_64(Ls, Winv + (long long)j0 * NB);
 }
 
 // Shared helper: load the n x n lower block Ljj into Ls (identity padded), 8 loads in flight per thread,

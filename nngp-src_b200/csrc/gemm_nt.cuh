@@ -253,14 +253,6 @@ __device__ __forceinline__ void ring_prologue(const TileSrc& src, uint8_t* ringA
 struct NoGate {  // default refill gate: operand tiles are always ready to be loaded
   __device__ __forceinline__ void operator()(int) const {}
 };
-// Persistent kernels: the tile this CTA works on next.  When `valid`, the stages released by the last STAGES k-tiles
-// of the current tile are refilled with the FIRST k-tiles of the next one, so its operands are in flight while this
-// tile's epilogue runs (the next mma_mainloop call is then told that its prologue has been issued).
-struct NextTile {
-  bool valid = false;
-  TileSrc src;
-  int ktiles = 0;
-};
 // `gate(kt)` is called by thread 0 right before it issues the TMA loads of k-tile kt (refills only; the caller
 // gates its own prologue): the persistent solve uses it to wait until the producer of that k-tile's A operand
 // (another CTA) has published it.  `active == false` (warp-uniform): this warp's 32-row slab lies entirely beyond
@@ -270,7 +262,7 @@ template <int STAGES, class Gate = NoGate>
 __device__ __forceinline__ void mma_mainloop(double (&acc)[4][4][2], const TileSrc& src, uint8_t* ringA, uint8_t* ringB,
                                              uint64_t* full_bar, uint64_t* empty_bar, int& stage, uint32_t& phase,
                                              int ktiles, int wm, int wn, int lane, uint32_t zero, Gate gate = Gate(),
-                                             bool active = true, const NextTile* next = nullptr) {
+                                             bool active = true) {
   const int g = lane >> 2, t = lane & 3;
   // Which k does lane (g, t) feed into DMMA step s?  Any bijection (s, t) -> 0..15 is a valid GEMM as long as the A
   // and the B fragment use the same one.  We use  k = 8*(t>>1) + 2*s + (t&1):  logical 16-byte chunk 4*(t>>1) + s,
@@ -289,15 +281,10 @@ __device__ __forceinline__ void mma_mainloop(double (&acc)[4][4][2], const TileS
   auto release = [&](int s, uint32_t ph, uint32_t seen, int kdone) {
     __syncwarp();
     if (lane == 0) mbar_arrive_addr(smem_u32(&empty_bar[s]) + (seen & zero));
-    if (threadIdx.x == 0) {
-      if (kdone + STAGES < ktiles) {
-        mbar_wait(&empty_bar[s], ph);  // all 8 warps are done with this stage in this round
-        gate(kdone + STAGES);
-        ring_issue<STAGES>(src, ringA, ringB, full_bar, s, kdone + STAGES);
-      } else if (next != nullptr && next->valid && kdone + STAGES - ktiles < next->ktiles) {
-        mbar_wait(&empty_bar[s], ph);
-        ring_issue<STAGES>(next->src, ringA, ringB, full_bar, s, kdone + STAGES - ktiles);
-      }
+    if (threadIdx.x == 0 && kdone + STAGES < ktiles) {
+      mbar_wait(&empty_bar[s], ph);  // all 8 warps are done with this stage in this round
+      gate(kdone + STAGES);
+      ring_issue<STAGES>(src, ringA, ringB, full_bar, s, kdone + STAGES);
     }
     __syncwarp();
   };
@@ -338,8 +325,12 @@ __device__ __forceinline__ void mma_mainloop(double (&acc)[4][4][2], const TileS
 }
 
 // Gram epilogue (K1 + K2 + K3 (+ K8)): k = scale * acc + sb2, depth-1 arc-cosine steps in registers, store, and
-// (optionally) the fused posterior-mean GEMV partial of this warp's 32 columns.  Shared by the one-tile-per-CTA
-// kernel and the persistent kernel.
+// (optionally) the fused posterior-mean GEMV partial of this warp's 32 columns.
+// (A persistent variant of the Gram kernel -- one CTA per SM slot walking the tiles, the next tile's TMA loads in
+// flight during the epilogue -- was measured in round 2 and dropped: 0.41 of the DMMA peak at C2 against 0.51 for
+// one tile per CTA.  Two co-resident persistent CTAs run in lock-step, both in the main loop or both in the
+// epilogue; with one tile per CTA the hardware scheduler staggers them, and a DMMA phase overlapping an FP64-FMA
+// phase is what fills the shared FP64 pipe.)
 #ifndef NNGP_GRAM_ILP
 #define NNGP_GRAM_ILP 4   // entries advanced through the layers together (2, 4 or 8): independent dependency chains
 #endif                    // (sqrt, reciprocal, two Horner halves each) for the scheduler to interleave; 8 spills
@@ -606,94 +597,6 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     gram_epilogue(acc, p, tile_n, row_base_e, col_base_e, wn, t);
-  }
-}
-
-// Persistent Gram kernel: one CTA per slot (2 per SM) walks the output tiles  idx = blockIdx.x, + gridDim.x, ...
-// (row-major over (tile_m, tile_n); only the tiles at or below the diagonal when p.lower).  While a tile's
-// arc-cosine epilogue runs on the FP64 pipe, the TMA loads of the CTA's NEXT tile are already in flight: the ring
-// stages released by the last k-tiles of a tile are refilled with the first k-tiles of the next one (NextTile), so a
-// tile neither pays a launch / barrier-init / pipeline-fill bubble nor leaves the copy engine idle during the
-// epilogue.  With D = 128 a tile is only 8 k-tiles: in the one-tile-per-CTA kernel that bubble is a third of the tile.
-__device__ __forceinline__ void gram_tile_coords(const GemmParams& p, int tiles_n, int idx, int& tile_m, int& tile_n) {
-  if (!p.lower) {
-    tile_m = idx / tiles_n;
-    tile_n = idx - tile_m * tiles_n;
-  } else {   // row tile m holds the column tiles 0 .. min(2 m + 1, tiles_n - 1): m (m + 1) tiles lie above it
-    int m = (int)((sqrt(4.0 * (double)idx + 1.0) - 1.0) * 0.5);
-    while (m * (m + 1) > idx) --m;
-    while ((m + 1) * (m + 2) <= idx) ++m;
-    tile_m = m;
-    tile_n = idx - m * (m + 1);
-  }
-}
-
-__global__ void __launch_bounds__(GEMM_THREADS, NNGP_GEMM_MINBLOCKS)
-gram_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                       const GemmParams p, int tiles_n, int ntiles) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
-  uint8_t* ring = smem_raw + pad;
-  uint8_t* ringA = ring;
-  uint8_t* ringB = ring + GEMM_STAGES * GEMM_A_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ringB + GEMM_STAGES * GEMM_B_STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + GEMM_STAGES;
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int s = 0; s < GEMM_STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], GEMM_CONSUMER_WARPS);
-    }
-    fence_mbar_init();
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-  }
-  __syncthreads();
-  const int ktiles = p.ktiles;
-  const int wm = warp >> 1, wn = warp & 1;
-  const int g = lane >> 2, t = lane & 3;
-  int idx = blockIdx.x;
-  if (idx >= ntiles) return;
-  int tile_m, tile_n;
-  gram_tile_coords(p, tiles_n, idx, tile_m, tile_n);
-  TileSrc src;
-  src.tmA = &tmA; src.tmB = &tmB;
-  src.a_col0 = p.a_col0; src.a_row = p.a_row0 + tile_m * GEMM_BM;
-  src.b_col0 = p.b_col0; src.b_row = p.b_row0 + tile_n * GEMM_BN;
-  int stage = 0;
-  uint32_t phase = 0;
-  if (threadIdx.x == 0) ring_prologue<GEMM_STAGES>(src, ringA, ringB, full_bar, stage, ktiles);
-  const bool chain = ktiles >= GEMM_STAGES;   // fewer k-tiles than stages: plain per-tile prologue (tiny D)
-  for (;;) {
-    NextTile next;
-    const int idx2 = idx + (int)gridDim.x;
-    int tm2 = 0, tn2 = 0;
-    if (idx2 < ntiles) {
-      gram_tile_coords(p, tiles_n, idx2, tm2, tn2);
-      next.valid = chain;
-      next.src = src;
-      next.src.a_row = p.a_row0 + tm2 * GEMM_BM;
-      next.src.b_row = p.b_row0 + tn2 * GEMM_BN;
-      next.ktiles = ktiles;
-    }
-    double acc[4][4][2];
-#pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-      for (int ni = 0; ni < 4; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
-    mma_mainloop<GEMM_STAGES>(acc, src, ringA, ringB, full_bar, empty_bar, stage, phase, ktiles, wm, wn, lane, p.zero,
-                              NoGate(), true, &next);
-    gram_epilogue(acc, p, tile_n, tile_m * GEMM_BM + wm * 32 + g, tile_n * GEMM_BN + wn * 32 + 2 * t, wn, t);
-    if (idx2 >= ntiles) break;
-    if (!chain) {
-      __syncthreads();   // every warp has left the ring
-      if (threadIdx.x == 0) ring_prologue<GEMM_STAGES>(next.src, ringA, ringB, full_bar, stage, ktiles);
-    }
-    idx = idx2; tile_m = tm2; tile_n = tn2;
-    src = next.src;
   }
 }
 

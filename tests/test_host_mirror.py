@@ -353,3 +353,46 @@ def test_unmodified_reference_active_train_driver_runs_on_the_shims(fake_engine,
         for m in [k for k in sys.modules if k == "jax" or k.startswith("jax.") or k == "neural_tangents"
                   or k == "active" or k.startswith("active.")]:
             del sys.modules[m]
+
+
+def test_first_party_cli_loader_reproduces_the_forest_fixture(forest, fake_engine, capsys, tmp_path):
+    """python -m nngp_b200.train (mirror of train.py:225-298): its loader + split on the reference's shipped forest
+    queries give exactly the committed C1 fixture (made by tests/golden/make_forest_fixture.py); on boxes without the
+    reference tree a small synthetic query directory exercises the same code.  The run prints train.py's lines and the
+    oracle's squared error (the engine is the oracle-backed fake here; the GPU test drives the real one)."""
+    import os
+    import re
+    from nngp_b200 import train as cli
+    qdir = "/root/reference/Queries/forest_data"
+    have_ref = os.path.isdir(qdir)
+    if not have_ref:
+        qdir = str(tmp_path)
+        rng = np.random.default_rng(0)
+        with open(tmp_path / "query_1.txt", "w") as fh:
+            for _ in range(200):
+                preds = []
+                for c, (lo, hi) in cli.FOREST_RANGES.items():
+                    if rng.random() < 0.5:
+                        a, b = sorted(rng.integers(lo, hi + 1, 2).tolist())
+                        preds.append(f"{c},{b},{a}")
+                fh.write("#".join(preds or ["A,3000,2000"]) + f"@{int(rng.integers(1, 5000))}\n")
+    args = cli.build_parser().parse_args(["--query_path", qdir])
+    args.join_query = False
+    x, y = cli.load_training_data(args)
+    xtr, ytr, xte, yte, _, _ = cli.train_test_val_split(x, y)
+    if have_ref:
+        assert np.array_equal(xtr, forest["x_train"]) and np.array_equal(ytr[:, 0], forest["y_train"])
+        assert np.array_equal(xte, forest["x_test"]) and np.array_equal(yte[:, 0], forest["y_test"])
+        xtr, ytr, xte, yte = xtr[:300], ytr[:300], xte[:100], yte[:100]        # keep the CPU fake quick
+    capsys.readouterr()
+    _, std, mse = cli.NNGP_train_and_test(args, xtr, ytr, xte, yte)
+    out = capsys.readouterr().out
+    rm, rv = oracle.Fit(xtr, ytr).predict(xte)
+    assert abs(mse - float(np.sum((rm[:, None] - yte) ** 2))) <= 1e-9 * max(1.0, mse)
+    assert np.allclose(std, np.sqrt(rv), rtol=1e-9)
+    assert float(re.search(r"Mean Square Error: ([-+0-9.eE]+)", out).group(1)) == mse
+    assert "Kernel construction in" in out and "Inference time=" in out and "q-error: median" in out
+    with pytest.raises(NotImplementedError):
+        a2 = cli.build_parser().parse_args(["--relations", "a,b"])
+        a2.join_query = True
+        cli.main(a2)
