@@ -23,6 +23,7 @@
 #include "dense_kernels.cuh"
 #include "gemm_nt.cuh"
 #include "trsm_fused.cuh"
+#include "potrf_panel.cuh"
 #include "active_kernels.cuh"
 
 using namespace nngp;
@@ -79,6 +80,7 @@ struct nngp_handle {
   DevBuf Linv;    // inv(L_JJ) of every 64 x 64 diagonal block of L (trtri_diag_kernel), operand of the solves' diagonal step
   DevBuf y;       // raw labels of the last nngp_fit (kept for nngp_append_fit)
   DevBuf app_x, app_y;  // nngp_append_fit staging: [X; X_new], [y; y_new]
+  DevBuf panel_sync;   // fused panel kernel: {item counter, progress[row tiles], inv_ready[column blocks]}
   DevBuf panel_inv;  // scratch inverses of a factorisation that is not the handle's own factor (Schur block, nngp_diag_potrf)
   DevBuf zkeep;   // z = L^-1 y of the last fit (the backward substitution destroys its copy in the factor buffer)
   DevBuf Linvfull;  // latency mode: the explicit inverse factor L^-1 (N x N, lower, row-major, ld = ldl)
@@ -358,7 +360,71 @@ bool panel_solve_fma() {
   return v;
 }
 
+// The whole panel as one persistent kernel (potrf_panel.cuh); NNGP_PANEL=steps selects the launch-per-step chain below.
+bool panel_fused() {
+  static const bool v = [] { const char* e = getenv("NNGP_PANEL"); return !(e && !strcmp(e, "steps")); }();
+  return v;
+}
+
+int potrf_panel_fused(nngp_handle* h, double* A, int64_t ld, int64_t N, int64_t R, int64_t j0, int64_t w, double* Winv) {
+  PanelParams p{};
+  p.A = A; p.ld = ld; p.j0 = (int)j0; p.rows = (int)(R - j0); p.ncols = (int)w;
+  p.row_tiles = (int)((R - j0 + GEMM_BM - 1) / GEMM_BM);
+  p.col_blocks = (int)((w + NB - 1) / NB);
+  p.info = h->flags.as<int>();
+  p.Winv = Winv;
+  const size_t nints = (size_t)1 + p.row_tiles + p.col_blocks;
+  CK(cudaMemsetAsync(h->panel_sync.p, 0, nints * sizeof(int), h->cur));   // (sized by run_potrf)
+  p.counter = h->panel_sync.as<int>();
+  p.progress = p.counter + 1;
+  p.inv_ready = p.progress + p.row_tiles;
+  CUtensorMap tmA, tmL, tmW;
+  CKR(get_tmap(h, A, R, N, ld, GEMM_BM, &tmA));
+  CKR(get_tmap(h, A, R, N, ld, GEMM_BN, &tmL));
+  CKR(get_tmap(h, Winv, round_up(N, NB), NB, NB, GEMM_BN, &tmW));
+  // Grid: one CTA per row tile, but no more than a quarter of the GPU's CTA slots.  The kernel's CTAs spend most of
+  // their life waiting for the owner's potf2; every slot they hold is a slot the trailing update running beside
+  // them (look-ahead) cannot use -- with 2 x #SMs spinning CTAs the overlap was gone (measured: 11.0 ms at N = 8192,
+  // no better than the launch-per-step chain).  NNGP_PANEL_GRID overrides (A/B runs).
+  static const int forced_grid = [] { const char* e = getenv("NNGP_PANEL_GRID"); return e ? atoi(e) : 0; }();
+  const long long total = (long long)p.row_tiles * p.col_blocks;
+  int grid = (int)std::min<long long>(p.row_tiles, h->sm_count / 2);
+  if (forced_grid > 0) grid = forced_grid;
+  grid = (int)std::max<long long>(1, std::min<long long>(grid, total));
+  // NNGP_PANEL_TRACE=1 (diagnostics): time stamps of the owner items of every panel -> stderr (synchronises!)
+#ifdef NNGP_PANEL_TRACE
+  static const bool trace = [] { const char* e = getenv("NNGP_PANEL_TRACE"); return e && atoi(e) > 0; }();
+#else
+  const bool trace = false;   // (the stamps are compiled into the kernel only by build.sh -DNNGP_PANEL_TRACE)
+#endif
+  unsigned long long* tr_d = nullptr;
+  if (trace) {
+    CK(cudaMalloc(&tr_d, (size_t)p.col_blocks * 10 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(tr_d, 0, (size_t)p.col_blocks * 10 * sizeof(unsigned long long), h->cur));
+    p.trace = tr_d;
+  }
+  potrf_panel_kernel<<<grid, GEMM_THREADS, TF_SMEM_BYTES, h->cur>>>(tmA, tmL, tmW, p);
+  CK(cudaGetLastError());
+  h->st.kernel_launches++;
+  if (trace) {
+    std::vector<unsigned long long> tr((size_t)p.col_blocks * 10);
+    CK(cudaStreamSynchronize(h->cur));
+    CK(cudaMemcpy(tr.data(), tr_d, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    cudaFree(tr_d);
+    const unsigned long long t00 = tr[0];
+    fprintf(stderr, "panel j0=%lld rows=%d grid=%d: per owner item [claimed, update done, R stored, factor done, inverse stored, flag+reload, W+R staged, diag done, published] us since the panel's first claim\n",
+            (long long)j0, p.rows, grid);
+    for (int J = 0; J < p.col_blocks; ++J) {
+      fprintf(stderr, "  J=%d:", J);
+      for (int k = 0; k < 9; ++k) fprintf(stderr, " %8.2f", tr[(size_t)J * 10 + k] ? (double)(tr[(size_t)J * 10 + k] - t00) / 1e3 : -1.0);
+      fprintf(stderr, "\n");
+    }
+  }
+  return NNGP_OK;
+}
+
 int potrf_panel(nngp_handle* h, double* A, int64_t ld, int64_t N, int64_t R, int64_t j0, int64_t w, double* Winv) {
+  if (panel_fused()) return potrf_panel_fused(h, A, ld, N, R, j0, w, Winv);
   int* info = h->flags.as<int>();
   MatView Av{A, R, N, ld}, Wv{Winv, round_up(N, NB), NB, NB};
   for (int64_t s0 = j0; s0 < j0 + w; s0 += NB) {
@@ -400,6 +466,8 @@ int run_potrf(nngp_handle* h, double* A, int64_t ld, int64_t N, int64_t extra, d
   const int W = chol_outer_width(N);
   const int64_t R = N + extra;
   MatView Av{A, R, N, ld};
+  // counters / flags of the fused panel kernel, sized once so that nothing is (re)allocated between the panels
+  CKR(ensure(h, h->panel_sync, (size_t)(2 + (R + GEMM_BM - 1) / GEMM_BM + (W + NB - 1) / NB) * sizeof(int)));
   const bool lookahead = h->panel_stream != nullptr && N > 2 * W;
   static const int la_mode = [] { const char* e = getenv("NNGP_LA_MODE"); return e ? atoi(e) : 1; }();
   cudaEvent_t ev_cols = get_event(h), ev_panel = get_event(h);
@@ -583,7 +651,20 @@ int run_inverse_variance(nngp_handle* h, const double* B, int64_t ldb, int64_t r
   p.ldc = ldb; p.W = nullptr; p.tri_k = 1;
   MatView a{B, rows, N, ldb}, b{h->Linvfull.as<double>(), N, N, h->ldl};
   const int64_t row_tiles = (rows + GEMM_BM - 1) / GEMM_BM;
-  if (row_tiles * col_tiles < 4LL * h->sm_count) {
+  if (rows <= TGV_MAXR) {
+    // A handful of queries: one streaming pass over L^-1 (tri_gemv_kernel), then the fixed-order row reduction.
+    CKR(ensure(h, h->partial, (size_t)rows * N * 8));
+    const int ngroups = (int)((N + 7) / 8);
+    const dim3 tg((unsigned)((ngroups + 1) / 2));
+    const double* Wf = h->Linvfull.as<double>();
+    double* vp = h->partial.as<double>();
+    if (rows == 1) tri_gemv_kernel<1><<<tg, 256, 0, h->stream>>>(Wf, h->ldl, (int)N, B, ldb, (int)rows, vp);
+    else if (rows == 2) tri_gemv_kernel<2><<<tg, 256, 0, h->stream>>>(Wf, h->ldl, (int)N, B, ldb, (int)rows, vp);
+    else if (rows <= 4) tri_gemv_kernel<4><<<tg, 256, 0, h->stream>>>(Wf, h->ldl, (int)N, B, ldb, (int)rows, vp);
+    else tri_gemv_kernel<8><<<tg, 256, 0, h->stream>>>(Wf, h->ldl, (int)N, B, ldb, (int)rows, vp);
+    h->st.kernel_launches++;
+    var_from_split_kernel<<<(unsigned)rows, 256, 0, h->stream>>>(kss, h->partial.as<double>(), (int)rows, (int)N, p.ktiles, p.ktiles, var);
+  } else if (row_tiles * col_tiles < 4LL * h->sm_count) {
     // Few rows: a column tile near the end of the triangular product is one serial loop of up to N/16 k-tiles on ONE
     // SM while most of the GPU idles.  Split K into <= 8 chunks (grid z), keep the partial products of the valid rows
     // (rows x N x chunks doubles) and square / reduce them in a second, fixed-order kernel.
@@ -887,6 +968,7 @@ static int create_single(const nngp_config* cfg, nngp_handle** out) {
   if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(trsm_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM_BYTES);
   if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(trsm_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM_BYTES);
   if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(gemm_nt_kernel<EPI_DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+  if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM_BYTES);
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
     fail(h, NNGP_ECUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s",
          cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
@@ -973,7 +1055,7 @@ void nngp_destroy(nngp_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->X, &h->q, &h->L, &h->alpha, &h->flags, &h->lam_d, &h->xt, &h->qt, &h->kss,
-                    &h->blk, &h->mean_d, &h->var_d, &h->ssq, &h->sync_ints, &h->Mmat, &h->Kdd, &h->blk2, &h->cross, &h->partial, &h->mean_partial, &h->ka, &h->kb, &h->kqa, &h->kqb, &h->kout, &h->Linv, &h->Linvfull, &h->panel_inv, &h->zkeep, &h->L2, &h->y, &h->app_x, &h->app_y, &h->sel_mean, &h->sel_var, &h->sel_score, &h->sel_key,
+                    &h->blk, &h->mean_d, &h->var_d, &h->ssq, &h->sync_ints, &h->Mmat, &h->Kdd, &h->blk2, &h->cross, &h->partial, &h->mean_partial, &h->ka, &h->kb, &h->kqa, &h->kqb, &h->kout, &h->Linv, &h->Linvfull, &h->panel_inv, &h->panel_sync, &h->zkeep, &h->L2, &h->y, &h->app_x, &h->app_y, &h->sel_mean, &h->sel_var, &h->sel_score, &h->sel_key,
                     &h->sel_state, &h->sel_okey, &h->sel_oidx, &h->sel_max})
     release(*b);
   for (auto& r : h->pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

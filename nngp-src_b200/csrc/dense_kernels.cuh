@@ -86,14 +86,54 @@ __global__ void diag_reg_kernel(double* __restrict__ K, long long ld, int N, dou
 // factor is bitwise that of the one-column-per-step version this replaces (34 us -> 10 us per block).
 // On a non-positive pivot: *info = global pivot index + 1 (first failure wins), block left as is.
 constexpr int POTF2_THREADS = 256;
-// In-place inverse of the lower-triangular 64 x 64 block in Ls (identity padded), by all 256 threads of the CTA, as a
-// recursive block inversion:  inv [[A, 0], [B, C]] = [[A^-1, 0], [-C^-1 B A^-1, C^-1]].  Level 0 inverts the sixteen
-// 4 x 4 diagonal blocks (one thread each); levels m = 4, 8, 16, 32 fill the off-diagonal m x m blocks of every
-// 2m x 2m diagonal super-block with two small products (T = B A^-1 into the scratch `T`, then -C^-1 T over B: the
-// region that held B is exactly where the result belongs, so no second matrix is needed).  9 barriers and ~350
-// multiply-adds per thread -- ~2 us, where a column-wise forward substitution is a 64-step chain of divisions and
-// shuffles (~20 us measured, on the critical path of the Cholesky panel chain).  `T`: 1024 doubles.
-// The same routine serves the factorisation (potf2_64_kernel) and imported states (trtri_diag_kernel): same bits.
+// In-place inverse of the lower-triangular 64 x 64 block in Ls (identity padded, zeros above the diagonal), by all 256
+// threads of the CTA, as a recursive block inversion:  inv [[A, 0], [B, C]] = [[A^-1, 0], [-C^-1 B A^-1, C^-1]].
+// Level 0 inverts the sixteen 4 x 4 diagonal blocks (one thread each); levels M = 4, 8, 16, 32 fill the off-diagonal
+// M x M blocks of every 2M x 2M diagonal super-block with two small products (T = B A^-1 into the scratch `T`, then
+// -C^-1 T over B: the region that held B is exactly where the result belongs, so no second matrix is needed).
+// Each thread owns S = M/8 adjacent outputs of a row and runs the FULLY UNROLLED dense k loop (the zeros above the
+// diagonals of A^-1 / C^-1 make the triangular bounds unnecessary), so the shared-memory loads pipeline instead of
+// serialising behind a loop-carried bound: 9 barriers, ~2 us, against ~12 us with data-dependent trip counts and
+// ~20 us for a column-wise forward substitution (a 64-step chain of divisions and shuffles) -- this sits on the
+// critical path of the Cholesky panel chain.  `T`: 1024 doubles.
+// The same routine serves the factorisation (potf2_64_block) and imported states (trtri_diag_kernel): same bits.
+template <int M>
+__device__ __forceinline__ void invert_level(double (*Ls)[NB + 1], double* __restrict__ T) {
+  constexpr int S = M >= 8 ? M / 8 : 1;          // outputs per thread
+  constexpr int GROUPS = M / S;                  // thread groups per output row
+  constexpr int NTHR = (NB / (2 * M)) * M * GROUPS;   // 256 for M >= 8, 128 for M = 4
+  const int tid = threadIdx.x;
+  const int pr = tid / (M * GROUPS), rem = tid - pr * (M * GROUPS), i = rem / GROUPS, j0 = (rem - i * GROUPS) * S;
+  const int a0 = pr * 2 * M, c0 = a0 + M;
+  double acc[S];
+  if (tid < NTHR) {     // T = B A^-1
+#pragma unroll
+    for (int s = 0; s < S; ++s) acc[s] = 0.0;
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+      const double b = Ls[c0 + i][a0 + k];
+#pragma unroll
+      for (int s = 0; s < S; ++s) acc[s] = fma(b, Ls[a0 + k][a0 + j0 + s], acc[s]);
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) T[pr * M * M + i * M + j0 + s] = acc[s];
+  }
+  __syncthreads();
+  if (tid < NTHR) {     // B <- -C^-1 T
+#pragma unroll
+    for (int s = 0; s < S; ++s) acc[s] = 0.0;
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+      const double c = Ls[c0 + i][c0 + k];
+#pragma unroll
+      for (int s = 0; s < S; ++s) acc[s] = fma(c, T[pr * M * M + k * M + j0 + s], acc[s]);
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) Ls[c0 + i][a0 + j0 + s] = -acc[s];
+  }
+  __syncthreads();
+}
+
 __device__ __forceinline__ void invert_lower_64_inplace(double (*Ls)[NB + 1], double* __restrict__ T) {
   const int tid = threadIdx.x;
   if (tid < NB / 4) {
@@ -112,28 +152,10 @@ __device__ __forceinline__ void invert_lower_64_inplace(double (*Ls)[NB + 1], do
     Ls[o + 3][o] = w30; Ls[o + 3][o + 1] = w31; Ls[o + 3][o + 2] = w32;
   }
   __syncthreads();
-  for (int m = 4; m < NB; m *= 2) {
-    const int mm = m * m, elems = (NB / (2 * m)) * mm;      // = 32 m outputs per product
-    // T = B A^-1:  T[i][j] = sum_{k >= j} B[i][k] Ainv[k][j]   (A^-1 is lower triangular)
-    for (int e = tid; e < elems; e += blockDim.x) {
-      const int pr = e / mm, ij = e - pr * mm, i = ij / m, j = ij - i * m;
-      const int a0 = pr * 2 * m, c0 = a0 + m;
-      double acc = 0.0;
-      for (int k = j; k < m; ++k) acc = fma(Ls[c0 + i][a0 + k], Ls[a0 + k][a0 + j], acc);
-      T[e] = acc;
-    }
-    __syncthreads();
-    // B <- -C^-1 T:  X[i][j] = -sum_{k <= i} Cinv[i][k] T[k][j]   (C^-1 is lower triangular)
-    for (int e = tid; e < elems; e += blockDim.x) {
-      const int pr = e / mm, ij = e - pr * mm, i = ij / m, j = ij - i * m;
-      const int a0 = pr * 2 * m, c0 = a0 + m;
-      const double* Tp = T + pr * mm;
-      double acc = 0.0;
-      for (int k = 0; k <= i; ++k) acc = fma(Ls[c0 + i][c0 + k], Tp[k * m + j], acc);
-      Ls[c0 + i][a0 + j] = -acc;
-    }
-    __syncthreads();
-  }
+  invert_level<4>(Ls, T);
+  invert_level<8>(Ls, T);
+  invert_level<16>(Ls, T);
+  invert_level<32>(Ls, T);
 }
 
 // Ls (inverse, lower) -> global row-major 64 x 64 block (upper part written as zeros), coalesced.
@@ -144,14 +166,33 @@ __device__ __forceinline__ void store_inverse_64(const double (*Ls)[NB + 1], dou
   }
 }
 
-// `Winv` (optional): also write inv(L_JJ) (64 x 64 row-major, identity padded) -- the operand of the DMMA panel solve
-// below the block (potrf_panel) and of the prediction solves' diagonal step.
-__global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_64_kernel(double* __restrict__ A, long long ld, int n, int pivot0,
-                                                                 int* __restrict__ info, double* __restrict__ Winv) {
-  __shared__ double Ld[2][4][4];     // factored diagonal 4 x 4 block (lower), double-buffered by micro-panel parity
-  __shared__ double Rinv[2][4];      // reciprocal pivots of its 4 columns
-  __shared__ double P[2][NB][4];     // the finished micro-panel: P[.][r][ja] = L[r][4 jb + ja]
-  __shared__ int s_bad[2];
+// Shared memory of one 64 x 64 block factorisation (45.9 KB): static in potf2_64_kernel, aliased onto the drained
+// operand ring in the fused panel kernel (potrf_panel.cuh).
+struct Potf2Smem {
+  double Ld[2][4][4];     // factored diagonal 4 x 4 block (lower), double-buffered by micro-panel parity
+  double Rinv[2][4];      // reciprocal pivots of its 4 columns
+  double P[2][NB][4];     // the finished micro-panel: P[.][r][ja] = L[r][4 jb + ja]
+  int s_bad[2];
+  double Ls[NB][NB + 1];  // the factored block, then its inverse
+  double T[16 * NB];      // scratch of the block inversion
+};
+
+// The block-wide routine (256 threads): factor, store, and -- `Winv` optional -- also write inv(L_JJ) (64 x 64 row-major,
+// identity padded), the operand of the DMMA panel solve below the block and of the prediction solves' diagonal step.
+// Returns 0, or the 1-based pivot index inside the block on a non-positive pivot (block-uniform; *info is set).
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ int potf2_64_block(double* __restrict__ A, long long ld, int n, int pivot0, int* __restrict__ info,
+                                              double* __restrict__ Winv, Potf2Smem& sm,
+                                              unsigned long long* trace = nullptr) {
+  double (&Ld)[2][4][4] = sm.Ld;
+  double (&Rinv)[2][4] = sm.Rinv;
+  double (&P)[2][NB][4] = sm.P;
+  int (&s_bad)[2] = sm.s_bad;
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   double v[4][4];
@@ -195,7 +236,7 @@ __global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_64_kernel(double* __re
     __syncthreads();
     if (s_bad[buf]) {  // CTA-uniform exit
       if (tid == 0) atomicCAS(info, 0, pivot0 + s_bad[buf]);
-      return;
+      return s_bad[buf];
     }
     if (tx == jb && ty > jb) {  // B: the micro-panel below the diagonal block
 #pragma unroll
@@ -244,9 +285,9 @@ __global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_64_kernel(double* __re
       const int r = ty * 4 + a, c = tx * 4 + b;
       if (r < n && c <= r) A[(long long)r * ld + c] = v[a][b];
     }
+  if (trace != nullptr && tid == 0) trace[0] = global_timer_ns();   // (debug builds of the panel kernel: factor done)
   if (Winv != nullptr) {
-    __shared__ double Ls[NB][NB + 1];
-    __shared__ double Tscratch[16 * NB];
+    double (*Ls)[NB + 1] = sm.Ls;
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -255,9 +296,16 @@ __global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_64_kernel(double* __re
         Ls[r][c] = (r < n && c <= r) ? v[a][b] : ((r == c) ? 1.0 : 0.0);
       }
     __syncthreads();
-    invert_lower_64_inplace(Ls, Tscratch);
+    invert_lower_64_inplace(Ls, sm.T);
     store_inverse_64(Ls, Winv);
   }
+  return 0;
+}
+
+__global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_64_kernel(double* __restrict__ A, long long ld, int n, int pivot0,
+                                                                    int* __restrict__ info, double* __restrict__ Winv) {
+  __shared__ Potf2Smem sm;
+  potf2_64_block(A, ld, n, pivot0, info, Winv, sm);
 }
 
 // X * Ljj^T = B in place, for `rows` rows of B (row-major, ldb) and the n x n (n <= 64) lower block
@@ -566,7 +614,15 @@ __global__ void mean_reduce_kernel(const double* __restrict__ partial, int tiles
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   double s = 0.0;
-  for (int t = 0; t < tiles; ++t) s += partial[(long long)t * rows + r];
+  int t = 0;
+  for (; t + 8 <= tiles; t += 8) {       // 8 loads in flight, added in tile order: the same sum, without 8 serial misses
+    double b[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) b[u] = partial[(long long)(t + u) * rows + r];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += b[u];
+  }
+  for (; t < tiles; ++t) s += partial[(long long)t * rows + r];
   mean[r] = s;
 }
 
@@ -599,12 +655,22 @@ __global__ void __launch_bounds__(256) var_from_split_kernel(const double* __res
   __shared__ double red[256];
   const int r = blockIdx.x;
   double sacc = 0.0;
-  for (int c = threadIdx.x; c < N; c += 256) {
-    const int kt = min(ktiles_total, (c / 64 + 1) * 4);
-    const int nz = (kt + kchunk - 1) / kchunk;
-    double v = 0.0;
-    for (int z = 0; z < nz; ++z) v += vpart[((long long)z * rows + r) * N + c];
-    sacc = fma(v, v, sacc);
+  if (kchunk >= ktiles_total) {          // a single chunk (tri_gemv path): plain strided sum of squares, loads batched
+    const double* vr = vpart + (long long)r * N;
+    int c = threadIdx.x;
+    for (; c + 3 * 256 < N; c += 4 * 256) {
+      const double v0 = vr[c], v1 = vr[c + 256], v2 = vr[c + 512], v3 = vr[c + 768];
+      sacc = fma(v0, v0, sacc); sacc = fma(v1, v1, sacc); sacc = fma(v2, v2, sacc); sacc = fma(v3, v3, sacc);
+    }
+    for (; c < N; c += 256) { const double v0 = vr[c]; sacc = fma(v0, v0, sacc); }
+  } else {
+    for (int c = threadIdx.x; c < N; c += 256) {
+      const int kt = min(ktiles_total, (c / 64 + 1) * 4);
+      const int nz = (kt + kchunk - 1) / kchunk;
+      double v = 0.0;
+      for (int z = 0; z < nz; ++z) v += vpart[((long long)z * rows + r) * N + c];
+      sacc = fma(v, v, sacc);
+    }
   }
   red[threadIdx.x] = sacc;
   __syncthreads();
@@ -613,6 +679,72 @@ __global__ void __launch_bounds__(256) var_from_split_kernel(const double* __res
     __syncthreads();
   }
   if (threadIdx.x == 0) var[r] = kss[r] - red[0];
+}
+
+// latency mode, a handful of queries (rows <= 8): v[r][j] = sum_{k <= j} W[j][k] ks[r][k] with W = L^-1 (lower, row-
+// major) as a matrix-vector product that streams W exactly once -- the HBM floor of the request (4 N^2 bytes) --
+// instead of pushing a 128-row DMMA tile that is 99 % padding through the tensor pipe.  A CTA takes a group of 8
+// consecutive rows of W, one per warp, paired with the mirrored group from the other end of the matrix so that every
+// CTA streams the same number of bytes; the query rows are staged in shared memory one k-chunk at a time and shared by
+// the 8 warps.  Lane l accumulates k = 2 l, 2 l + 1 (+ 64, ...) and the warp combines with a fixed xor tree:
+// deterministic.  Output: v[r * N + j] (squared and row-reduced by var_from_split_kernel with a single chunk).
+constexpr int TGV_MAXR = 8;
+constexpr int TGV_SMEM_DOUBLES = 4096;            // staged query values per k-chunk: R x KC, KC = 4096 / R
+template <int R>
+__global__ void __launch_bounds__(256, 2) tri_gemv_kernel(const double* __restrict__ W, long long ldw, int N,
+                                                          const double* __restrict__ ks, long long ldk, int rows,
+                                                          double* __restrict__ v) {
+  constexpr int KC = TGV_SMEM_DOUBLES / R;
+  constexpr int U = 4;                            // independent 16-byte loads in flight per lane (the stream is
+  __shared__ double ks_s[R][KC];                  // latency-bound otherwise: 1.5 TB/s with one load per lane)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ngroups = (N + 7) / 8;
+  for (int half = 0; half < 2; ++half) {
+    const int grp = half == 0 ? (int)blockIdx.x : ngroups - 1 - (int)blockIdx.x;
+    if (half == 1 && grp <= (int)blockIdx.x) break;          // the middle group of an odd count is taken once
+    const int j = grp * 8 + warp;
+    const int jmax = min(grp * 8 + 7, N - 1);                 // longest row of the group
+    double acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.0;
+    const double* wj = W + (long long)min(j, N - 1) * ldw;
+    for (int k0 = 0; k0 <= jmax; k0 += KC) {
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < R * KC; idx += 256) {
+        const int r = idx / KC, kk = idx - r * KC;
+        ks_s[r][kk] = (r < rows && k0 + kk <= jmax) ? ks[(long long)r * ldk + k0 + kk] : 0.0;
+      }
+      __syncthreads();
+      if (j < N) {
+        const int kend = min(k0 + KC, j + 1);
+        for (int kb = k0 + 2 * lane; kb < kend; kb += 64 * U) {
+          double2 w2[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {          // all U loads are issued before the first use
+            const int k = kb + 64 * u;
+            w2[u] = (k < kend) ? *reinterpret_cast<const double2*>(wj + k) : make_double2(0.0, 0.0);   // (ldw, k even)
+            if (k + 1 >= kend) w2[u].y = 0.0;    // beyond the diagonal: not part of row j
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {          // ascending k: the order of the sums does not depend on U
+            const int kk = min(kb + 64 * u, kend - 1) - k0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              acc[r] = fma(w2[u].x, ks_s[r][kk], acc[r]);
+              acc[r] = fma(w2[u].y, ks_s[r][min(kk + 1, KC - 1)], acc[r]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      double a = acc[r];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0 && j < N && r < rows) v[(long long)r * N + j] = a;
+    }
+  }
 }
 
 // A <- I (n x n, leading dimension ld)

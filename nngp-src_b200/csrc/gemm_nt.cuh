@@ -512,7 +512,14 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   int stage = 0;
   uint32_t phase = 0;
-  mma_mainloop<GEMM_STAGES>(acc, src, ringA, ringB, full_bar, empty_bar, stage, phase, ktiles, wm, wn, lane, p.zero);
+  if constexpr (EPI == EPI_ROWDOT) {
+    // small batches (latency mode): a 32-row slab without a valid row skips its fragment loads and DMMAs
+    const bool slab_active = tile_m * GEMM_BM + wm * 32 < p.M;
+    mma_mainloop<GEMM_STAGES>(acc, src, ringA, ringB, full_bar, empty_bar, stage, phase, ktiles, wm, wn, lane, p.zero,
+                              NoGate(), slab_active);
+  } else {
+    mma_mainloop<GEMM_STAGES>(acc, src, ringA, ringB, full_bar, empty_bar, stage, phase, ktiles, wm, wn, lane, p.zero);
+  }
 
   // ===== epilogue (registers -> global) =====
   // The tile coordinates are laundered through an empty asm so that the compiler re-derives the output addresses

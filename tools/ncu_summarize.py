@@ -45,7 +45,8 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct",
         "smsp__cycles_active.avg", "sm__cycles_elapsed.max", "smsp__inst_executed.sum",
-        "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio" ]
+        "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active"]
 
 
 def full(path, out):
@@ -64,6 +65,14 @@ def full(path, out):
                 try:
                     if float(r[idx[h]]) >= 3.0:
                         d.setdefault("stalls_pct", {})[h.split("warp_issue_stalled_")[-1].split("_per_warp")[0]] = float(r[idx[h]])
+                except ValueError:
+                    pass
+        for h in hdr:      # warp stall reasons, in issue slots per issued instruction
+            if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio"):
+                try:
+                    if float(r[idx[h]]) >= 0.2:
+                        name = h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]
+                        d.setdefault("stall_slots_per_issue", {})[name] = round(float(r[idx[h]]), 3)
                 except ValueError:
                     pass
         res.append(d)
