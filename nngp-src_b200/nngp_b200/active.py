@@ -40,10 +40,14 @@ class ActiveLearner(object):
 
     def retrain(self, kernel_fn, predict_fn, X_train, Y_train, X_delta, Y_delta):
         """``self.train(kernel_fn, X_train, Y_train)`` (ActiveLearner.py:76) where X_train = [old; X_delta]: the fitted
-        engine of ``predict_fn`` appends the new rows on the device and refits; the returned predict_fn is bound to it."""
+        engine of ``predict_fn`` appends the new rows on the device and refits; the returned predict_fn is bound to it.
+        The engine is TAKEN from ``predict_fn``: a caller that keeps the old closure (to compare rounds) gets the old
+        model back -- it refits lazily from its own data -- never the new one."""
         if not hasattr(predict_fn, "engine"):
             return self.train(kernel_fn, X_train, Y_train)
         h = predict_fn.engine(self.kernel_type)
+        if hasattr(predict_fn, "release"):     # the engine changes owner: the old closure refits if it is used again
+            predict_fn.release(self.kernel_type)
         h.append_fit(X_delta, Y_delta)
         kernel_fn = _batch.batch(kernel_fn, device_count=0, batch_size=0)
         return _predict.gradient_descent_mse_ensemble(kernel_fn, X_train, Y_train, diag_reg=1e-3,

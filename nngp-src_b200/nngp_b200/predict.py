@@ -103,6 +103,14 @@ def gradient_descent_mse_ensemble(kernel_fn, x_train, y_train, learning_rate=1.0
             return mean
         return Gaussian(mean, LazyCovariance(var))
 
+    def _release(get="nngp"):
+        """Hand the fitted engine of ``get`` over to the caller and forget it here: this closure then refits from its
+        own (x_train, y_train) the next time it is used -- in the reference every ``gradient_descent_mse_ensemble``
+        call is an independent fit, so a predict_fn kept from an earlier active-learning round must not start
+        answering with a later round's model (``ActiveLearner.retrain`` appends to the engine it takes from here)."""
+        return state.pop(get, None)
+
     predict_fn.engine = _fitted            # bench / tests: access to the underlying C-ABI handle
+    predict_fn.release = _release
     predict_fn.spec = kernel_fn.spec
     return predict_fn

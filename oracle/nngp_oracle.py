@@ -161,7 +161,9 @@ class Fit:
         self.x = np.asarray(x, dtype=np.float64)
         self.y = np.asarray(y, dtype=np.float64).reshape(-1)
         self.depth, self.sigma_w, self.sigma_b = depth, sigma_w, sigma_b
-        self.c, self.alpha, self.lam = np.asarray(c), np.asarray(alpha).reshape(-1), float(lam)
+        # column-major like the factor Fit.__init__ gets from LAPACK: solve_triangular would otherwise copy the whole
+        # N x N matrix into Fortran order on every predict() call
+        self.c, self.alpha, self.lam = np.asfortranarray(c), np.asarray(alpha).reshape(-1), float(lam)
         return self
 
     def log_marginal_likelihood(self):

@@ -396,3 +396,24 @@ def test_first_party_cli_loader_reproduces_the_forest_fixture(forest, fake_engin
         a2 = cli.build_parser().parse_args(["--relations", "a,b"])
         a2.join_query = True
         cli.main(a2)
+
+
+def test_retrain_takes_the_engine_and_the_old_closure_stays_valid(fake_engine):
+    """ActiveLearner.retrain appends to the handle of the previous predict_fn.  That closure must not start
+    answering with the new model: it gives the engine up and refits from its own data when used again (in the
+    reference every gradient_descent_mse_ensemble call is an independent fit, active/ActiveLearner.py:69,76)."""
+    from nngp_b200 import synth
+    from nngp_b200.active import ActiveLearner
+    _, _, kernel_fn = stax.serial(stax.Dense(512), stax.Relu(), stax.Dense(1))
+    xtr, ytr, xpool, ypool = synth.make_problem(60, 40, 8)
+    al = ActiveLearner(budget=10, active_iters=1, verbose=False)
+    old_fn = al.train(kernel_fn, xtr, ytr[:, None])
+    before = old_fn(x_test=xpool, get="nngp", compute_cov=False)
+    sel = al.active_test(old_fn, xpool)
+    x2, y2, _, _ = al.merge_data(sel, xtr, ytr[:, None], xpool, ypool[:, None])
+    new_fn = al.retrain(kernel_fn, old_fn, x2, y2, xpool[sel], ypool[sel][:, None])
+    after_new = new_fn(x_test=xpool, get="nngp", compute_cov=False)
+    after_old = old_fn(x_test=xpool, get="nngp", compute_cov=False)
+    assert not np.allclose(after_new, before)                 # the new closure serves the extended model
+    assert np.array_equal(after_old, before)                  # the old one still serves the old model (refitted)
+    assert new_fn.engine() is not old_fn.engine()
