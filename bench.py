@@ -185,6 +185,13 @@ def _traffic(workload: str, world: int):
     return rec.get("dram_bytes_per_launch"), rec.get("source")
 
 
+def _guard(fn):
+    try:
+        return fn()
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
+
+
 def _time_predict(torch, dist, world, h, local, xte_host, steps, warmup, sample_clocks=True):
     """(device-resident ms, e2e ms, stats, e2e stats, clocks) of one handle predicting xte_host per step."""
     t = xte_host.shape[0]
@@ -306,6 +313,7 @@ def run_b200(args):
     ms_total, ms_e2e, e2e_steps, st, st_e2e, clocks = _time_predict(torch, dist, world, h, local, xte_host, args.steps, warmup, sample_clocks=(rank == 0))
 
     in_process = None
+    hard_exit = False
     if world > 1 and not args.no_extras:
         # In-process multi-GPU: ONE handle on rank 0 drives all N GPUs through the same nngp_predict call (replicas +
         # row split behind the C ABI).  The other ranks free their state and wait on a host-side (gloo) barrier.
@@ -314,7 +322,7 @@ def run_b200(args):
             torch.cuda.empty_cache()
         dist.barrier(group=gloo)
         if rank == 0:
-            try:
+            def leg():
                 hm = _lib.Handle(depth=depth, diag_reg=1e-3, stats_level=1, device_ids=list(range(world)))
                 xall = np.concatenate([xte_host] + [synth.encodings(t_rank, d, 2 + r, join_dims=jd) for r in range(1, world)])
                 hm.fit(xtr, ytr)
@@ -331,21 +339,28 @@ def run_b200(args):
                 for _ in range(k):
                     hm.predict(pin.numpy(), mean_out=mo.numpy(), var_out=vo.numpy())
                 sec = time.perf_counter() - t0
-                in_process = {"value": k * xall.shape[0] / sec, "unit": UNIT, "ms_per_step": sec / k * 1e3, "steps": k,
-                              "n_gpus": hm.n_gpus, "api": "ONE nngp_handle with n_gpus=N: nngp_fit replicates the packed lower "
-                              "triangle peer-to-peer (pipelined chain), nngp_predict splits rows over the GPUs; host buffers in/out, wall clock",
-                              "replicate_ms": sfit["replicate_ms"], "replicate_bytes": sfit["replicate_bytes"],
-                              "replicate_gb_per_s": sfit["replicate_bytes"] / max(sfit["replicate_ms"], 1e-9) / 1e6,
-                              "fit_seconds_device": sfit["fit_total_ms"] / 1e3,
-                              "same_bits_as_rank0_shard": bool(np.array_equal(mo.numpy()[:1024], h.predict(xte_host[:1024])[0]))}
+                rec = {"value": k * xall.shape[0] / sec, "unit": UNIT, "ms_per_step": sec / k * 1e3, "steps": k,
+                       "n_gpus": hm.n_gpus, "api": "ONE nngp_handle with n_gpus=N: nngp_fit replicates the packed lower "
+                       "triangle peer-to-peer (pipelined chain), nngp_predict splits rows over the GPUs; host buffers in/out, wall clock",
+                       "replicate_ms": sfit["replicate_ms"], "replicate_bytes": sfit["replicate_bytes"],
+                       "replicate_gb_per_s": sfit["replicate_bytes"] / max(sfit["replicate_ms"], 1e-9) / 1e6,
+                       "fit_seconds_device": sfit["fit_total_ms"] / 1e3,
+                       "same_bits_as_rank0_shard": bool(np.array_equal(mo.numpy()[:1024], h.predict(xte_host[:1024])[0]))}
                 hm.close()
-            except Exception as e:  # noqa: BLE001
-                in_process = {"error": repr(e)}
+                return rec
+
+            # bounded: a side record must never cost the run its headline line (the worker is a daemon thread)
+            box = {}
+            th = threading.Thread(target=lambda: box.update(rec=_guard(leg)), daemon=True)
+            th.start()
+            th.join(timeout=420.0)
+            in_process = box.get("rec", {"error": "the in-process multi-GPU leg did not finish within 420 s"})
+            hard_exit = th.is_alive()
         dist.barrier(group=gloo)
 
     if rank != 0:
         if world > 1:
-            dist.barrier()
+            dist.barrier(group=gloo)      # host-side: rank 0 is busy with its CPU legs / printing
             dist.destroy_process_group()
         return
 
@@ -465,7 +480,11 @@ def run_b200(args):
                                          f"timed by --impl reference)"}
     print(json.dumps(out))
     if world > 1:
-        dist.barrier()
+        dist.barrier(group=gloo)
+    if hard_exit:            # a stuck side leg still holds CUDA calls: leave without running destructors
+        sys.stdout.flush()
+        os._exit(0)
+    if world > 1:
         dist.destroy_process_group()
 
 

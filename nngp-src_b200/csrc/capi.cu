@@ -105,6 +105,7 @@ struct nngp_handle {
   nngp_stats_t st;
   std::vector<EvRec> pending;
   std::vector<cudaEvent_t> ev_pool;
+  std::vector<cudaEvent_t> rep_events;   // no-timing events of replicate_state (recorded on this handle's copy stream)
 };
 
 namespace {
@@ -335,7 +336,7 @@ int run_gemm_rowdot(nngp_handle* h, const double* V, int64_t ldv, int64_t rows, 
 // Right-looking over W-wide outer panels (trailing SYRK with K = W on the DMMA core), left-looking
 // over the 64-wide sub-panels inside a panel (potf2 on the diagonal block, one-thread-per-row
 // forward substitution for the block column below it).
-// Outer panel width: 256 keeps the panel chain short for small N; for N >= 16384 the trailing SYRK
+// Outer panel width: 256 keeps the panel chain short for small N; for larger N the trailing SYRK
 // dominates and K = 512 runs closer to the DMMA peak (measured at N = 32768: 394 / 378 / 371 ms for
 // W = 256 / 384 / 512; at N = 8192: 13.8 / 14.5 / 15.2 ms).  NNGP_CHOL_W overrides.
 int chol_outer_width(int64_t N) {
@@ -345,7 +346,7 @@ int chol_outer_width(int64_t N) {
     return v >= NB ? (v / NB) * NB : 0;
   }();
   if (forced) return forced;
-  return N >= 16384 ? 512 : 256;
+  return N >= 4096 ? 512 : 256;   // (with the fused panel kernel: N = 4096 3.44 vs 3.54 ms, N = 8192 9.67 vs 9.96 ms)
 }
 
 // `R` = N + extra rows riding along below the matrix (see run_potrf).
@@ -850,7 +851,10 @@ int replicate_state(nngp_handle* h) {
       if (g > 0) ce = cudaStreamWaitEvent(st, ev[(size_t)g][(size_t)i], 0);   // item i has reached src
       if (ce == cudaSuccess) ce = copy_item(src, dst, i, st);
       cudaEvent_t e = nullptr;
-      if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+      if (ce == cudaSuccess) {   // events are kept on the source handle and reused by the next replication
+        if (!src->rep_events.empty()) { e = src->rep_events.back(); src->rep_events.pop_back(); }
+        else ce = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+      }
       if (ce == cudaSuccess) { ev[(size_t)g + 1][(size_t)i] = e; ce = cudaEventRecord(e, st); }
     }
   }
@@ -859,7 +863,8 @@ int replicate_state(nngp_handle* h) {
     cudaError_t e2 = cudaStreamSynchronize(chain[g]->copy_stream);
     if (ce == cudaSuccess) ce = e2;
   }
-  for (auto& v : ev) for (auto e : v) if (e) cudaEventDestroy(e);
+  for (size_t g = 1; g < ev.size(); ++g)       // ev[g] was recorded on chain[g - 1]'s stream (same device)
+    for (auto e : ev[g]) if (e) chain[g - 1]->rep_events.push_back(e);
   cudaSetDevice(h->device);
   if (ce != cudaSuccess) return fail(h, NNGP_ECUDA, "replicating the fitted state to the other GPUs failed: %s", cudaGetErrorString(ce));
   for (int g = 1; g < G; ++g) {
@@ -1060,6 +1065,7 @@ void nngp_destroy(nngp_handle* h) {
     release(*b);
   for (auto& r : h->pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : h->ev_pool) cudaEventDestroy(e);
+  for (auto e : h->rep_events) cudaEventDestroy(e);
   if (h->panel_stream) cudaStreamDestroy(h->panel_stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->stream) cudaStreamDestroy(h->stream);

@@ -141,6 +141,9 @@ __device__ __forceinline__ double rcp_newton(double x) {
   return fma(r, e, r);
 }
 
+// max(x, 0) for finite x through the sign bit (integer pipe); -0 and negative rounding residue become +0
+__device__ __forceinline__ double clamp_nonneg(double x) { return (__double2hiint(x) < 0) ? 0.0 : x; }
+
 __device__ __forceinline__ double atan2_pos(double s, double s2, double k) {
   constexpr double C[21] = {
     1.0,
@@ -166,9 +169,12 @@ __device__ __forceinline__ double atan2_pos(double s, double s2, double k) {
     1.2631178430477426e-05};
   const double half_pi = 1.57079632679489661923;
   const double pi = 3.14159265358979323846;
+  // The comparisons run on the integer pipe (bit patterns of non-negative doubles order like the values; the sign of
+  // k is its top bit): a DSETP would queue on the FP64 pipe this epilogue shares with the co-resident CTA's DMMAs.
   const double a = fabs(k);
   const double a2 = k * k;
-  const double mx2 = fmax(s2, a2);
+  const bool s_bigger = __double_as_longlong(s2) > __double_as_longlong(a2);
+  const double mx2 = s_bigger ? s2 : a2;
   const double t = (s * a) * rcp_newton(mx2);
   const double u = t * t;
   const double w = u * u;
@@ -178,9 +184,9 @@ __device__ __forceinline__ double atan2_pos(double s, double s2, double k) {
 #pragma unroll
   for (int i = 17; i >= 1; i -= 2) po = fma(po, w, C[i]);
   const double at = t * fma(u, po, pe);
-  const double th0 = (s2 > a2) ? (half_pi - at) : at;
-  const double th = (k < 0.0) ? (pi - th0) : th0;
-  return (mx2 == 0.0) ? half_pi : th;
+  const double th0 = s_bigger ? (half_pi - at) : at;
+  const double th = (__double2hiint(k) < 0) ? (pi - th0) : th0;
+  return (__double_as_longlong(mx2) == 0LL) ? half_pi : th;
 }
 
 // One ReLU arc-cosine step followed by the next Dense layer's affine map
@@ -189,7 +195,7 @@ __device__ __forceinline__ double atan2_pos(double s, double s2, double k) {
 //   k' = sw2 * ( s/(2 pi) + (1/2 - theta/(2 pi)) k ) + sb2
 __device__ __forceinline__ double arccos_step(double k, double q1, double q2, double sw2, double sb2) {
   const double inv_2pi = 0.15915494309189533577;
-  double s2 = fmax(q1 * q2 - k * k, 0.0);
+  double s2 = clamp_nonneg(q1 * q2 - k * k);
   double s = sqrt(s2);
   double theta = atan2_pos(s, s2, k);
   double dot_sigma = 0.5 - inv_2pi * theta;
@@ -202,7 +208,7 @@ __device__ __forceinline__ double arccos_step(double k, double q1, double q2, do
 // ([nt: Relu `ntk *= dot_sigma`, Dense `ntk = nngp + W_std^2 * ntk`]).
 __device__ __forceinline__ void arccos_step_ntk(double& k, double& ntk, double q1, double q2, double sw2, double sb2) {
   const double inv_2pi = 0.15915494309189533577;
-  double s2 = fmax(q1 * q2 - k * k, 0.0);
+  double s2 = clamp_nonneg(q1 * q2 - k * k);
   double s = sqrt(s2);
   double theta = atan2_pos(s, s2, k);
   double dot_sigma = 0.5 - inv_2pi * theta;
@@ -359,11 +365,12 @@ __device__ __forceinline__ void gram_epilogue(const double (&acc)[4][4][2], cons
         if (!p.ntk) {
           for (int s = 0; s < p.steps; ++s) {
 #pragma unroll
-            for (int j = 0; j < W; ++j) {
-              k[j] = arccos_step(k[j], qa, qb[j], p.sw2, p.sb2);
-              qb[j] = p.sw2 * (0.5 * qb[j]) + p.sb2;
+            for (int j = 0; j < W; ++j) k[j] = arccos_step(k[j], qa, qb[j], p.sw2, p.sb2);
+            if (s + 1 < p.steps) {              // the diagonals of the next layer (not needed after the last one)
+#pragma unroll
+              for (int j = 0; j < W; ++j) qb[j] = p.sw2 * (0.5 * qb[j]) + p.sb2;
+              qa = p.sw2 * (0.5 * qa) + p.sb2;
             }
-            qa = p.sw2 * (0.5 * qa) + p.sb2;
           }
         } else {
           double n[W];
@@ -371,11 +378,12 @@ __device__ __forceinline__ void gram_epilogue(const double (&acc)[4][4][2], cons
           for (int j = 0; j < W; ++j) n[j] = k[j];
           for (int s = 0; s < p.steps; ++s) {
 #pragma unroll
-            for (int j = 0; j < W; ++j) {
-              arccos_step_ntk(k[j], n[j], qa, qb[j], p.sw2, p.sb2);
-              qb[j] = p.sw2 * (0.5 * qb[j]) + p.sb2;
+            for (int j = 0; j < W; ++j) arccos_step_ntk(k[j], n[j], qa, qb[j], p.sw2, p.sb2);
+            if (s + 1 < p.steps) {
+#pragma unroll
+              for (int j = 0; j < W; ++j) qb[j] = p.sw2 * (0.5 * qb[j]) + p.sb2;
+              qa = p.sw2 * (0.5 * qa) + p.sb2;
             }
-            qa = p.sw2 * (0.5 * qa) + p.sb2;
           }
           if (p.C2) {
 #pragma unroll

@@ -1,5 +1,6 @@
-"""How the explicit 64 x 64 diagonal-block inverses of the solve behave when K + lambda*I is badly conditioned:
-CUDA path vs the CPU oracle (LAPACK substitution) for decreasing relative diag_reg.  GPU box only.
+"""How the explicit 64 x 64 diagonal-block inverses of the solve -- and, in latency mode, the explicit inverse factor
+L^-1 -- behave when K + lambda*I is badly conditioned: CUDA path vs the CPU oracle (LAPACK substitution) for
+decreasing relative diag_reg.  GPU box only.
     python tests/checks/illcond_report.py"""
 import json
 import sys
@@ -24,7 +25,13 @@ for reg in (1e-3, 1e-5, 1e-7, 1e-9):
         rm, rv = ref.predict(xte)
         k = oracle.kernel_fn(xtr)
         ev = np.linalg.eigvalsh(k + ref.lam * np.eye(3000))
+        hl = _lib.Handle(diag_reg=reg, latency_mode=True)
+        hl.fit(xtr, ytr)
+        kss = oracle.final_diag(oracle.layer0_diag(xte))
+        vl = np.concatenate([hl.predict(xte[a:b])[1] for a, b in ((0, 1), (1, 8), (8, 300), (300, 1000))])   # GEMV, split-K, tiled
         out.append({"diag_reg": reg, "cond": float(ev[-1] / ev[0]), "mean_rel": float(np.max(np.abs(m - rm)) / np.max(np.abs(rm))),
+                    "latency_mode_var_rel_to_kss": float(np.max(np.abs(vl - rv)) / np.max(kss)),
+                    "latency_mode_var_rel": float(np.max(np.abs(vl - rv) / np.abs(rv))),
                     "var_rel_to_kss": float(np.max(np.abs(v - rv)) / np.max(oracle.final_diag(oracle.layer0_diag(xte)))),
                     "var_rel": float(np.max(np.abs(v - rv) / np.abs(rv))), "min_var_over_kss": float(np.min(rv) / np.max(rv))})
     except Exception as e:  # noqa: BLE001
