@@ -346,7 +346,9 @@ int chol_outer_width(int64_t N) {
     return v >= NB ? (v / NB) * NB : 0;
   }();
   if (forced) return forced;
-  return N >= 4096 ? 512 : 256;   // (with the fused panel kernel: N = 4096 3.44 vs 3.54 ms, N = 8192 9.67 vs 9.96 ms)
+  // (with the fused panel kernel: N = 4096 3.44 vs 3.54 ms, N = 8192 9.67 vs 9.96 ms for W = 512 vs 256;
+  //  N = 32768: 356.0 / 353.9 / 352.0 ms for W = 512 / 768 / 1024)
+  return N >= 24576 ? 1024 : (N >= 4096 ? 512 : 256);
 }
 
 // `R` = N + extra rows riding along below the matrix (see run_potrf).
@@ -1124,7 +1126,15 @@ int nngp_kernel(nngp_handle* h, const double* x1, int64_t M, const double* x2, i
     bptr = h->kb.as<double>();
     qb = h->kqb.as<double>();
   }
-  CKR(run_gram(h, h->ka.as<double>(), ldx, M, h->kqa.as<double>(), bptr, ldx, Nn, qb, D, h->kout.as<double>(), ldo, 0));
+  // kernel_fn(x, None) is symmetric: compute the tiles at / below the diagonal only and mirror them (NNGP mode; the
+  // entries are bitwise symmetric anyway -- same products, same summation order).  'ntk' keeps the full square.
+  const bool sym = !x2 && h->cfg.kernel_type == 0 && M >= 4 * GEMM_BM;
+  CKR(run_gram(h, h->ka.as<double>(), ldx, M, h->kqa.as<double>(), bptr, ldx, Nn, qb, D, h->kout.as<double>(), ldo, sym ? 1 : 0));
+  if (sym) {
+    dim3 mg((unsigned)((M + 31) / 32), (unsigned)((M + 31) / 32));
+    mirror_lower_kernel<<<mg, dim3(32, 8), 0, h->stream>>>(h->kout.as<double>(), ldo, (int)M);
+    h->st.kernel_launches++;
+  }
   CKR(download(h, h->kout.as<double>(), M, Nn, ldo, k_out));
   int flags[2];
   CK(cudaMemcpyAsync(flags, h->flags.p, sizeof flags, cudaMemcpyDeviceToHost, h->stream));

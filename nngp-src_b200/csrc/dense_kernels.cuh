@@ -771,6 +771,24 @@ __global__ void transpose_kernel(const double* __restrict__ in, double* __restri
   }
 }
 
+// A[j][i] <- A[i][j] for i > j: fills the strict upper triangle of a symmetric matrix whose lower tiles were computed
+// (kernel_fn(x, None): the Gram kernel then skips the tiles above the diagonal).  32 x 32 tiles through shared memory,
+// one CTA per lower tile (bx <= by); grid (n/32, n/32), block (32, 8).
+__global__ void mirror_lower_kernel(double* __restrict__ A, long long ld, int n) {
+  __shared__ double tile[32][33];
+  if (blockIdx.x > blockIdx.y) return;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;     // source tile: rows r0.., columns c0.. (c0 <= r0)
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < n && c < n) tile[i][threadIdx.x] = A[(long long)r * ld + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = c0 + i, c = r0 + threadIdx.x;             // destination: rows c0.., columns r0..
+    if (r < n && c < n && c > r) A[(long long)r * ld + c] = tile[threadIdx.x][i];
+  }
+}
+
 // zero the strict upper triangle of an N x N row-major matrix (state export)
 __global__ void zero_upper_kernel(double* __restrict__ A, long long ld, int N) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -351,3 +351,18 @@ def test_nccl_broadcast_fit_gives_every_rank_the_same_bits():
                        capture_output=True, text=True, timeout=900, cwd=str(ROOT))
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-3000:])
     assert "NCCL_BROADCAST_OK" in r.stdout
+
+
+def test_symmetric_kernel_skips_upper_tiles_and_stays_bitwise_symmetric(lib, synth):
+    """kernel_fn(x, None) (train.py:216): only the tiles at / below the diagonal are computed, the rest is mirrored --
+    the result must be what the full rectangular computation kernel_fn(x, x) gives, bit for bit."""
+    x = synth.encodings(1500, 40, 4)
+    for depth in (2, 3):
+        h = lib.Handle(depth=depth, stats_level=2)
+        k_sym = h.kernel(x)
+        flops_sym = h.stats()["gram_flops"]
+        h.stats_reset()
+        k_full = h.kernel(x, x)
+        assert np.array_equal(k_sym, k_full) and np.array_equal(k_sym, k_sym.T)
+        assert flops_sym < 0.6 * h.stats()["gram_flops"]
+        assert relmax(k_sym, oracle.kernel_fn(x, None, depth)) < 1e-13
