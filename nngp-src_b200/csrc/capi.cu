@@ -28,6 +28,9 @@
 
 using namespace nngp;
 
+// (the fused panel kernel may ask for more shared memory than it uses, to keep an SM to itself: potrf_panel_fused)
+constexpr int PANEL_SMEM_MAX = 200 * 1024;
+
 namespace {
 
 thread_local std::string g_create_error;
@@ -394,6 +397,9 @@ int potrf_panel_fused(nngp_handle* h, double* A, int64_t ld, int64_t N, int64_t 
   int grid = (int)std::min<long long>(p.row_tiles, h->sm_count / 2);
   if (forced_grid > 0) grid = forced_grid;
   grid = (int)std::max<long long>(1, std::min<long long>(grid, total));
+  static const int forced_smem = [] { const char* e = getenv("NNGP_PANEL_SMEM"); return e ? atoi(e) : -1; }();
+  int panel_smem = TF_SMEM_BYTES;
+  if (forced_smem >= 0) panel_smem = std::min(std::max(panel_smem, forced_smem), PANEL_SMEM_MAX);
   // NNGP_PANEL_TRACE=1 (diagnostics): time stamps of the owner items of every panel -> stderr (synchronises!)
 #ifdef NNGP_PANEL_TRACE
   static const bool trace = [] { const char* e = getenv("NNGP_PANEL_TRACE"); return e && atoi(e) > 0; }();
@@ -406,7 +412,7 @@ int potrf_panel_fused(nngp_handle* h, double* A, int64_t ld, int64_t N, int64_t 
     CK(cudaMemsetAsync(tr_d, 0, (size_t)p.col_blocks * 10 * sizeof(unsigned long long), h->cur));
     p.trace = tr_d;
   }
-  potrf_panel_kernel<<<grid, GEMM_THREADS, TF_SMEM_BYTES, h->cur>>>(tmA, tmL, tmW, p);
+  potrf_panel_kernel<<<grid, GEMM_THREADS, panel_smem, h->cur>>>(tmA, tmL, tmW, p);
   CK(cudaGetLastError());
   h->st.kernel_launches++;
   if (trace) {
@@ -481,27 +487,52 @@ int run_potrf(nngp_handle* h, double* A, int64_t ld, int64_t N, int64_t extra, d
   };
   int rc = NNGP_OK;
   cudaError_t ce = cudaSuccess;
+  // NNGP_CHOL_TRACE=1 (diagnostics): device time line of every panel / (A) / (B) launch -> stderr (synchronises)
+  static const bool tl_on = [] { const char* e = getenv("NNGP_CHOL_TRACE"); return e && atoi(e) > 0; }();
+  struct Span { const char* what; int64_t j0; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  auto span_begin = [&](const char* what, int64_t j) { if (tl_on) { Span sp{what, j, nullptr, nullptr}; cudaEventCreate(&sp.a); cudaEventCreate(&sp.b); cudaEventRecord(sp.a, h->cur); spans.push_back(sp); } };
+  auto span_end = [&]() { if (tl_on) cudaEventRecord(spans.back().b, h->cur); };
   if (lookahead) ce = edge(ev_cols, h->stream, h->panel_stream);  // panel stream starts after the work queued so far
   for (int64_t j0 = 0; j0 < N && rc == NNGP_OK && ce == cudaSuccess; j0 += W) {
     const int64_t w = std::min<int64_t>(W, N - j0);
     const int64_t t0 = j0 + w;
     h->cur = lookahead ? h->panel_stream : h->stream;
+    span_begin("panel", j0);
     rc = potrf_panel(h, A, ld, N, R, j0, w, Winv);
+    span_end();
     if (rc != NNGP_OK || t0 >= N) break;
     if (lookahead) ce = edge(ev_panel, h->panel_stream, h->stream);
     h->cur = h->stream;
     const int64_t w2 = std::min<int64_t>(W, N - t0);
     const int64_t t1 = t0 + w2;
     // (A) next panel's columns: A[t0:R, t0:t1] (lower tiles) -= A[t0:R, j0:t0] * A[t0:t1, j0:t0]^T
+    span_begin("A", j0);
     rc = run_gemm_sub(h, Av, t0, j0, Av, t0, j0, R - t0, w2, w, A + t0 * ld + t0, ld, 1);
+    span_end();
     if (rc != NNGP_OK) break;
     if (lookahead && la_mode != 2 && ce == cudaSuccess) ce = edge(ev_cols, h->stream, h->panel_stream);
     // (B) the rest of the trailing matrix: A[t1:R, t1:N] (lower) -= A[t1:R, j0:t0] * A[t1:N, j0:t0]^T
+    span_begin("B", j0);
     if (t1 < N) rc = run_gemm_sub(h, Av, t1, j0, Av, t1, j0, R - t1, N - t1, w, A + t1 * ld + t1, ld, 1);
+    span_end();
     if (lookahead && la_mode == 2 && ce == cudaSuccess) ce = edge(ev_cols, h->stream, h->panel_stream);  // no overlap
   }
   if (lookahead && ce == cudaSuccess) ce = edge(ev_panel, h->panel_stream, h->stream);  // join
   h->cur = h->stream;
+  if (tl_on && !spans.empty()) {
+    cudaStreamSynchronize(h->stream);
+    if (h->panel_stream) cudaStreamSynchronize(h->panel_stream);
+    fprintf(stderr, "cholesky time line N=%lld W=%d (ms since the first panel's start): what j0 start end\n", (long long)N, W);
+    for (auto& sp : spans) {
+      float t0 = 0.f, t1 = 0.f;
+      cudaEventElapsedTime(&t0, spans[0].a, sp.a);
+      cudaEventElapsedTime(&t1, spans[0].a, sp.b);
+      fprintf(stderr, "  %-5s %6lld %8.3f %8.3f  (%.3f)\n", sp.what, (long long)sp.j0, t0, t1, t1 - t0);
+    }
+    for (auto& sp : spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    cudaGetLastError();
+  }
   h->ev_pool.push_back(ev_cols);
   h->ev_pool.push_back(ev_panel);
   if (ce != cudaSuccess) rc = fail(h, NNGP_ECUDA, "look-ahead event plumbing failed: %s", cudaGetErrorString(ce));
@@ -693,7 +724,8 @@ int run_inverse_variance(nngp_handle* h, const double* B, int64_t ldb, int64_t r
 }
 
 // out <- L^-T z  (blocked backward substitution; z is destroyed; reads L exactly once)
-int run_trsv_bwd(nngp_handle* h, const double* L, int64_t ld, int64_t N, double* z, double* out) {
+// (`Winv`: the inverses of L's 64 x 64 diagonal blocks, as the factorisation / run_trtri_diag leave them in h->Linv)
+int run_trsv_bwd(nngp_handle* h, const double* L, int64_t ld, int64_t N, double* z, double* out, const double* Winv) {
   const int64_t nblk = (N + NB - 1) / NB;
   static const bool steps = [] { const char* e = getenv("NNGP_TRSV"); return e && !strcmp(e, "steps"); }();
   if (!steps) {  // one persistent launch: column slices of SW, one CTA each, all co-resident (grid <= #SMs)
@@ -711,7 +743,7 @@ int run_trsv_bwd(nngp_handle* h, const double* L, int64_t ld, int64_t N, double*
       int Ni = (int)N, swi = (int)sw;
       const double* zc = z;
       int* fl = h->sync_ints.as<int>();
-      void* args[] = {(void*)&L, (void*)&ld, (void*)&Ni, (void*)&swi, (void*)&zc, (void*)&out, (void*)&fl};
+      void* args[] = {(void*)&L, (void*)&ld, (void*)&Ni, (void*)&swi, (void*)&zc, (void*)&out, (void*)&fl, (void*)&Winv};
       cudaError_t le = cudaLaunchCooperativeKernel((const void*)trsv_bwd_persistent_kernel, dim3((unsigned)grid),
                                                    dim3(TRSVP_THREADS), args, smem, h->stream);
       if (le == cudaSuccess) {
@@ -975,7 +1007,7 @@ static int create_single(const nngp_config* cfg, nngp_handle** out) {
   if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(trsm_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM_BYTES);
   if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(trsm_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM_BYTES);
   if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(gemm_nt_kernel<EPI_DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
-  if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SMEM_BYTES);
+  if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM_MAX);
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
     fail(h, NNGP_ECUDA, "cudaFuncSetAttribute(max dynamic smem) failed: %s",
          cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
@@ -1202,7 +1234,7 @@ static int fit_impl(nngp_handle* h, const double* x_train, const double* y_train
   h->st.kernel_launches++;
   CKR(ensure(h, h->zkeep, (size_t)N * sizeof(double)));
   CK(cudaMemcpyAsync(h->zkeep.p, L + N * h->ldl, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-  CKR(run_trsv_bwd(h, L, h->ldl, N, L + N * h->ldl, alpha));  // alpha = L^-T z
+  CKR(run_trsv_bwd(h, L, h->ldl, N, L + N * h->ldl, alpha, h->Linv.as<double>()));  // alpha = L^-T z
   if (ntk) {  // M = L^-1 K_dd L^-T : two row-wise solves around a transpose (M is symmetric)
     double* Kd = h->Kdd.as<double>();
     double* Mm = h->Mmat.as<double>();
@@ -1406,7 +1438,7 @@ static int append_incremental(nngp_handle* h, int64_t M) {
   lml_terms_kernel<<<1, 1024, 0, h->stream>>>(Ln, ldn, (int)Nn, zrow, h->lam_d.as<double>() + 1);
   h->st.kernel_launches++;
   CK(cudaMemcpyAsync(h->zkeep.p, zrow, (size_t)Nn * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-  CKR(run_trsv_bwd(h, Ln, ldn, Nn, zrow, h->alpha.as<double>()));
+  CKR(run_trsv_bwd(h, Ln, ldn, Nn, zrow, h->alpha.as<double>(), h->Linv.as<double>()));
   t_solve.stop();
   t_total.stop();
 

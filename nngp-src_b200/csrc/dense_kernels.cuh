@@ -477,11 +477,12 @@ __global__ void __launch_bounds__(TRSV_THREADS) trsv_bwd_step_kernel(const doubl
 constexpr int TRSVP_THREADS = 256;
 __global__ void __launch_bounds__(TRSVP_THREADS) trsv_bwd_persistent_kernel(const double* __restrict__ L, long long ld,
                                                                             int N, int SW, const double* __restrict__ z,
-                                                                            double* __restrict__ aout, int* flags) {
+                                                                            double* __restrict__ aout, int* flags,
+                                                                            const double* __restrict__ Winv) {
   extern __shared__ double sm[];
-  double(*Ls)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(sm);   // [64][65]
+  double(*red)[NB] = reinterpret_cast<double(*)[NB]>(sm);            // [4][64] partial sums of the block solve
   double* as = sm + NB * (NB + 1);                                   // [64]
-  double* rd = as + NB;                                              // [64]
+  double* rd = as + NB;                                              // [64] (unused since the block solve is a product)
   double* zs = rd + NB;                                              // [SW]
   const int tid = threadIdx.x;
   // slices are handed out back to front: the CTAs scheduled first own the blocks that are solved first, so a CTA
@@ -497,22 +498,23 @@ __global__ void __launch_bounds__(TRSVP_THREADS) trsv_bwd_persistent_kernel(cons
     const int n = min(NB, N - j0);
     const bool owner = j0 >= c0 && j0 < c1;
     if (owner) {
-      load_diag_block(L + (long long)j0 * ld + j0, ld, n, Ls, rd);
-      if (tid < NB) as[tid] = (tid < n) ? zs[j0 - c0 + tid] : 0.0;
-      __syncthreads();
-      if (tid < 32) {
-        const int lane = tid;
-        double y0 = as[lane], y1 = as[lane + 32];
-        for (int k = NB - 1; k >= 0; --k) {
-          const double num = __shfl_sync(0xffffffffu, (k < 32) ? y0 : y1, k & 31);
-          const double ak = num * rd[k];
-          if (lane == (k & 31)) { if (k < 32) y0 = ak; else y1 = ak; }
-          if (lane < k) y0 = fma(-Ls[k][lane], ak, y0);
-          if (lane + 32 < k) y1 = fma(-Ls[k][lane + 32], ak, y1);
-        }
-        as[lane] = y0;
-        as[lane + 32] = y1;
+      // L_JJ^T a_J = r_J  as  a_J = W_J^T r_J  with the block inverse the factorisation left in Winv (the operand the
+      // prediction solves use): 16 multiply-adds per thread and one barrier instead of a 64-step substitution chain
+      // (3 us of every block step were this solve; the chain of N/64 steps is what bounds the kernel).
+      const int i = tid & 63, part = tid >> 6;
+      const double* wj = Winv + (long long)j0 * NB;                  // 64 x 64 row-major, identity padded
+      double w[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) w[u] = __ldcg(wj + (long long)(part * 16 + u) * NB + i);
+      double acc = 0.0;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int k = part * 16 + u;
+        acc = fma(w[u], (k < n) ? zs[j0 - c0 + k] : 0.0, acc);       // a_i = sum_k W[k][i] r[k]   (W lower: k >= i)
       }
+      red[part][i] = acc;
+      __syncthreads();
+      if (tid < NB) as[tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
       __syncthreads();
       if (tid < n) aout[j0 + tid] = as[tid];
       __threadfence();
