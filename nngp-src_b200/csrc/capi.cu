@@ -1369,6 +1369,40 @@ int nngp_reserve(nngp_handle* h, int64_t n_train_max, int64_t dim, int64_t n_tes
     CKR(ensure(h, h->var_d, (size_t)T * 8));
     for (DevBuf* b : {&h->sel_mean, &h->sel_var, &h->sel_score, &h->sel_key}) CKR(ensure(h, *b, (size_t)T * 8));
   }
+  // replicas (cfg.n_gpus > 1): the state buffers at full size and the workspace for this GPU's share of the rows, so
+  // that a growing training set does not make every replica free and reallocate multi-GB buffers round after round
+  const int G = 1 + (int)h->peers.size();
+  for (auto* p : h->peers) {
+    CK(cudaSetDevice(p->device));
+    drop_fit(p);
+    int rc = ensure(p, p->X, (size_t)N * ldx * 8);
+    if (rc == NNGP_OK) rc = ensure(p, p->q, (size_t)N * 8);
+    if (rc == NNGP_OK) rc = ensure(p, p->L, (size_t)(N + 1) * ldl * 8);
+    if (rc == NNGP_OK) rc = ensure(p, p->alpha, (size_t)ldl * 8);
+    if (rc == NNGP_OK) rc = ensure(p, p->Linv, (size_t)round_up(N, NB) * NB * 8);
+    if (rc == NNGP_OK && h->cfg.latency_mode && h->cfg.kernel_type == 0) rc = ensure(p, p->Linvfull, (size_t)N * ldl * 8);
+    if (rc == NNGP_OK && T > 0) {
+      const int64_t Tg = (T + G - 1) / G + 1;
+      int64_t cap_rows = p->cfg.max_block_bytes / (ldl * 8);
+      cap_rows = std::min<int64_t>(std::max<int64_t>(cap_rows, GEMM_BM), 65535LL * GEMM_BM);
+      const int64_t nblocks = (Tg + cap_rows - 1) / cap_rows;
+      const int64_t TB = std::min<int64_t>(round_up(Tg, 2), round_up((Tg + nblocks - 1) / nblocks, GEMM_BM));
+      const int64_t col_tiles = (N + GEMM_BN - 1) / GEMM_BN;
+      rc = ensure(p, p->xt, (size_t)TB * ldx * 8);
+      if (rc == NNGP_OK) rc = ensure(p, p->qt, (size_t)TB * 8);
+      if (rc == NNGP_OK) rc = ensure(p, p->kss, (size_t)TB * 8);
+      if (rc == NNGP_OK) rc = ensure(p, p->blk, (size_t)TB * ldl * 8);
+      if (rc == NNGP_OK) rc = ensure(p, p->mean_partial, (size_t)TB * 2 * col_tiles * 8);
+      if (rc == NNGP_OK) rc = ensure(p, p->mean_d, (size_t)Tg * 8);
+      if (rc == NNGP_OK) rc = ensure(p, p->var_d, (size_t)Tg * 8);
+    }
+    if (rc != NNGP_OK) {
+      h->err = "replica on device " + std::to_string(p->device) + ": " + p->err;
+      cudaSetDevice(h->device);
+      return rc;
+    }
+  }
+  if (G > 1) CK(cudaSetDevice(h->device));
   return NNGP_OK;
 }
 
