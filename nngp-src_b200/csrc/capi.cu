@@ -408,15 +408,15 @@ int potrf_panel_fused(nngp_handle* h, double* A, int64_t ld, int64_t N, int64_t 
 #endif
   unsigned long long* tr_d = nullptr;
   if (trace) {
-    CK(cudaMalloc(&tr_d, (size_t)p.col_blocks * 10 * sizeof(unsigned long long)));
-    CK(cudaMemsetAsync(tr_d, 0, (size_t)p.col_blocks * 10 * sizeof(unsigned long long), h->cur));
+    CK(cudaMalloc(&tr_d, (size_t)p.col_blocks * 18 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(tr_d, 0, (size_t)p.col_blocks * 18 * sizeof(unsigned long long), h->cur));
     p.trace = tr_d;
   }
   potrf_panel_kernel<<<grid, GEMM_THREADS, panel_smem, h->cur>>>(tmA, tmL, tmW, p);
   CK(cudaGetLastError());
   h->st.kernel_launches++;
   if (trace) {
-    std::vector<unsigned long long> tr((size_t)p.col_blocks * 10);
+    std::vector<unsigned long long> tr((size_t)p.col_blocks * 18);
     CK(cudaStreamSynchronize(h->cur));
     CK(cudaMemcpy(tr.data(), tr_d, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     cudaFree(tr_d);
@@ -426,6 +426,10 @@ int potrf_panel_fused(nngp_handle* h, double* A, int64_t ld, int64_t N, int64_t 
     for (int J = 0; J < p.col_blocks; ++J) {
       fprintf(stderr, "  J=%d:", J);
       for (int k = 0; k < 9; ++k) fprintf(stderr, " %8.2f", tr[(size_t)J * 10 + k] ? (double)(tr[(size_t)J * 10 + k] - t00) / 1e3 : -1.0);
+      const unsigned long long* pt = tr.data() + (size_t)p.col_blocks * 10 + (size_t)J * 8;   // inside potf2_64_block
+      fprintf(stderr, "   | potf2: loaded %.2f; micro-panel 0: A %.2f B %.2f C %.2f; 1: A %.2f B %.2f C %.2f; factor done %.2f",
+              (double)(pt[1] - t00) / 1e3, (double)(pt[2] - t00) / 1e3, (double)(pt[3] - t00) / 1e3, (double)(pt[4] - t00) / 1e3,
+              (double)(pt[5] - t00) / 1e3, (double)(pt[6] - t00) / 1e3, (double)(pt[7] - t00) / 1e3, (double)(pt[0] - t00) / 1e3);
       fprintf(stderr, "\n");
     }
   }

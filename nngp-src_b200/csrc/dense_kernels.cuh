@@ -205,6 +205,9 @@ __device__ __forceinline__ int potf2_64_block(double* __restrict__ A, long long 
     }
   if (tid < 2) s_bad[tid] = 0;
   __syncthreads();
+#ifdef NNGP_PANEL_TRACE
+  if (trace != nullptr && tid == 0) trace[1] = global_timer_ns();   // block loaded
+#endif
   const int nblk = (n + 3) >> 2;
   for (int jb = 0; jb < nblk; ++jb) {
     const int buf = jb & 1;
@@ -234,6 +237,9 @@ __device__ __forceinline__ int potf2_64_block(double* __restrict__ A, long long 
       if (badj) s_bad[buf] = badj;
     }
     __syncthreads();
+#ifdef NNGP_PANEL_TRACE
+    if (trace != nullptr && tid == 0 && jb < 2) trace[2 + 3 * jb] = global_timer_ns();      // A done
+#endif
     if (s_bad[buf]) {  // CTA-uniform exit
       if (tid == 0) atomicCAS(info, 0, pivot0 + s_bad[buf]);
       return s_bad[buf];
@@ -261,6 +267,9 @@ __device__ __forceinline__ int potf2_64_block(double* __restrict__ A, long long 
         for (int ja = 0; ja < 4; ++ja) P[buf][ty * 4 + a][ja] = v[a][ja];
     }
     __syncthreads();
+#ifdef NNGP_PANEL_TRACE
+    if (trace != nullptr && tid == 0 && jb < 2) trace[3 + 3 * jb] = global_timer_ns();      // B done
+#endif
     if (tx > jb && ty >= tx) {  // C: trailing blocks (lower part), four rank-1 updates in column order
 #pragma unroll
       for (int ja = 0; ja < 4; ++ja) {
@@ -277,6 +286,9 @@ __device__ __forceinline__ int potf2_64_block(double* __restrict__ A, long long 
     }
     // no barrier here: step A of the next micro-panel writes the OTHER buffer, and its readers (steps B / C of the
     // micro-panel before this one) are behind this iteration's first barrier
+#ifdef NNGP_PANEL_TRACE
+    if (trace != nullptr && tid == 0 && jb < 2) trace[4 + 3 * jb] = global_timer_ns();      // C done (thread 0's view)
+#endif
   }
 #pragma unroll
   for (int a = 0; a < 4; ++a)
@@ -285,7 +297,9 @@ __device__ __forceinline__ int potf2_64_block(double* __restrict__ A, long long 
       const int r = ty * 4 + a, c = tx * 4 + b;
       if (r < n && c <= r) A[(long long)r * ld + c] = v[a][b];
     }
-  if (trace != nullptr && tid == 0) trace[0] = global_timer_ns();   // (debug builds of the panel kernel: factor done)
+#ifdef NNGP_PANEL_TRACE
+  if (trace != nullptr && tid == 0) { trace[0] = global_timer_ns(); }   // factor done
+#endif
   if (Winv != nullptr) {
     double (*Ls)[NB + 1] = sm.Ls;
 #pragma unroll

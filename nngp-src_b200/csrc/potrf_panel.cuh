@@ -182,7 +182,11 @@ potrf_panel_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       Potf2Smem& psm = *reinterpret_cast<Potf2Smem*>(ring);
       stamp(2);
       potf2_64_block(P0 + (long long)col0 * p.ld + col0, p.ld, nb, p.j0 + col0, p.info,
-                     p.Winv + (long long)(p.j0 + col0) * NB, psm, tr != nullptr ? tr + 3 : nullptr);
+                     p.Winv + (long long)(p.j0 + col0) * NB, psm,
+                     tr != nullptr ? p.trace + p.col_blocks * 10 + J * 8 : nullptr);
+#ifdef NNGP_PANEL_TRACE
+      if (tr != nullptr && tid == 0) tr[3] = p.trace[p.col_blocks * 10 + J * 8];   // factor done
+#endif
       stamp(4);
       __threadfence();            // L_JJ and W_J (generic stores) ...
       fence_proxy_async_all();    // ... before the TMA loads of the CTAs that acquire the flag

@@ -38,11 +38,30 @@ def nvcc_path():
     return cand if Path(cand).exists() else shutil.which("nvcc")
 
 
+def library_id(path=None):
+    """Build id embedded in a library file (read without loading it), or None."""
+    try:
+        data = Path(path or LIB).read_bytes()
+    except OSError:
+        return None
+    i = data.find(b"nngp-build-id:")
+    return data[i + 14:i + 30].decode("ascii", "replace") if i >= 0 else None
+
+
 def build(extra_flags=()) -> str:
-    """Compile for sm_100a (nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ...). Returns the build id."""
+    """Compile for sm_100a (nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ...). Returns the build id.
+    Serialised across processes (8 torchrun ranks loading a stale library must not run 8 compilers into one file):
+    whoever gets the lock second finds the library already up to date."""
     if nvcc_path() is None:
         raise ImportError("nngp_b200: libnngp_b200.so must be (re)built but nvcc is not available")
-    subprocess.run(["bash", str(PKG / "build.sh"), *extra_flags], check=True)
+    import fcntl
+    with open(PKG / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if extra_flags or library_id() != source_hash():
+                subprocess.run(["bash", str(PKG / "build.sh"), *extra_flags], check=True)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return source_hash()
 
 

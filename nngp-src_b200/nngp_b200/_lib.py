@@ -126,14 +126,8 @@ def load() -> C.CDLL:
 
 
 def built_id(path=None) -> str | None:
-    """nngp_build_id() of a library file, read without loading it into this process (it is scanned for the
-    marker the build embeds), or None."""
-    try:
-        data = Path(path or LIB_PATH).read_bytes()
-    except OSError:
-        return None
-    i = data.find(b"nngp-build-id:")
-    return data[i + 14:i + 30].decode("ascii", "replace") if i >= 0 else None
+    """nngp_build_id() of a library file, read without loading it into this process, or None."""
+    return _build.library_id(path or LIB_PATH)
 
 
 def build_id() -> str:
