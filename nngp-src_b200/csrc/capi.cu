@@ -388,13 +388,16 @@ int potrf_panel_fused(nngp_handle* h, double* A, int64_t ld, int64_t N, int64_t 
   CKR(get_tmap(h, A, R, N, ld, GEMM_BM, &tmA));
   CKR(get_tmap(h, A, R, N, ld, GEMM_BN, &tmL));
   CKR(get_tmap(h, Winv, round_up(N, NB), NB, NB, GEMM_BN, &tmW));
-  // Grid: one CTA per row tile, but no more than a quarter of the GPU's CTA slots.  The kernel's CTAs spend most of
+  // Grid: a few CTAs per row tile, but no more than a quarter of the GPU's CTA slots.  The kernel's CTAs spend most of
   // their life waiting for the owner's potf2; every slot they hold is a slot the trailing update running beside
   // them (look-ahead) cannot use -- with 2 x #SMs spinning CTAs the overlap was gone (measured: 11.0 ms at N = 8192,
   // no better than the launch-per-step chain).  NNGP_PANEL_GRID overrides (A/B runs).
   static const int forced_grid = [] { const char* e = getenv("NNGP_PANEL_GRID"); return e ? atoi(e) : 0; }();
   const long long total = (long long)p.row_tiles * p.col_blocks;
-  int grid = (int)std::min<long long>(p.row_tiles, h->sm_count / 2);
+  // (3 CTAs per row tile: the extra ones claim the row tile's NEXT column blocks early and work through the k-tiles
+  //  that already exist while the owner is still factoring -- N = 4096: 3.45 -> 3.28 ms, 8192: 9.65 -> 9.50 ms)
+  static const int grid_mult = [] { const char* e = getenv("NNGP_PANEL_GRID_MULT"); return e ? std::max(1, atoi(e)) : 3; }();
+  int grid = (int)std::min<long long>((long long)p.row_tiles * grid_mult, h->sm_count / 2);
   if (forced_grid > 0) grid = forced_grid;
   grid = (int)std::max<long long>(1, std::min<long long>(grid, total));
   static const int forced_smem = [] { const char* e = getenv("NNGP_PANEL_SMEM"); return e ? atoi(e) : -1; }();
@@ -427,7 +430,7 @@ int potrf_panel_fused(nngp_handle* h, double* A, int64_t ld, int64_t N, int64_t 
       fprintf(stderr, "  J=%d:", J);
       for (int k = 0; k < 9; ++k) fprintf(stderr, " %8.2f", tr[(size_t)J * 10 + k] ? (double)(tr[(size_t)J * 10 + k] - t00) / 1e3 : -1.0);
       const unsigned long long* pt = tr.data() + (size_t)p.col_blocks * 10 + (size_t)J * 8;   // inside potf2_64_block
-      fprintf(stderr, "   | potf2: loaded %.2f; micro-panel 0: A %.2f B %.2f C %.2f; 1: A %.2f B %.2f C %.2f; factor done %.2f",
+      fprintf(stderr, "   | potf2: loaded %.2f; micro-panel 8: A %.2f B %.2f C %.2f; 9: A %.2f B %.2f C %.2f; factor done %.2f",
               (double)(pt[1] - t00) / 1e3, (double)(pt[2] - t00) / 1e3, (double)(pt[3] - t00) / 1e3, (double)(pt[4] - t00) / 1e3,
               (double)(pt[5] - t00) / 1e3, (double)(pt[6] - t00) / 1e3, (double)(pt[7] - t00) / 1e3, (double)(pt[0] - t00) / 1e3);
       fprintf(stderr, "\n");

@@ -209,36 +209,44 @@ __device__ __forceinline__ int potf2_64_block(double* __restrict__ A, long long 
   if (trace != nullptr && tid == 0) trace[1] = global_timer_ns();   // block loaded
 #endif
   const int nblk = (n + 3) >> 2;
+  // A(jb): the thread that owns diagonal block jb factors its 4 x 4 block in registers and publishes it (buffer jb & 1)
+  auto factor_diag = [&](int jb) {
+    const int buf = jb & 1;
+    int badj = 0;
+#pragma unroll
+    for (int ja = 0; ja < 4; ++ja) {
+      const double d = v[ja][ja];
+      if (!(d > 0.0) && badj == 0 && jb * 4 + ja < n) badj = jb * 4 + ja + 1;  // also catches NaN
+      const double rinv = rsqrt(d);
+      Rinv[buf][ja] = rinv;
+      double l[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) l[a] = (a > ja) ? v[a][ja] * rinv : 0.0;
+      v[ja][ja] = d * rinv;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        if (a > ja) v[a][ja] = l[a];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) v[a][b] = fma(-l[a], l[b], v[a][b]);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) Ld[buf][a][b] = v[a][b];
+    if (badj) s_bad[buf] = badj;
+  };
+  // Schedule: A(0); then per micro-panel  B(jb) | barrier | C(jb) with A(jb+1) folded in | barrier.  The 4 x 4 factor
+  // of the NEXT diagonal block -- four dependent rsqrt-scale-update steps on one thread, the longest phase -- runs
+  // right after that thread's own rank-4 update, beside the other threads' updates, instead of as a phase of its own
+  // (2 barriers per micro-panel as before, but a third less on the critical path).  Per element the operations and
+  // their order are unchanged: same bits.
+  if (ty == 0 && tx == 0) factor_diag(0);
+  __syncthreads();
   for (int jb = 0; jb < nblk; ++jb) {
     const int buf = jb & 1;
-    if (ty == jb && tx == jb) {  // A: the diagonal block
-      int badj = 0;
-#pragma unroll
-      for (int ja = 0; ja < 4; ++ja) {
-        const double d = v[ja][ja];
-        if (!(d > 0.0) && badj == 0 && jb * 4 + ja < n) badj = jb * 4 + ja + 1;  // also catches NaN
-        const double rinv = rsqrt(d);
-        Rinv[buf][ja] = rinv;
-        double l[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) l[a] = (a > ja) ? v[a][ja] * rinv : 0.0;
-        v[ja][ja] = d * rinv;
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          if (a > ja) v[a][ja] = l[a];
-#pragma unroll
-          for (int b = 0; b < 4; ++b) v[a][b] = fma(-l[a], l[b], v[a][b]);
-        }
-      }
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) Ld[buf][a][b] = v[a][b];
-      if (badj) s_bad[buf] = badj;
-    }
-    __syncthreads();
 #ifdef NNGP_PANEL_TRACE
-    if (trace != nullptr && tid == 0 && jb < 2) trace[2 + 3 * jb] = global_timer_ns();      // A done
+    if (trace != nullptr && tid == 0 && (jb == 8 || jb == 9)) trace[2 + 3 * (jb - 8)] = global_timer_ns();      // A(jb) visible
 #endif
     if (s_bad[buf]) {  // CTA-uniform exit
       if (tid == 0) atomicCAS(info, 0, pivot0 + s_bad[buf]);
@@ -268,7 +276,7 @@ __device__ __forceinline__ int potf2_64_block(double* __restrict__ A, long long 
     }
     __syncthreads();
 #ifdef NNGP_PANEL_TRACE
-    if (trace != nullptr && tid == 0 && jb < 2) trace[3 + 3 * jb] = global_timer_ns();      // B done
+    if (trace != nullptr && tid == 0 && (jb == 8 || jb == 9)) trace[3 + 3 * (jb - 8)] = global_timer_ns();      // B done
 #endif
     if (tx > jb && ty >= tx) {  // C: trailing blocks (lower part), four rank-1 updates in column order
 #pragma unroll
@@ -283,11 +291,11 @@ __device__ __forceinline__ int potf2_64_block(double* __restrict__ A, long long 
 #pragma unroll
           for (int b = 0; b < 4; ++b) v[a][b] = fma(-lr[a], lc[b], v[a][b]);
       }
+      if (tx == jb + 1 && ty == jb + 1 && jb + 1 < nblk) factor_diag(jb + 1);   // A(jb+1), into the OTHER buffer
     }
-    // no barrier here: step A of the next micro-panel writes the OTHER buffer, and its readers (steps B / C of the
-    // micro-panel before this one) are behind this iteration's first barrier
+    __syncthreads();
 #ifdef NNGP_PANEL_TRACE
-    if (trace != nullptr && tid == 0 && jb < 2) trace[4 + 3 * jb] = global_timer_ns();      // C done (thread 0's view)
+    if (trace != nullptr && tid == 0 && (jb == 8 || jb == 9)) trace[4 + 3 * (jb - 8)] = global_timer_ns();      // C + A(jb+1) done
 #endif
   }
 #pragma unroll

@@ -45,3 +45,23 @@ def test_b200_arm_fails_loudly_without_gpu():
     r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, timeout=600, cwd=str(ROOT))
     assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+
+
+def test_reference_arm_under_torchrun_only_rank0_works_and_prints():
+    """Contract: launched like the B200 arm (torch.distributed.run, N ranks), rank 0 alone runs the CPU arm and prints
+    ONE line; the other ranks exit 0 without work."""
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(ROOT / "bench.py"),
+                        "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", "--workload", "c2"],
+                       capture_output=True, text=True, timeout=900, cwd=str(ROOT))
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip().startswith("{")]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and "x2" in d["config"]["parallelism"]
+    cb = d["cpu_baseline"]
+    assert cb["blas_threads"] in (-1, cb["cores"]), cb      # torchrun's OMP_NUM_THREADS=1 must not reach OpenBLAS
