@@ -35,6 +35,7 @@ extern "C" {
 
 #define NNGP_B200_ABI_VERSION 5
 #define NNGP_MAX_GPUS 8
+#define NNGP_MAX_LAYERS 16
 
 #if defined(__GNUC__)
 #define NNGP_API __attribute__((visibility("default")))
@@ -81,6 +82,11 @@ typedef struct nngp_config {
                                  prediction batches (the serving case, estimator.py:42-62: a few query lines per
                                  call) run as a dependency-free triangular GEMM on it instead of the substitution
                                  chain.  Same posterior to rounding (not bitwise the substitution's); default 0.     */
+  int32_t per_layer;          /* 1: Dense layer l (0-based, l < depth <= NNGP_MAX_LAYERS) uses sigma_w_layers[l] /
+                                 sigma_b_layers[l] instead of the uniform sigma_w / sigma_b -- stax.serial chains whose
+                                 Dense layers differ in W_std / b_std [nt allows it; the reference never does]          */
+  double sigma_w_layers[NNGP_MAX_LAYERS];
+  double sigma_b_layers[NNGP_MAX_LAYERS];
 } nngp_config;
 
 /* Per-stage device timings (CUDA events on the handle's stream) and work counters,

@@ -59,6 +59,7 @@ inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
 struct nngp_handle {
   nngp_config cfg;
+  double lsw2[NNGP_MAX_LAYERS], lsb2[NNGP_MAX_LAYERS];   // sigma_w^2 / sigma_b^2 of Dense layer l (uniform: all alike)
   int device = 0;
   // cfg.n_gpus > 1: replicas of the fitted state on the other GPUs (each a complete single-GPU handle with its own
   // streams and workspace; nngp_predict runs them on one host thread each).  `owner` is set on a replica.
@@ -304,8 +305,11 @@ int run_gram(nngp_handle* h, const double* A, int64_t lda, int64_t M, const doub
   p.ktiles = (int)((D + GEMM_BK - 1) / GEMM_BK);
   p.C = out; p.ldc = ldo; p.lower = lower;
   p.q1 = qa; p.q2 = qb;
-  const double sw2 = h->cfg.sigma_w * h->cfg.sigma_w, sb2 = h->cfg.sigma_b * h->cfg.sigma_b;
-  p.scale = sw2 / (double)D; p.sw2 = sw2; p.sb2 = sb2; p.steps = h->cfg.depth - 1;
+  p.scale = h->lsw2[0] / (double)D; p.sb2 = h->lsb2[0]; p.steps = h->cfg.depth - 1;
+  for (int i = 0; i < GEMM_MAX_LAYERS; ++i) {      // step s is followed by Dense layer s + 1
+    p.lsw2[i] = h->lsw2[std::min(i + 1, NNGP_MAX_LAYERS - 1)];
+    p.lsb2[i] = h->lsb2[std::min(i + 1, NNGP_MAX_LAYERS - 1)];
+  }
   MatView a{A, M, D, lda}, b{B, N, D, ldb};
   // the flop counter must use the true D, not the padded k extent
   const double before = h->st.gram_flops;
@@ -959,6 +963,13 @@ static int create_single(const nngp_config* cfg, nngp_handle** out) {
     return fail(h, NNGP_EINVAL, "nngp_create: kernel_type must be 0 (nngp) or 1 (ntk)");
   if (!(cfg->sigma_w > 0.0) || !(cfg->sigma_b >= 0.0) || !(cfg->diag_reg >= 0.0))
     return fail(h, NNGP_EINVAL, "nngp_create: need sigma_w > 0, sigma_b >= 0, diag_reg >= 0");
+  if (cfg->per_layer) {
+    if (cfg->depth > NNGP_MAX_LAYERS)
+      return fail(h, NNGP_EINVAL, "nngp_create: per-layer sigmas support at most %d Dense layers (depth=%d)", NNGP_MAX_LAYERS, cfg->depth);
+    for (int l = 0; l < cfg->depth; ++l)
+      if (!(cfg->sigma_w_layers[l] > 0.0) || !(cfg->sigma_b_layers[l] >= 0.0))
+        return fail(h, NNGP_EINVAL, "nngp_create: layer %d needs sigma_w > 0, sigma_b >= 0", l);
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();
@@ -975,6 +986,13 @@ static int create_single(const nngp_config* cfg, nngp_handle** out) {
                 prop.major, prop.minor);
   nngp_handle* nh = new nngp_handle();
   nh->cfg = *cfg;
+  for (int l = 0; l < NNGP_MAX_LAYERS; ++l) {
+    const int ll = std::min(l, std::max(cfg->depth - 1, 0));
+    const double w = cfg->per_layer ? cfg->sigma_w_layers[ll] : cfg->sigma_w;
+    const double b = cfg->per_layer ? cfg->sigma_b_layers[ll] : cfg->sigma_b;
+    nh->lsw2[l] = w * w;
+    nh->lsb2[l] = b * b;
+  }
   if (nh->cfg.max_block_bytes <= 0) nh->cfg.max_block_bytes = (int64_t)32 << 30;
   nh->device = dev;
   nh->sm_count = prop.multiProcessorCount;
@@ -1144,7 +1162,7 @@ int nngp_kernel(nngp_handle* h, const double* x1, int64_t M, const double* x2, i
   if (M > 65535LL * GEMM_BM || Nn > 0x7fffffffLL || D > 0x7fffffffLL)
     return fail(h, NNGP_EINVAL, "nngp_kernel: shape too large for one call");
   const int64_t ldx = round_up(D, 2), ldo = round_up(Nn, 2);
-  const double sw2 = h->cfg.sigma_w * h->cfg.sigma_w, sb2 = h->cfg.sigma_b * h->cfg.sigma_b;
+  const double sw2 = h->lsw2[0], sb2 = h->lsb2[0];   // first Dense layer
   CKR(ensure(h, h->ka, (size_t)M * ldx * 8));
   CKR(ensure(h, h->kqa, (size_t)M * 8));
   CKR(ensure(h, h->kout, (size_t)M * ldo * 8));
@@ -1199,7 +1217,7 @@ static int fit_impl(nngp_handle* h, const double* x_train, const double* y_train
   CKR(bind_device(h));
   drop_fit(h);
   CKR(alloc_state(h, N, D));
-  const double sw2 = h->cfg.sigma_w * h->cfg.sigma_w, sb2 = h->cfg.sigma_b * h->cfg.sigma_b;
+  const double sw2 = h->lsw2[0], sb2 = h->lsb2[0];   // first Dense layer
   double* X = h->X.as<double>();
   double* L = h->L.as<double>();
   double* alpha = h->alpha.as<double>();
@@ -1424,7 +1442,7 @@ static int append_incremental(nngp_handle* h, int64_t M) {
   const int64_t N = h->N, D = h->D, Nn = N + M;
   const int64_t ldo = h->ldl, ldn = round_up(Nn, 16);
   h->have_inv = false;    // (latency mode: rebuilt by nngp_append_fit once the factor is extended)
-  const double sw2 = h->cfg.sigma_w * h->cfg.sigma_w, sb2 = h->cfg.sigma_b * h->cfg.sigma_b;
+  const double sw2 = h->lsw2[0], sb2 = h->lsb2[0];   // first Dense layer
   StageTimer t_total(h, &h->st.fit_total_ms);
   CKR(ensure(h, h->L2, (size_t)(Nn + 1) * ldn * sizeof(double)));
   double* Ln = h->L2.as<double>();
@@ -1575,7 +1593,7 @@ static int predict_impl(nngp_handle* h, const double* x_test, int64_t T, double*
     return fail(h, NNGP_ESTATE, "nngp_predict: this imported 'ntk' state has no M yet (nngp_set_state_ntk_m) -- the variance needs it");
   CKR(bind_device(h));
   const int64_t N = h->N, D = h->D, ldx = h->ldx, ldl = h->ldl;
-  const double sw2 = h->cfg.sigma_w * h->cfg.sigma_w, sb2 = h->cfg.sigma_b * h->cfg.sigma_b;
+  const double sw2 = h->lsw2[0], sb2 = h->lsb2[0];   // first Dense layer
 
   // Row-block size: what fits the buffer cap, in equal blocks of whole 128-row tiles.
   const bool ntk = h->cfg.kernel_type == 1;
@@ -1646,7 +1664,9 @@ static int predict_impl(nngp_handle* h, const double* x_test, int64_t T, double*
     for (auto e : ev_chunk) h->ev_pool.push_back(e);
 
     if (var_out) {
-      q_final_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, h->stream>>>(h->qt.as<double>(), (int)rows, h->cfg.depth - 1, sw2, sb2, h->kss.as<double>());
+      LayerSig sig;
+      for (int i = 0; i < 16; ++i) { sig.sw2[i] = h->lsw2[std::min(i + 1, NNGP_MAX_LAYERS - 1)]; sig.sb2[i] = h->lsb2[std::min(i + 1, NNGP_MAX_LAYERS - 1)]; }
+      q_final_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, h->stream>>>(h->qt.as<double>(), (int)rows, h->cfg.depth - 1, sig, h->kss.as<double>());
       h->st.kernel_launches++;
       if (ntk) {
         // var_i = K_ii + v_i^T M v_i - 2 v_i . u_i,  v_i = L^-1 theta_i, u_i = L^-1 k_i, M = L^-1 K_dd L^-T
@@ -1736,7 +1756,7 @@ int nngp_set_state(nngp_handle* h, const double* x, const double* l, const doubl
   CKR(bind_device(h));
   drop_fit(h);
   CKR(alloc_state(h, N, D));
-  const double sw2 = h->cfg.sigma_w * h->cfg.sigma_w, sb2 = h->cfg.sigma_b * h->cfg.sigma_b;
+  const double sw2 = h->lsw2[0], sb2 = h->lsb2[0];   // first Dense layer
   CKR(upload_matrix(h, x, N, D, h->X.as<double>(), h->ldx));
   CKR(upload_matrix(h, l, N, N, h->L.as<double>(), h->ldl));
   CKR(upload_matrix(h, alpha, N, 1, h->alpha.as<double>(), 1));
@@ -1847,7 +1867,7 @@ int nngp_state_import_end(nngp_handle* h, double lambda) {
   if (!h->importing) return fail(h, NNGP_ESTATE, "nngp_state_import_end: no import in progress");
   CKR(bind_device(h));
   h->importing = false;
-  const double sw2 = h->cfg.sigma_w * h->cfg.sigma_w, sb2 = h->cfg.sigma_b * h->cfg.sigma_b;
+  const double sw2 = h->lsw2[0], sb2 = h->lsb2[0];   // first Dense layer
   row_sqnorm_kernel<<<(unsigned)((h->N * 32 + 255) / 256), 256, 0, h->stream>>>(h->X.as<double>(), h->ldx, (int)h->N, (int)h->D, sw2, sb2, h->q.as<double>());
   h->st.kernel_launches++;
   CKR(run_trtri_diag(h));

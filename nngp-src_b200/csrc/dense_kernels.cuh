@@ -41,13 +41,18 @@ __global__ void row_sqnorm_kernel(const double* __restrict__ x, long long ldx, i
   if (lane == 0) q[warp] = sw2 * (s / (double)D) + sb2;
 }
 
-// kss[r] = layer-(depth-1) diagonal: q <- sw2*q/2 + sb2, `steps` times.
-__global__ void q_final_kernel(const double* __restrict__ q, int rows, int steps, double sw2, double sb2,
-                               double* __restrict__ kss) {
+// kss[r] = layer-(depth-1) diagonal: q <- sw2_s*q/2 + sb2_s for the Dense layer that follows arc-cosine step s.
+struct LayerSig {
+  double sw2[16], sb2[16];   // entry min(s, 15)
+};
+__global__ void q_final_kernel(const double* __restrict__ q, int rows, int steps, LayerSig sig, double* __restrict__ kss) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows) return;
   double v = q[i];
-  for (int s = 0; s < steps; ++s) v = sw2 * (0.5 * v) + sb2;
+  for (int s = 0; s < steps; ++s) {
+    const int li = s < 16 ? s : 15;
+    v = sig.sw2[li] * (0.5 * v) + sig.sb2[li];
+  }
   kss[i] = v;
 }
 

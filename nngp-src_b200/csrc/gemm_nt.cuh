@@ -28,6 +28,7 @@ namespace nngp {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BN = 64;
 constexpr int GEMM_BK = 16;
+constexpr int GEMM_MAX_LAYERS = 16;   // == NNGP_MAX_LAYERS (include/nngp_b200.h)
 constexpr int GEMM_STAGES = 4;
 constexpr int GEMM_CONSUMER_WARPS = 8;
 constexpr int GEMM_THREADS = GEMM_CONSUMER_WARPS * 32;  // no dedicated producer warp: thread 0 issues the TMA loads
@@ -51,8 +52,10 @@ struct GemmParams {
   // EPI_GRAM only
   const double* q1;    // per-row layer-0 diagonal of the A rows  (sigma_w^2 |x|^2/D + sigma_b^2)
   const double* q2;    // same for the B rows
-  double scale;        // sigma_w^2 / D
-  double sw2, sb2;     // sigma_w^2, sigma_b^2
+  double scale;        // sigma_w^2 / D of the first Dense layer
+  double sb2;          // sigma_b^2 of the first Dense layer
+  double lsw2[GEMM_MAX_LAYERS];   // sigma_w^2 / sigma_b^2 of the Dense layer that FOLLOWS arc-cosine step s
+  double lsb2[GEMM_MAX_LAYERS];   // (entry min(s, 15): a uniform network of any depth fills all entries alike)
   int steps;           // depth-1 arc-cosine steps
   int ntk;             // 1: C receives the NTK Theta, C2 (if not null) the NNGP kernel K
   double* C2;
@@ -364,12 +367,14 @@ __device__ __forceinline__ void gram_epilogue(const double (&acc)[4][4][2], cons
         double qa = q1r;
         if (!p.ntk) {
           for (int s = 0; s < p.steps; ++s) {
+            const int li = s < GEMM_MAX_LAYERS ? s : GEMM_MAX_LAYERS - 1;
+            const double sw2 = p.lsw2[li], sb2 = p.lsb2[li];
 #pragma unroll
-            for (int j = 0; j < W; ++j) k[j] = arccos_step(k[j], qa, qb[j], p.sw2, p.sb2);
+            for (int j = 0; j < W; ++j) k[j] = arccos_step(k[j], qa, qb[j], sw2, sb2);
             if (s + 1 < p.steps) {              // the diagonals of the next layer (not needed after the last one)
 #pragma unroll
-              for (int j = 0; j < W; ++j) qb[j] = p.sw2 * (0.5 * qb[j]) + p.sb2;
-              qa = p.sw2 * (0.5 * qa) + p.sb2;
+              for (int j = 0; j < W; ++j) qb[j] = sw2 * (0.5 * qb[j]) + sb2;
+              qa = sw2 * (0.5 * qa) + sb2;
             }
           }
         } else {
@@ -377,12 +382,14 @@ __device__ __forceinline__ void gram_epilogue(const double (&acc)[4][4][2], cons
 #pragma unroll
           for (int j = 0; j < W; ++j) n[j] = k[j];
           for (int s = 0; s < p.steps; ++s) {
+            const int li = s < GEMM_MAX_LAYERS ? s : GEMM_MAX_LAYERS - 1;
+            const double sw2 = p.lsw2[li], sb2 = p.lsb2[li];
 #pragma unroll
-            for (int j = 0; j < W; ++j) arccos_step_ntk(k[j], n[j], qa, qb[j], p.sw2, p.sb2);
+            for (int j = 0; j < W; ++j) arccos_step_ntk(k[j], n[j], qa, qb[j], sw2, sb2);
             if (s + 1 < p.steps) {
 #pragma unroll
-              for (int j = 0; j < W; ++j) qb[j] = p.sw2 * (0.5 * qb[j]) + p.sb2;
-              qa = p.sw2 * (0.5 * qa) + p.sb2;
+              for (int j = 0; j < W; ++j) qb[j] = sw2 * (0.5 * qb[j]) + sb2;
+              qa = sw2 * (0.5 * qa) + sb2;
             }
           }
           if (p.C2) {

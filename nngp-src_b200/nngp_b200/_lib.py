@@ -34,6 +34,9 @@ class NngpConfig(C.Structure):
         ("n_gpus", C.c_int32),
         ("device_ids", C.c_int32 * 8),
         ("latency_mode", C.c_int32),
+        ("per_layer", C.c_int32),
+        ("sigma_w_layers", C.c_double * 16),
+        ("sigma_b_layers", C.c_double * 16),
     ]
 
 
@@ -205,7 +208,21 @@ class Handle:
         self._lib = load()
         cfg = NngpConfig()
         self._lib.nngp_default_config(C.byref(cfg))
-        cfg.depth, cfg.sigma_w, cfg.sigma_b = int(depth), float(sigma_w), float(sigma_b)
+        # sigma_w / sigma_b: one value for every Dense layer, or one per layer (stax.serial chains whose layers differ)
+        sw, sb = np.atleast_1d(np.asarray(sigma_w, dtype=np.float64)), np.atleast_1d(np.asarray(sigma_b, dtype=np.float64))
+        if sw.size > 1 or sb.size > 1:
+            sw = np.broadcast_to(sw, (int(depth),)) if sw.size == 1 else sw
+            sb = np.broadcast_to(sb, (int(depth),)) if sb.size == 1 else sb
+            if sw.size != int(depth) or sb.size != int(depth) or int(depth) > 16:
+                raise ValueError(f"nngp_b200: per-layer sigma_w / sigma_b need one value per Dense layer "
+                                 f"(depth={depth} <= 16), got {sw.size} / {sb.size}")
+            if np.all(sw == sw[0]) and np.all(sb == sb[0]):
+                sw, sb = sw[:1], sb[:1]                      # uniform after all
+        cfg.depth, cfg.sigma_w, cfg.sigma_b = int(depth), float(sw[0]), float(sb[0])
+        cfg.per_layer = int(sw.size > 1)
+        for i in range(16):
+            cfg.sigma_w_layers[i] = float(sw[i]) if i < sw.size and sw.size > 1 else 0.0
+            cfg.sigma_b_layers[i] = float(sb[i]) if i < sb.size and sb.size > 1 else 0.0
         cfg.diag_reg, cfg.diag_reg_absolute = float(diag_reg), int(bool(diag_reg_absolute))
         cfg.device, cfg.max_block_bytes, cfg.stats_level = int(device), int(max_block_bytes), int(stats_level)
         if kernel_type not in ("nngp", "ntk"):
@@ -393,15 +410,20 @@ class Handle:
         neuroestimator/README.md:28-29; its ``load_model`` is a warm-up, estimator.py:37-40)."""
         st = self.get_state()
         extra = {"m": st["m"]} if self.is_ntk else {}
+        if self.cfg.per_layer:
+            sw = np.array(self.cfg.sigma_w_layers[:self.cfg.depth])
+            sb = np.array(self.cfg.sigma_b_layers[:self.cfg.depth])
+        else:
+            sw, sb = self.cfg.sigma_w, self.cfg.sigma_b
         np.savez(_npz_path(path), x=st["x"], l=st["l"], alpha=st["alpha"], lam=st["lambda"], depth=self.cfg.depth,
-                 sigma_w=self.cfg.sigma_w, sigma_b=self.cfg.sigma_b, diag_reg=self.cfg.diag_reg,
+                 sigma_w=sw, sigma_b=sb, diag_reg=self.cfg.diag_reg,
                  diag_reg_absolute=self.cfg.diag_reg_absolute, kernel_type="ntk" if self.is_ntk else "nngp", **extra)
 
     @classmethod
     def load(cls, path, **kw) -> "Handle":
         z = np.load(_npz_path(path))
         kt = str(z["kernel_type"]) if "kernel_type" in z.files else "nngp"
-        h = cls(depth=int(z["depth"]), sigma_w=float(z["sigma_w"]), sigma_b=float(z["sigma_b"]),
+        h = cls(depth=int(z["depth"]), sigma_w=z["sigma_w"], sigma_b=z["sigma_b"],
                 diag_reg=float(z["diag_reg"]), diag_reg_absolute=bool(z["diag_reg_absolute"]), kernel_type=kt, **kw)
         h.set_state(z["x"], z["l"], z["alpha"], float(z["lam"]), m=z["m"] if kt == "ntk" else None)
         return h

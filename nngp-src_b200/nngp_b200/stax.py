@@ -21,8 +21,8 @@ from . import _lib, runtime
 @dataclass(frozen=True)
 class KernelSpec:
     depth: int           # number of Dense layers; depth-1 ReLU arc-cosine steps
-    sigma_w: float       # W_std
-    sigma_b: float       # b_std (None -> 0)
+    sigma_w: object      # W_std: a float when every Dense layer has the same, else a tuple with one value per layer
+    sigma_b: object      # b_std (None -> 0): likewise
 
 
 class _Layer(tuple):
@@ -98,10 +98,13 @@ def serial(*layers):
             kinds[i] == kinds[i + 1] for i in range(len(kinds) - 1)):
         raise NotImplementedError(f"nngp_b200.stax.serial: only Dense (Relu Dense)* chains are supported, got {kinds}")
     dense = [l for l in layers if l.kind == "dense"]
-    w = {l.params["W_std"] for l in dense}
-    b = {l.params["b_std"] for l in dense}
-    if len(w) != 1 or len(b) != 1:
-        raise NotImplementedError("nngp_b200.stax.serial: all Dense layers must share W_std and b_std")
-    spec = KernelSpec(depth=len(dense), sigma_w=w.pop(), sigma_b=b.pop())
+    w = tuple(l.params["W_std"] for l in dense)
+    b = tuple(l.params["b_std"] for l in dense)
+    if len(set(w)) == 1 and len(set(b)) == 1:
+        spec = KernelSpec(depth=len(dense), sigma_w=w[0], sigma_b=b[0])
+    else:                                   # layers differ [nt allows it]: per-layer values (nngp_config.per_layer)
+        if len(dense) > 16:
+            raise NotImplementedError("nngp_b200.stax.serial: per-layer W_std / b_std support at most 16 Dense layers")
+        spec = KernelSpec(depth=len(dense), sigma_w=w, sigma_b=b)
     init_fn, apply_fn, _ = dense[0]
     return init_fn, apply_fn, KernelFn(spec)

@@ -12,6 +12,14 @@ import mpmath as mp
 mp.mp.dps = 50
 
 
+def _layers(depth, sigma_w, sigma_b):
+    """[(sw2_l, sb2_l)] for Dense layer l: scalars apply to every layer, sequences give one value per layer."""
+    sw = list(sigma_w) if hasattr(sigma_w, "__len__") else [sigma_w] * depth
+    sb = list(sigma_b) if hasattr(sigma_b, "__len__") else [sigma_b] * depth
+    assert len(sw) == depth and len(sb) == depth
+    return [(mp.mpf(float(a)) ** 2, mp.mpf(float(b)) ** 2) for a, b in zip(sw, sb)]
+
+
 def _diag0(x, sw2, sb2):
     d = len(x[0])
     return [sw2 * (mp.fsum(v * v for v in row) / d) + sb2 for row in x]
@@ -20,17 +28,20 @@ def _diag0(x, sw2, sb2):
 def kernel(x1, x2, depth, sigma_w, sigma_b, get="nngp"):
     x1 = [[mp.mpf(float(v)) for v in r] for r in x1]
     x2 = x1 if x2 is None else [[mp.mpf(float(v)) for v in r] for r in x2]
-    sw2, sb2 = mp.mpf(sigma_w) ** 2, mp.mpf(sigma_b) ** 2
+    lay = _layers(depth, sigma_w, sigma_b)
+    sw2, sb2 = lay[0]
     d = len(x1[0])
     q1, q2 = _diag0(x1, sw2, sb2), _diag0(x2, sw2, sb2)
     out = []
     for i, a in enumerate(x1):
         row = []
         for j, b in enumerate(x2):
+            sw2, sb2 = lay[0]
             k = sw2 * (mp.fsum(u * v for u, v in zip(a, b)) / d) + sb2
             ntk = k
             qa, qb = q1[i], q2[j]
-            for _ in range(depth - 1):
+            for layer in range(1, depth):
+                sw2, sb2 = lay[layer]
                 s2 = qa * qb - k * k
                 s = mp.sqrt(s2) if s2 > 0 else mp.mpf(0)
                 theta = mp.pi / 2 if (s == 0 and k == 0) else mp.atan2(s, k)

@@ -50,11 +50,23 @@ def _pool():
     return _POOL
 
 
-def _relu_layers(k, ntk, q1, q2, depth, sw2, sb2):
-    """depth-1 ReLU arc-cosine steps on the block k (rows: q1, columns: q2), in place (Appendix A.1 / A.5)."""
+def _layer_sigmas(depth, sigma_w, sigma_b):
+    """(sw2[l], sb2[l]) for Dense layer l = 0..depth-1: scalars apply to every layer, sequences give one value per
+    layer [nt: every stax.Dense carries its own W_std / b_std]."""
+    sw = np.broadcast_to(np.asarray(sigma_w, dtype=np.float64), (depth,)) if np.ndim(sigma_w) == 0 else np.asarray(sigma_w, dtype=np.float64)
+    sb = np.broadcast_to(np.asarray(sigma_b, dtype=np.float64), (depth,)) if np.ndim(sigma_b) == 0 else np.asarray(sigma_b, dtype=np.float64)
+    if sw.shape != (depth,) or sb.shape != (depth,):
+        raise ValueError(f"per-layer sigma_w / sigma_b need {depth} values")
+    return sw ** 2, sb ** 2
+
+
+def _relu_layers(k, ntk, q1, q2, depth, sw2l, sb2l):
+    """depth-1 ReLU arc-cosine steps on the block k (rows: q1, columns: q2), in place (Appendix A.1 / A.5);
+    sw2l[l], sb2l[l]: Dense layer l (the step with index l-1 is followed by layer l)."""
     factor = 1.0 / TWO_PI
     q1, q2l = q1.copy(), q2.copy()
-    for _ in range(depth - 1):
+    for layer in range(1, depth):
+        sw2, sb2 = sw2l[layer], sb2l[layer]
         prod = q1[:, None] * q2l[None, :]
         s = np.sqrt(np.maximum(prod - k * k, 0.0))
         theta = np.arctan2(s, k)
@@ -67,17 +79,21 @@ def _relu_layers(k, ntk, q1, q2, depth, sw2, sb2):
         q2l = sw2 * (0.5 * q2l) + sb2
 
 
-def layer0_diag(x: np.ndarray, sigma_w: float = 1.0, sigma_b: float = 0.0) -> np.ndarray:
-    """q0 = sigma_w^2 |x|^2 / D + sigma_b^2   [nt: _inputs_to_kernel (/channel count) then Dense._affine]."""
+def layer0_diag(x: np.ndarray, sigma_w=1.0, sigma_b=0.0) -> np.ndarray:
+    """q0 = sigma_w^2 |x|^2 / D + sigma_b^2   [nt: _inputs_to_kernel (/channel count) then Dense._affine]
+    (per-layer sequences: the first layer's values)."""
     x = np.asarray(x, dtype=np.float64)
-    return sigma_w**2 * (np.einsum("ij,ij->i", x, x) / x.shape[1]) + sigma_b**2
+    sw = float(np.asarray(sigma_w, dtype=np.float64).reshape(-1)[0])
+    sb = float(np.asarray(sigma_b, dtype=np.float64).reshape(-1)[0])
+    return sw**2 * (np.einsum("ij,ij->i", x, x) / x.shape[1]) + sb**2
 
 
-def final_diag(q0: np.ndarray, depth: int = 2, sigma_w: float = 1.0, sigma_b: float = 0.0) -> np.ndarray:
+def final_diag(q0: np.ndarray, depth: int = 2, sigma_w=1.0, sigma_b=0.0) -> np.ndarray:
     """K(x,x) after depth-1 ReLU steps: q <- sigma_w^2 q/2 + sigma_b^2   [nt: ABRelu nngp_fn_diag + Dense]."""
+    sw2l, sb2l = _layer_sigmas(depth, sigma_w, sigma_b)
     q = np.array(q0, dtype=np.float64, copy=True)
-    for _ in range(depth - 1):
-        q = sigma_w**2 * (0.5 * q) + sigma_b**2
+    for layer in range(1, depth):
+        q = sw2l[layer] * (0.5 * q) + sb2l[layer]
     return q
 
 
@@ -95,7 +111,8 @@ def kernel_fn(x1: np.ndarray, x2: np.ndarray | None = None, depth: int = 2, sigm
     x1 = np.asarray(x1, dtype=np.float64)
     x2 = x1 if x2 is None else np.asarray(x2, dtype=np.float64)
     D = x1.shape[1]
-    sw2, sb2 = sigma_w**2, sigma_b**2
+    sw2l, sb2l = _layer_sigmas(depth, sigma_w, sigma_b)
+    sw2, sb2 = sw2l[0], sb2l[0]
     q1_all, q2 = layer0_diag(x1, sigma_w, sigma_b), layer0_diag(x2, sigma_w, sigma_b)
     out = np.empty((x1.shape[0], x2.shape[0]), dtype=np.float64)
     out_ntk = np.empty_like(out) if get in ("ntk", "both") else None
@@ -112,7 +129,7 @@ def kernel_fn(x1: np.ndarray, x2: np.ndarray | None = None, depth: int = 2, sigm
         def work(i, k=k, ntk=ntk, r0=r0):
             a, b = bounds[i], bounds[i + 1]
             if b > a:
-                _relu_layers(k[a:b], None if ntk is None else ntk[a:b], q1_all[r0 + a:r0 + b], q2, depth, sw2, sb2)
+                _relu_layers(k[a:b], None if ntk is None else ntk[a:b], q1_all[r0 + a:r0 + b], q2, depth, sw2l, sb2l)
 
         if nthr == 1:
             work(0)
@@ -126,13 +143,14 @@ def kernel_fn(x1: np.ndarray, x2: np.ndarray | None = None, depth: int = 2, sigm
     return out_ntk if get == "ntk" else (out, out_ntk)
 
 
-def final_diag_ntk(q0: np.ndarray, depth: int = 2, sigma_w: float = 1.0, sigma_b: float = 0.0) -> np.ndarray:
+def final_diag_ntk(q0: np.ndarray, depth: int = 2, sigma_w=1.0, sigma_b=0.0) -> np.ndarray:
     """Theta(x,x): theta = 0 on the diagonal so kdot = 1/2."""
+    sw2l, sb2l = _layer_sigmas(depth, sigma_w, sigma_b)
     q = np.array(q0, dtype=np.float64, copy=True)
     ntk = q.copy()
-    for _ in range(depth - 1):
-        q = sigma_w**2 * (0.5 * q) + sigma_b**2
-        ntk = q + sigma_w**2 * (0.5 * ntk)
+    for layer in range(1, depth):
+        q = sw2l[layer] * (0.5 * q) + sb2l[layer]
+        ntk = q + sw2l[layer] * (0.5 * ntk)
     return ntk
 
 

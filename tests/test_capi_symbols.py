@@ -49,9 +49,11 @@ def test_build_id_tracks_every_source_file(lib):
 
 def test_struct_layouts_match_header(lib):
     # nngp_config: int32, 3 doubles, 2 int32, int64, 2 int32 (56 bytes) + n_gpus, device_ids[8], latency_mode
-    assert ctypes.sizeof(lib.NngpConfig) == 56 + 4 * 10
+    # ... + per_layer (int32, padded to 8) + sigma_w_layers[16] + sigma_b_layers[16]
+    assert ctypes.sizeof(lib.NngpConfig) == 104 + 2 * 16 * 8
     assert lib.NngpConfig.n_gpus.offset == 56 and lib.NngpConfig.device_ids.offset == 60
-    assert lib.NngpConfig.latency_mode.offset == 92
+    assert lib.NngpConfig.latency_mode.offset == 92 and lib.NngpConfig.per_layer.offset == 96
+    assert lib.NngpConfig.sigma_w_layers.offset == 104 and lib.NngpConfig.sigma_b_layers.offset == 232
     assert ctypes.sizeof(lib.NngpStats) == 8 * 25
 
 

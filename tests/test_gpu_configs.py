@@ -366,3 +366,61 @@ def test_symmetric_kernel_skips_upper_tiles_and_stays_bitwise_symmetric(lib, syn
         assert np.array_equal(k_sym, k_full) and np.array_equal(k_sym, k_sym.T)
         assert flops_sym < 0.6 * h.stats()["gram_flops"]
         assert relmax(k_sym, oracle.kernel_fn(x, None, depth)) < 1e-13
+
+
+# ---------------------------------------------------------------------------------------------- per-layer sigmas
+@pytest.mark.parametrize("case", ["layers_d2", "layers_d3"])
+def test_per_layer_sigmas_match_mpmath_and_oracle(lib, golden_dir, case):
+    """stax.serial chains whose Dense layers differ in W_std / b_std (nngp_config.per_layer): kernel entries against
+    50-digit mpmath, posterior against mpmath and the oracle, NNGP and NTK; through the stax mirror too."""
+    from nngp_b200 import stax
+    z = np.load(golden_dir / "mp_layers.npz")
+    g = {k.split("/")[1]: z[k] for k in z.files if k.startswith(case + "/")}
+    sw, sb, reg = tuple(float(v) for v in g["sigma_w"]), tuple(float(v) for v in g["sigma_b"]), float(g["diag_reg"])
+    depth = len(sw)
+    x, y, xt = g["x_train"], g["y_train"], g["x_test"]
+    h = lib.Handle(depth=depth, sigma_w=sw, sigma_b=sb, diag_reg=reg)
+    assert relmax(h.kernel(x), g["K_dd"]) < 1e-13 and relmax(h.kernel(xt, x), g["K_td"]) < 1e-13
+    h.fit(x, y)
+    m, v = h.predict(xt)
+    assert abs(h.dims()[2] - float(g["lam"])) < 1e-12 * float(g["lam"])
+    assert relmax(m, g["mean"]) < 1e-8 and relmax(v, g["var"]) < 1e-7
+    ref = oracle.Fit(x, y, depth, sw, sb, diag_reg=reg)
+    rm, rv = ref.predict(xt)
+    assert relmax(m, rm) < 1e-9 and relmax(v, rv) < 1e-8
+    hn = lib.Handle(depth=depth, sigma_w=sw, sigma_b=sb, diag_reg=reg, kernel_type="ntk")
+    assert relmax(hn.kernel(xt, x), g["Theta_td"]) < 1e-8
+    hn.fit(x, y)
+    mn, vn = hn.predict(xt)
+    assert relmax(mn, g["ntk_mean"]) < 1e-6 and relmax(vn, g["ntk_var"]) < 1e-5
+    # the stax mirror builds the same spec from the layer list
+    layers = []
+    for l in range(depth):
+        layers += ([stax.Relu()] if l else []) + [stax.Dense(512 if l + 1 < depth else 1, W_std=sw[l], b_std=sb[l])]
+    _, _, kernel_fn = stax.serial(*layers)
+    assert np.array_equal(kernel_fn(x), h.kernel(x))
+    # a model file keeps the per-layer values
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        h.save(td + "/m")
+        h2 = lib.Handle.load(td + "/m")
+        assert np.array_equal(h2.predict(xt)[0], m)
+    with pytest.raises(ValueError):
+        lib.Handle(depth=3, sigma_w=(1.0, 2.0))
+
+
+def test_new_entry_points_reject_misuse(lib, synth):
+    xtr, ytr, xte, _ = synth.make_problem(100, 10, 8)
+    h = lib.Handle()
+    with pytest.raises(lib.NngpError):
+        h.state_pack(0, 4, np.empty(4))                       # nothing fitted
+    with pytest.raises(lib.NngpError):
+        h.state_import_end(1.0)                               # no import in progress
+    with pytest.raises(ValueError):
+        lib.Handle(n_gpus=9)
+    with pytest.raises((lib.NngpError, ValueError)):
+        lib.Handle(device_ids=[0, 99])                        # no such GPU
+    h.fit(xtr, ytr)
+    with pytest.raises(ValueError):
+        h.state_pack(0, 10 ** 12, np.empty(4))
+    assert h.n_gpus == 1 and len(lib.build_id()) == 16

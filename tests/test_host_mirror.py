@@ -56,14 +56,38 @@ def test_serial_collapses_to_kernel_spec():
     assert batch.batch(kernel_fn, device_count=0, batch_size=0) is kernel_fn                        # train.py:166-168
     with pytest.raises(NotImplementedError):
         init_fn(None, (1, 2))
-    for bad in ([stax.Dense(1), stax.Dense(1)], [stax.Relu(), stax.Dense(1)], [stax.Dense(1), stax.Relu()],
-                [stax.Dense(1, W_std=2.0), stax.Relu(), stax.Dense(1)]):
+    for bad in ([stax.Dense(1), stax.Dense(1)], [stax.Relu(), stax.Dense(1)], [stax.Dense(1), stax.Relu()]):
         with pytest.raises(NotImplementedError):
             stax.serial(*bad)
+    # Dense layers that differ in W_std / b_std [nt allows it; the reference never does]: per-layer spec
+    _, _, kmix = stax.serial(stax.Dense(1, W_std=2.0), stax.Relu(), stax.Dense(1, b_std=0.3))
+    assert kmix.spec == stax.KernelSpec(depth=2, sigma_w=(2.0, 1.0), sigma_b=(0.0, 0.3))
     with pytest.raises(NotImplementedError):
         stax.Conv(3, (3, 3))
     with pytest.raises(NotImplementedError):
         stax.Dense(1, parameterization="standard")
+
+
+def test_per_layer_sigmas_in_the_oracle():
+    """Per-layer W_std / b_std: closed form for depth 2 (K = W1^2 * kappa(k0, q0, q0') + b1^2 with k0 = W0^2 x.x'/D + b0^2),
+    the uniform case as a special case, and the diagonal recursions."""
+    rng = np.random.default_rng(3)
+    x = rng.uniform(0, 10, (7, 6))
+    w, b = (1.7, 0.6), (0.2, 0.4)
+    k = oracle.kernel_fn(x, None, 2, w, b)
+    k0 = w[0] ** 2 * (x @ x.T) / 6 + b[0] ** 2
+    q0 = np.diag(k0)
+    s = np.sqrt(np.maximum(np.outer(q0, q0) - k0 ** 2, 0))
+    th = np.arctan2(s, k0)
+    want = w[1] ** 2 * (s / (2 * np.pi) + (0.5 - th / (2 * np.pi)) * k0) + b[1] ** 2
+    assert np.allclose(k, want, rtol=1e-13)
+    assert np.allclose(np.diag(k), oracle.final_diag(oracle.layer0_diag(x, w, b), 2, w, b), rtol=1e-13)
+    assert np.array_equal(oracle.kernel_fn(x, None, 3, (1.5, 1.5, 1.5), (0.05,) * 3), oracle.kernel_fn(x, None, 3, 1.5, 0.05))
+    th3 = oracle.kernel_fn(x, None, 3, (1.0, 1.3, 0.8), (0.1, 0.0, 0.2), get="ntk")
+    assert np.allclose(np.diag(th3), oracle.final_diag_ntk(oracle.layer0_diag(x, (1.0, 1.3, 0.8), (0.1, 0.0, 0.2)), 3,
+                                                           (1.0, 1.3, 0.8), (0.1, 0.0, 0.2)), rtol=1e-7)   # (theta ~ 1e-8 on the diagonal: DESIGN 5.5)
+    with pytest.raises(ValueError):
+        oracle.kernel_fn(x, None, 3, (1.0, 1.0), 0.0)
 
 
 def test_kernel_fn_get_semantics(fake_engine):

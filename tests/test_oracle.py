@@ -193,3 +193,29 @@ def test_device_atan2_algorithm_in_numpy():
     mp.mp.dps = 40
     hi = np.array([float(mp.atan2(mp.mpf(float(a)), mp.mpf(float(b)))) for a, b in zip(s[2000:4000], k[2000:4000])])
     assert np.max(np.abs(atan2_pos(s[2000:4000], k[2000:4000]) - hi)) <= 9e-16
+
+
+@pytest.mark.parametrize("case", ["layers_d2", "layers_d3"])
+def test_per_layer_sigmas_against_mpmath(case, golden_dir):
+    """Dense layers with different W_std / b_std (nt allows it): the numpy oracle against 50-digit mpmath vectors
+    (tests/golden/make_mp_layers_golden.py), NNGP and NTK, kernels and posteriors."""
+    z = np.load(golden_dir / "mp_layers.npz")
+    g = {k.split("/")[1]: z[k] for k in z.files if k.startswith(case + "/")}
+    sw, sb, reg = tuple(g["sigma_w"]), tuple(g["sigma_b"]), float(g["diag_reg"])
+    depth = len(sw)
+    x, y, xt = g["x_train"], g["y_train"], g["x_test"]
+    k, th = o.kernel_fn(x, None, depth, sw, sb, get="both")
+    ks, ths = o.kernel_fn(xt, x, depth, sw, sb, get="both")
+
+    def rel(a, b):
+        return np.max(np.abs(a - b)) / np.max(np.abs(b))
+
+    assert rel(k, g["K_dd"]) < 1e-14 and rel(ks, g["K_td"]) < 1e-14
+    assert rel(th, g["Theta_dd"]) < 1e-8 and rel(ths, g["Theta_td"]) < 1e-8      # (theta ~ 1e-8 at duplicates)
+    f = o.Fit(x, y, depth, sw, sb, diag_reg=reg)
+    m, v = f.predict(xt)
+    assert abs(f.lam - float(g["lam"])) < 1e-13 * f.lam
+    assert rel(m, g["mean"]) < 1e-9 and rel(v, g["var"]) < 1e-8
+    fn = o.FitNTK(x, y, depth, sw, sb, diag_reg=reg)
+    mn, vn = fn.predict(xt)
+    assert rel(mn, g["ntk_mean"]) < 1e-7 and rel(vn, g["ntk_var"]) < 1e-5
