@@ -725,7 +725,7 @@ __global__ void __launch_bounds__(256, 2) tri_gemv_kernel(const double* __restri
                                                           double* __restrict__ v) {
   constexpr int KC = TGV_SMEM_DOUBLES / R;
   constexpr int U = 4;                            // independent 16-byte loads in flight per lane (the stream is
-  __shared__ double ks_s[R][KC];                  // latency-bound otherwise: 1.5 TB/s with one load per lane)
+  __shared__ __align__(16) double ks_s[R][KC];    // latency-bound otherwise: 1.5 TB/s with one load per lane)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ngroups = (N + 7) / 8;
   for (int half = 0; half < 2; ++half) {
@@ -756,11 +756,12 @@ __global__ void __launch_bounds__(256, 2) tri_gemv_kernel(const double* __restri
           }
 #pragma unroll
           for (int u = 0; u < U; ++u) {          // ascending k: the order of the sums does not depend on U
-            const int kk = min(kb + 64 * u, kend - 1) - k0;
+            const int kk = min(kb + 64 * u, kend - 1 - ((kend - 1 - k0) & 1)) - k0;   // even: one 16-byte load per row
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-              acc[r] = fma(w2[u].x, ks_s[r][kk], acc[r]);
-              acc[r] = fma(w2[u].y, ks_s[r][min(kk + 1, KC - 1)], acc[r]);
+              const double2 kv = *reinterpret_cast<const double2*>(&ks_s[r][kk]);
+              acc[r] = fma(w2[u].x, kv.x, acc[r]);
+              acc[r] = fma(w2[u].y, kv.y, acc[r]);
             }
           }
         }
