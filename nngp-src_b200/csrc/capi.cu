@@ -1572,8 +1572,13 @@ int nngp_predict(nngp_handle* h, const double* x_test, int64_t T, double* mean_o
     const int64_t lo = (int64_t)g * T / G, hi = (int64_t)(g + 1) * T / G;
     rcs[(size_t)g] = predict_impl(hg, x_test + lo * D, hi - lo, mean_out + lo, var_out ? var_out + lo : nullptr);
   };
-  for (int g = 1; g < G; ++g) workers.emplace_back(shard, g);
+  int started = 1;
+  try {
+    for (int g = 1; g < G; ++g) { workers.emplace_back(shard, g); started = g + 1; }
+  } catch (...) {   // (no exception may cross the C ABI) a worker thread could not be created: its shard runs here
+  }
   shard(0);
+  for (int g = started; g < G; ++g) shard(g);
   for (auto& w : workers) w.join();
   cudaSetDevice(h->device);
   for (int g = 1; g < G; ++g)

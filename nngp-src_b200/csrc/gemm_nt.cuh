@@ -335,11 +335,16 @@ __device__ __forceinline__ void mma_mainloop(double (&acc)[4][4][2], const TileS
 
 // Gram epilogue (K1 + K2 + K3 (+ K8)): k = scale * acc + sb2, depth-1 arc-cosine steps in registers, store, and
 // (optionally) the fused posterior-mean GEMV partial of this warp's 32 columns.
-// (A persistent variant of the Gram kernel -- one CTA per SM slot walking the tiles, the next tile's TMA loads in
-// flight during the epilogue -- was measured in round 2 and dropped: 0.41 of the DMMA peak at C2 against 0.51 for
-// one tile per CTA.  Two co-resident persistent CTAs run in lock-step, both in the main loop or both in the
-// epilogue; with one tile per CTA the hardware scheduler staggers them, and a DMMA phase overlapping an FP64-FMA
-// phase is what fills the shared FP64 pipe.)
+// Two other organisations of this kernel were built and measured in round 2, and dropped (0.55 / 0.58 of the DMMA peak
+// at D = 128 depth 2 / D = 256 depth 3 for one tile per CTA, 2 CTAs per SM):
+//   * persistent: one CTA per SM slot walking the tiles, the next tile's TMA loads in flight during the epilogue --
+//     0.41: two co-resident persistent CTAs run in lock-step, both in the main loop or both in the epilogue; with one
+//     tile per CTA the hardware scheduler staggers them, and a DMMA phase overlapping an FP64-FMA phase is what fills
+//     the shared FP64 pipe;
+//   * warp-specialised: one 512-thread CTA per SM, 8 DMMA warps running the main loops back to back and handing the
+//     accumulator tiles through shared memory to 8 epilogue warps -- 0.45 / 0.50 (0.47 / 0.52 with 8 entries in flight
+//     per thread): the register file caps the CTA at 16 warps, and 8 warps cannot keep enough of the epilogue's
+//     dependent FP64 chains in flight; the epilogue becomes the longer side.
 #ifndef NNGP_GRAM_ILP
 #define NNGP_GRAM_ILP 4   // entries advanced through the layers together (2, 4 or 8): independent dependency chains
 #endif                    // (sqrt, reciprocal, two Horner halves each) for the scheduler to interleave; 8 spills
