@@ -171,19 +171,6 @@ class Fit:
         self.c = sla.cholesky(k.T, lower=True, overwrite_a=True, check_finite=False)
         self.alpha = sla.cho_solve((self.c, True), self.y, check_finite=False)      # [nt: cho_solve]
 
-    @classmethod
-    def from_state(cls, x, y, c, alpha, lam, depth=2, sigma_w=1.0, sigma_b=0.0):
-        """A Fit around an existing factorisation (lower factor c, alpha, lambda) -- bench.py's bounded CPU sample
-        times predict() against a model of the full size without paying the CPU fit again."""
-        self = cls.__new__(cls)
-        self.x = np.asarray(x, dtype=np.float64)
-        self.y = np.asarray(y, dtype=np.float64).reshape(-1)
-        self.depth, self.sigma_w, self.sigma_b = depth, sigma_w, sigma_b
-        # column-major like the factor Fit.__init__ gets from LAPACK: solve_triangular would otherwise copy the whole
-        # N x N matrix into Fortran order on every predict() call
-        self.c, self.alpha, self.lam = np.asfortranarray(c), np.asarray(alpha).reshape(-1), float(lam)
-        return self
-
     def log_marginal_likelihood(self):
         """-1/2 y^T (K+lam I)^-1 y - sum log C_ii - N/2 log 2 pi  (standard GP evidence; cf. train.py:86-103)."""
         n = self.y.shape[0]

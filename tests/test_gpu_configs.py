@@ -424,3 +424,27 @@ def test_new_entry_points_reject_misuse(lib, synth):
     with pytest.raises(ValueError):
         h.state_pack(0, 10 ** 12, np.empty(4))
     assert h.n_gpus == 1 and len(lib.build_id()) == 16
+
+
+def test_in_process_multi_gpu_latency_mode_and_reserve(lib, synth):
+    """Replicas carry the explicit inverse factor (latency mode) and follow appends after nngp_reserve sized them."""
+    _need_two_gpus()
+    xtr, ytr, xte, _ = synth.make_problem(1500, 1200, 24)
+    h1 = lib.Handle(latency_mode=True)
+    hg = lib.Handle(latency_mode=True, n_gpus=2)
+    hg.reserve(2500, 24, 1200)
+    h1.fit(xtr, ytr)
+    hg.fit(xtr, ytr)
+    m1, v1 = h1.predict(xte)             # 1200 rows <= 4096: the inverse path, on one / on two GPUs
+    mg, vg = hg.predict(xte)
+    assert np.array_equal(mg, m1) and np.array_equal(vg, v1)
+    ref = oracle.Fit(xtr, ytr)
+    rm, rv = ref.predict(xte[:200])
+    assert relmax(mg[:200], rm) < 1e-6 and np.max(np.abs(vg[:200] - rv) / np.abs(rv)) < 1e-6
+    xn = synth.encodings(700, 24, 9)
+    yn = synth.labels(xn)
+    h1.append_fit(xn, yn)
+    hg.append_fit(xn, yn)
+    m1b, v1b = h1.predict(xte)
+    mgb, vgb = hg.predict(xte)
+    assert np.array_equal(mgb, m1b) and np.array_equal(vgb, v1b) and not np.array_equal(v1b, v1)
