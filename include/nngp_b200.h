@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define NNGP_B200_ABI_VERSION 5
+#define NNGP_B200_ABI_VERSION 6
 #define NNGP_MAX_GPUS 8
 #define NNGP_MAX_LAYERS 16
 
@@ -87,6 +87,13 @@ typedef struct nngp_config {
                                  Dense layers differ in W_std / b_std [nt allows it; the reference never does]          */
   double sigma_w_layers[NNGP_MAX_LAYERS];
   double sigma_b_layers[NNGP_MAX_LAYERS];
+  int32_t variance_slices;    /* 0: off.  s = 5..9 ('nngp' only; implies the explicit inverse factor of latency_mode):
+                                 the variance product K_* L^-T of LARGE prediction batches runs on the INT8 tensor cores
+                                 (tcgen05.mma kind::i8, accumulators in TMEM): both operands are split row-wise into s
+                                 signed 7-bit digit planes, the s(s+1)/2 exact int32 plane products with p + q < s are
+                                 recombined in FP64.  s = 7 keeps the posterior variance within ~1e-8 relative of the
+                                 FP64 path at cond(K + lambda I) = 1e7 (s = 8: 1e-10); the mean is untouched.  N <= 2^19 / s. */
+  int32_t reserved0;
 } nngp_config;
 
 /* Per-stage device timings (CUDA events on the handle's stream) and work counters,
@@ -109,6 +116,8 @@ typedef struct nngp_stats_t {
   double replicate_ms;     /* n_gpus > 1: wall time of the last peer-to-peer replication of the fitted state */
   int64_t replicate_bytes; /* bytes each replica received in it                        */
   double inverse_ms;       /* latency_mode: device time of building L^-1 in the last fit */
+  double sliced_ms;        /* variance_slices: device time of digit-plane splitting + the int8 plane products   */
+  double sliced_macs;      /* int8 multiply-accumulates issued to the tensor cores in them                       */
 } nngp_stats_t;
 
 typedef struct nngp_handle nngp_handle;
@@ -227,6 +236,14 @@ NNGP_API int nngp_abi_version(void);
 NNGP_API const char* nngp_build_id(void);
 /* Number of GPUs the handle predicts on (1 unless cfg.n_gpus > 1). */
 NNGP_API int nngp_num_gpus(const nngp_handle* h);
+
+/* Diagnostic / test entry of the digit-plane product behind cfg.variance_slices: V = A B^T for A [M, K] and B [N, K]
+ * (dense row-major, host or device), computed with `slices` int8 planes per operand on the tcgen05 kind::i8 path;
+ * `lower` != 0 treats B as lower triangular (entries with k > row ignored, N == K).  v_out [M, N] receives the product,
+ * rowsq_out [M] (optional) the row sums of V^2 in the order the variance uses.  Independent of any fitted model.
+ * [no reference counterpart: the reference's only matrix product is XLA's dot, train.py:157-158]              */
+NNGP_API int nngp_sliced_product(nngp_handle* h, const double* a, int64_t M, int64_t K, const double* b, int64_t N,
+                                 int32_t lower, int32_t slices, double* v_out, double* rowsq_out);
 
 /* Packed fitted state, for shipping a fit to other processes (one process per GPU, nngp_b200/dist.py) or to a
  * file without a staging copy of the whole N x N factor.  The state is ONE logical array of doubles:

@@ -25,6 +25,7 @@
 #include "trsm_fused.cuh"
 #include "potrf_panel.cuh"
 #include "active_kernels.cuh"
+#include "sliced_gemm.cuh"
 
 using namespace nngp;
 
@@ -89,6 +90,11 @@ struct nngp_handle {
   DevBuf zkeep;   // z = L^-1 y of the last fit (the backward substitution destroys its copy in the factor buffer)
   DevBuf Linvfull;  // latency mode: the explicit inverse factor L^-1 (N x N, lower, row-major, ld = ldl)
   bool have_inv = false;
+  // cfg.variance_slices: int8 digit planes of L^-1 ([s][wq_rb][wq_ldq]) + 2^(e-6) of its rows; planes of the current
+  // K_* row block, their row scales, and the per-CTA running-sum tiles of sliced_gemm_kernel
+  DevBuf Wq, wscale, Aq, ascale, slscratch;
+  bool have_wq = false;
+  int64_t wq_ldq = 0, wq_rb = 0;
   DevBuf L2;      // second factor buffer: target of the incremental (fixed-lambda) append, then swapped with L
   bool have_y = false;
   bool importing = false;   // between nngp_state_import_begin and _end
@@ -109,6 +115,7 @@ struct nngp_handle {
   nngp_stats_t st;
   std::vector<EvRec> pending;
   std::vector<cudaEvent_t> ev_pool;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sliced_spans;   // run_sliced_variance, collected by nngp_predict
   std::vector<cudaEvent_t> rep_events;   // no-timing events of replicate_state (recorded on this handle's copy stream)
 };
 
@@ -655,6 +662,7 @@ int run_predict_solve(nngp_handle* h, double* B, int64_t ldb, int64_t rows, cons
 // W is built once per fit on the same DMMA kernels: X L^T = I solved by the persistent kernel (upper-triangular
 // right-hand side: N^3/3 flop), X = L^-T, then W = X^T.  inv(L) is as benign as inv(L_JJ) in the diagonal step:
 // the error of K_* W^T is eps * cond(L) = eps * sqrt(cond(K + lambda I)) (tests/checks/illcond_report.py).
+int build_w_planes(nngp_handle* h);
 int build_inverse(nngp_handle* h) {
   const int64_t N = h->N, ldl = h->ldl;
   CKR(ensure(h, h->Linvfull, (size_t)N * ldl * sizeof(double)));
@@ -676,6 +684,7 @@ int build_inverse(nngp_handle* h) {
   h->ev_pool.push_back(a); h->ev_pool.push_back(b);
   flush_class_events(h);
   h->have_inv = true;
+  if (h->cfg.variance_slices > 0) CKR(build_w_planes(h));
   return NNGP_OK;
 }
 
@@ -730,6 +739,116 @@ int run_inverse_variance(nngp_handle* h, const double* B, int64_t ldb, int64_t r
     var_from_partial_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, h->stream>>>(kss, h->partial.as<double>(), col_tiles, (int)rows, var);
   }
   h->st.kernel_launches++;
+  CK(cudaGetLastError());
+  return NNGP_OK;
+}
+
+// ---- cfg.variance_slices: the variance product on the INT8 tensor cores (sliced_gemm.cuh) ---------------------
+int get_tmap_u8(nngp_handle* h, const void* base, uint64_t rows, uint64_t ldq, uint32_t box_rows, CUtensorMap* out) {
+  cuuint64_t gdim[2] = {ldq, rows};
+  cuuint64_t gstride[1] = {ldq};
+  cuuint32_t box[2] = {(cuuint32_t)SL_BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = h->encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(h, NNGP_ECUDA, "cuTensorMapEncodeTiled (digit planes) failed (CUresult %d; rows=%llu ld=%llu)", (int)r,
+                (unsigned long long)rows, (unsigned long long)ldq);
+  return NNGP_OK;
+}
+
+// digit planes of `rows` rows of A (columns [0, ncols), or [0, row] when tri) -> planes[s][rpad][ldq], scale[rows]
+int slice_matrix(nngp_handle* h, const double* A, int64_t lda, int64_t rows, int64_t ncols, int tri, int s, int64_t rpad,
+                 int64_t ldq, int8_t* planes, double* scale) {
+  slice_rows_kernel<<<(unsigned)rpad, SL_SLICE_THREADS, 0, h->stream>>>(A, lda, (int)rows, (int)ncols, tri, s, planes,
+                                                                       rpad * ldq, (int)ldq, scale);
+  h->st.kernel_launches++;
+  CK(cudaGetLastError());
+  return NNGP_OK;
+}
+
+// int8 MACs the kernel issues for this shape (every supercolumn runs the K extent of its last column tile)
+double sliced_macs(int64_t row_tiles, int64_t col_tiles, int64_t K, int tri, int s) {
+  double macs = 0.0;
+  const int64_t nsup = (col_tiles + SL_SUPER - 1) / SL_SUPER;
+  for (int64_t sup = 0; sup < nsup; ++sup) {
+    const int64_t width = std::min<int64_t>(SL_SUPER, col_tiles - sup * SL_SUPER);
+    const int64_t kext = tri ? std::min<int64_t>(K, std::min<int64_t>((sup + 1) * SL_SUPER, col_tiles) * SL_BN) : K;
+    macs += (double)row_tiles * (double)width * (double)(SL_BM * SL_BN) * (double)round_up(kext, SL_BK);
+  }
+  return macs * (double)(s * (s + 1) / 2);
+}
+
+// V = A W^T from the digit planes: vpart[col_tiles][rows] row sums of V^2 per 256-column tile and/or V itself
+int launch_sliced(nngp_handle* h, const int8_t* qa, int64_t ra, const double* sa, const int8_t* qw, int64_t rb,
+                  const double* sw, int64_t ldq, int s, int tri, int64_t rows, int64_t N, int64_t K, double* vpart, double* V,
+                  int64_t ldv) {
+  SlicedParams p{};
+  p.s = s; p.rows = (int)rows; p.N = (int)N; p.K = (int)K; p.tri = tri;
+  p.row_tiles = (int)((rows + SL_BM - 1) / SL_BM);
+  p.col_tiles = (int)((N + SL_BN - 1) / SL_BN);
+  p.ra = ra; p.rb = rb; p.rscale = sa; p.cscale = sw; p.vpart = vpart; p.V = V; p.ldv = ldv;
+  if ((int64_t)s * ra >= (1LL << 31) || (int64_t)s * rb >= (1LL << 31))
+    return fail(h, NNGP_EINVAL, "internal: digit-plane row range too large");
+  const int64_t tiles = (int64_t)p.row_tiles * p.col_tiles;
+  static const int grid_env = [] { const char* e = getenv("NNGP_SLICED_GRID"); return e ? atoi(e) : 0; }();
+  int grid = grid_env > 0 ? grid_env : (h->sm_count / SL_SUPER) * SL_SUPER;   // CTAs 4k..4k+3 share a K_* row tile
+  grid = (int)std::min<int64_t>(grid, tiles);
+  CKR(ensure(h, h->slscratch, (size_t)grid * SL_BM * SL_BN * sizeof(double)));
+  p.scratch = h->slscratch.as<double>();
+  CUtensorMap tmA, tmB;
+  CKR(get_tmap_u8(h, qa, (uint64_t)s * ra, (uint64_t)ldq, SL_BM, &tmA));
+  CKR(get_tmap_u8(h, qw, (uint64_t)s * rb, (uint64_t)ldq, SL_BN, &tmB));
+  CK(cudaFuncSetAttribute(sliced_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM_BYTES));   // (per device)
+  sliced_gemm_kernel<<<grid, SL_THREADS, SL_SMEM_BYTES, h->stream>>>(tmA, tmB, p);
+  CK(cudaGetLastError());
+  h->st.kernel_launches++;
+  h->st.sliced_macs += sliced_macs(p.row_tiles, p.col_tiles, K, tri, s);
+  return NNGP_OK;
+}
+
+// digit planes of W = L^-1, once per fit (and on every replica after the peer-to-peer copy)
+int build_w_planes(nngp_handle* h) {
+  const int s = h->cfg.variance_slices;
+  const int64_t N = h->N;
+  const int64_t ldq = round_up(N, SL_BK), rb = round_up(N, SL_BN);
+  if ((int64_t)s * 4096 * ldq >= (1LL << 31))
+    return fail(h, NNGP_EINVAL, "variance_slices = %d: int32 plane sums need N <= %lld (N = %lld)", s,
+                (long long)((1LL << 19) / s), (long long)N);
+  CKR(ensure(h, h->Wq, (size_t)s * rb * ldq));
+  CKR(ensure(h, h->wscale, (size_t)N * sizeof(double)));
+  CKR(slice_matrix(h, h->Linvfull.as<double>(), h->ldl, N, N, 1, s, rb, ldq, h->Wq.as<int8_t>(), h->wscale.as<double>()));
+  CK(cudaStreamSynchronize(h->stream));
+  h->wq_ldq = ldq; h->wq_rb = rb; h->have_wq = true;
+  return NNGP_OK;
+}
+
+// var[r] = kss[r] - |K_*[r,:] W^T|^2 with the product on the int8 tensor cores, in row sub-blocks whose planes fit
+// 16 GiB (whole waves of 37 row tiles x 4 column tiles, so that the static tile order stays balanced)
+int run_sliced_variance(nngp_handle* h, const double* B, int64_t ldb, int64_t rows, const double* kss, double* var) {
+  const int s = h->cfg.variance_slices;
+  const int64_t N = h->N, ldq = h->wq_ldq;
+  const int col_tiles = (int)((N + SL_BN - 1) / SL_BN);
+  const int64_t wave_rows = (int64_t)(h->sm_count / SL_SUPER) * SL_BM;
+  int64_t sb = ((16LL << 30) / ((int64_t)s * ldq)) / wave_rows * wave_rows;
+  sb = std::max<int64_t>(sb, SL_BM);
+  sb = std::min<int64_t>(sb, round_up(rows, SL_BM));
+  CKR(ensure(h, h->Aq, (size_t)s * sb * ldq));
+  CKR(ensure(h, h->ascale, (size_t)sb * sizeof(double)));
+  CKR(ensure(h, h->partial, (size_t)col_tiles * sb * sizeof(double)));
+  cudaEvent_t a = get_event(h), b = get_event(h);
+  cudaEventRecord(a, h->stream);
+  for (int64_t r0 = 0; r0 < rows; r0 += sb) {
+    const int64_t nr = std::min<int64_t>(sb, rows - r0), ra = round_up(nr, SL_BM);
+    CKR(slice_matrix(h, B + r0 * ldb, ldb, nr, N, 0, s, ra, ldq, h->Aq.as<int8_t>(), h->ascale.as<double>()));
+    CKR(launch_sliced(h, h->Aq.as<int8_t>(), ra, h->ascale.as<double>(), h->Wq.as<int8_t>(), h->wq_rb,
+                      h->wscale.as<double>(), ldq, s, 1, nr, N, N, h->partial.as<double>(), nullptr, 0));
+    var_from_partial_kernel<<<(unsigned)((nr + 255) / 256), 256, 0, h->stream>>>(kss + r0, h->partial.as<double>(), col_tiles, (int)nr, var + r0);
+    h->st.kernel_launches++;
+  }
+  cudaEventRecord(b, h->stream);
+  h->sliced_spans.push_back({a, b});
   CK(cudaGetLastError());
   return NNGP_OK;
 }
@@ -808,7 +927,7 @@ int bind_device(nngp_handle* h) {
   return NNGP_OK;
 }
 
-void drop_fit(nngp_handle* h) { h->importing = false; h->have_inv = false; h->fitted = false; h->have_lml = false; h->have_y = false; h->have_M = false; }
+void drop_fit(nngp_handle* h) { h->importing = false; h->have_inv = false; h->have_wq = false; h->fitted = false; h->have_lml = false; h->have_y = false; h->have_M = false; }
 
 int alloc_state(nngp_handle* h, int64_t N, int64_t D) {
   h->N = N; h->D = D;
@@ -916,6 +1035,12 @@ int replicate_state(nngp_handle* h) {
     nngp_handle* p = chain[g];
     p->lambda = h->lambda; p->fitted = true; p->have_M = ntk && h->have_M;
     p->have_lml = false; p->have_y = false; p->have_inv = h->have_inv;
+    if (h->have_wq) {          // each replica splits its own copy of L^-1 (a few ms) instead of receiving s more planes
+      cudaSetDevice(p->device);
+      const int rc = build_w_planes(p);
+      cudaSetDevice(h->device);
+      if (rc != NNGP_OK) { h->err = "replica on device " + std::to_string(p->device) + ": " + p->err; return rc; }
+    }
   }
   h->st.replicate_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
   int64_t bytes = (int64_t)N * ldx * 8 + 2 * N * 8 + round_up(N, NB) * NB * 8;
@@ -984,8 +1109,14 @@ static int create_single(const nngp_config* cfg, nngp_handle** out) {
   if (prop.major != 10)
     return fail(h, NNGP_ENODEV, "nngp_create: device %d is sm_%d%d; this library is built for sm_100a only", dev,
                 prop.major, prop.minor);
+  if (cfg->variance_slices != 0 && (cfg->variance_slices < 5 || cfg->variance_slices > SL_MAX_SLICES))
+    return fail(h, NNGP_EINVAL, "nngp_create: variance_slices must be 0 (off) or 5..%d (got %d)", SL_MAX_SLICES,
+                cfg->variance_slices);
+  if (cfg->variance_slices != 0 && cfg->kernel_type != 0)
+    return fail(h, NNGP_EINVAL, "nngp_create: variance_slices applies to kernel_type 0 ('nngp') only");
   nngp_handle* nh = new nngp_handle();
   nh->cfg = *cfg;
+  if (nh->cfg.variance_slices > 0) nh->cfg.latency_mode = 1;   // the digit planes are those of the explicit inverse
   for (int l = 0; l < NNGP_MAX_LAYERS; ++l) {
     const int ll = std::min(l, std::max(cfg->depth - 1, 0));
     const double w = cfg->per_layer ? cfg->sigma_w_layers[ll] : cfg->sigma_w;
@@ -1105,6 +1236,58 @@ int nngp_create(const nngp_config* cfg, nngp_handle** out) {
 
 int nngp_num_gpus(const nngp_handle* h) { return h ? 1 + (int)h->peers.size() : 0; }
 
+// sum_t partial[t][r] in tile order (the order the variance uses)
+static __global__ void rowsq_from_partial_kernel(const double* __restrict__ partial, int tiles, int rows, double* __restrict__ out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  double q = 0.0;
+  for (int t = 0; t < tiles; ++t) q += partial[(long long)t * rows + r];
+  out[r] = q;
+}
+
+int nngp_sliced_product(nngp_handle* h, const double* a, int64_t M, int64_t K, const double* b, int64_t N, int32_t lower,
+                        int32_t slices, double* v_out, double* rowsq_out) {
+  if (!h) return NNGP_EINVAL;
+  if (!a || !b || (!v_out && !rowsq_out) || M <= 0 || K <= 0 || N <= 0)
+    return fail(h, NNGP_EINVAL, "nngp_sliced_product: bad argument (M=%lld K=%lld N=%lld)", (long long)M, (long long)K, (long long)N);
+  if (slices < 1 || slices > SL_MAX_SLICES) return fail(h, NNGP_EINVAL, "nngp_sliced_product: slices must be 1..%d", SL_MAX_SLICES);
+  if (lower && N != K) return fail(h, NNGP_EINVAL, "nngp_sliced_product: a triangular B must be square (N=%lld K=%lld)", (long long)N, (long long)K);
+  const int64_t ldq = round_up(K, SL_BK), ra = round_up(M, SL_BM), rb = round_up(N, SL_BN);
+  if ((int64_t)slices * 4096 * ldq >= (1LL << 31)) return fail(h, NNGP_EINVAL, "nngp_sliced_product: K too large for int32 plane sums");
+  CKR(bind_device(h));
+  const int col_tiles = (int)(rb / SL_BN);
+  DevBuf dA, dB, qa, qb, sa, sb, dV, vp, rs;
+  auto cleanup = [&]() { for (DevBuf* x : {&dA, &dB, &qa, &qb, &sa, &sb, &dV, &vp, &rs}) release(*x); };
+  int rc = ensure(h, dA, (size_t)M * K * 8);
+  if (rc == NNGP_OK) rc = ensure(h, dB, (size_t)N * K * 8);
+  if (rc == NNGP_OK) rc = ensure(h, qa, (size_t)slices * ra * ldq);
+  if (rc == NNGP_OK) rc = ensure(h, qb, (size_t)slices * rb * ldq);
+  if (rc == NNGP_OK) rc = ensure(h, sa, (size_t)M * 8);
+  if (rc == NNGP_OK) rc = ensure(h, sb, (size_t)N * 8);
+  if (rc == NNGP_OK && v_out) rc = ensure(h, dV, (size_t)M * N * 8);
+  if (rc == NNGP_OK) rc = ensure(h, vp, (size_t)col_tiles * M * 8);
+  if (rc == NNGP_OK) rc = ensure(h, rs, (size_t)M * 8);
+  auto run = [&]() -> int {
+    CK(cudaMemcpyAsync(dA.p, a, (size_t)M * K * 8, cudaMemcpyDefault, h->stream));
+    CK(cudaMemcpyAsync(dB.p, b, (size_t)N * K * 8, cudaMemcpyDefault, h->stream));
+    CKR(slice_matrix(h, dA.as<double>(), K, M, K, 0, slices, ra, ldq, qa.as<int8_t>(), sa.as<double>()));
+    CKR(slice_matrix(h, dB.as<double>(), K, N, K, lower ? 1 : 0, slices, rb, ldq, qb.as<int8_t>(), sb.as<double>()));
+    CKR(launch_sliced(h, qa.as<int8_t>(), ra, sa.as<double>(), qb.as<int8_t>(), rb, sb.as<double>(), ldq, slices, lower ? 1 : 0,
+                      M, N, K, vp.as<double>(), v_out ? dV.as<double>() : nullptr, N));
+    if (v_out) CK(cudaMemcpyAsync(v_out, dV.p, (size_t)M * N * 8, cudaMemcpyDefault, h->stream));
+    if (rowsq_out) {
+      rowsq_from_partial_kernel<<<(unsigned)((M + 255) / 256), 256, 0, h->stream>>>(vp.as<double>(), col_tiles, (int)M, rs.as<double>());
+      CK(cudaMemcpyAsync(rowsq_out, rs.p, (size_t)M * 8, cudaMemcpyDefault, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    return NNGP_OK;
+  };
+  if (rc == NNGP_OK) rc = run();
+  cleanup();
+  return rc;
+}
+
 #ifndef NNGP_BUILD_ID
 #define NNGP_BUILD_ID "unknown"
 #endif
@@ -1120,11 +1303,12 @@ void nngp_destroy(nngp_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->X, &h->q, &h->L, &h->alpha, &h->flags, &h->lam_d, &h->xt, &h->qt, &h->kss,
                     &h->blk, &h->mean_d, &h->var_d, &h->ssq, &h->sync_ints, &h->Mmat, &h->Kdd, &h->blk2, &h->cross, &h->partial, &h->mean_partial, &h->ka, &h->kb, &h->kqa, &h->kqb, &h->kout, &h->Linv, &h->Linvfull, &h->panel_inv, &h->panel_sync, &h->zkeep, &h->L2, &h->y, &h->app_x, &h->app_y, &h->sel_mean, &h->sel_var, &h->sel_score, &h->sel_key,
-                    &h->sel_state, &h->sel_okey, &h->sel_oidx, &h->sel_max})
+                    &h->sel_state, &h->sel_okey, &h->sel_oidx, &h->sel_max, &h->Wq, &h->wscale, &h->Aq, &h->ascale, &h->slscratch})
     release(*b);
   for (auto& r : h->pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   for (auto e : h->rep_events) cudaEventDestroy(e);
+  for (auto& sp : h->sliced_spans) { cudaEventDestroy(sp.first); cudaEventDestroy(sp.second); }
   if (h->panel_stream) cudaStreamDestroy(h->panel_stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -1441,7 +1625,7 @@ int nngp_reserve(nngp_handle* h, int64_t n_train_max, int64_t dim, int64_t n_tes
 static int append_incremental(nngp_handle* h, int64_t M) {
   const int64_t N = h->N, D = h->D, Nn = N + M;
   const int64_t ldo = h->ldl, ldn = round_up(Nn, 16);
-  h->have_inv = false;    // (latency mode: rebuilt by nngp_append_fit once the factor is extended)
+  h->have_inv = false; h->have_wq = false;    // (latency mode: rebuilt by nngp_append_fit once the factor is extended)
   const double sw2 = h->lsw2[0], sb2 = h->lsb2[0];   // first Dense layer
   StageTimer t_total(h, &h->st.fit_total_ms);
   CKR(ensure(h, h->L2, (size_t)(Nn + 1) * ldn * sizeof(double)));
@@ -1690,6 +1874,8 @@ static int predict_impl(nngp_handle* h, const double* x_test, int64_t T, double*
         timers.emplace_back(h, &h->st.pred_trsm_ms);
         if (T <= latency_rows(h))                      // latency mode, small batch: dependency-free product with L^-1
           CKR(run_inverse_variance(h, blk, ldl, rows, h->kss.as<double>(), h->var_d.as<double>() + t0));
+        else if (h->have_wq)                           // variance_slices: the same product on the int8 tensor cores
+          CKR(run_sliced_variance(h, blk, ldl, rows, h->kss.as<double>(), h->var_d.as<double>() + t0));
         else                                           // solve + variance in one persistent kernel
           CKR(run_predict_solve(h, blk, ldl, rows, h->L.as<double>(), ldl, N, h->kss.as<double>(), h->var_d.as<double>() + t0));
         timers.back().stop();
@@ -1708,6 +1894,12 @@ static int predict_impl(nngp_handle* h, const double* x_test, int64_t T, double*
   t_total.collect();
   for (auto& t : timers) t.collect();
   if (ev_xt_free) h->ev_pool.push_back(ev_xt_free);
+  for (auto& sp : h->sliced_spans) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, sp.first, sp.second) == cudaSuccess) h->st.sliced_ms += ms;
+    h->ev_pool.push_back(sp.first); h->ev_pool.push_back(sp.second);
+  }
+  h->sliced_spans.clear();
   for (auto& sp : h2d_spans) {
     float ms = 0.f;
     if (h->cfg.stats_level >= 1 && cudaEventElapsedTime(&ms, sp.first, sp.second) == cudaSuccess) h->st.h2d_ms += ms;

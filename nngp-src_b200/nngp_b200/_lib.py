@@ -37,6 +37,8 @@ class NngpConfig(C.Structure):
         ("per_layer", C.c_int32),
         ("sigma_w_layers", C.c_double * 16),
         ("sigma_b_layers", C.c_double * 16),
+        ("variance_slices", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
 
@@ -49,7 +51,8 @@ class NngpStats(C.Structure):
         + [("gemm_launches", C.c_int64)]
         + [(n, C.c_double) for n in ("gram_ms", "gram_flops", "gram_evals")]
         + [(n, C.c_int64) for n in ("gram_launches", "kernel_launches", "h2d_bytes", "d2h_bytes", "queries")]
-        + [("replicate_ms", C.c_double), ("replicate_bytes", C.c_int64), ("inverse_ms", C.c_double)]
+        + [("replicate_ms", C.c_double), ("replicate_bytes", C.c_int64), ("inverse_ms", C.c_double),
+           ("sliced_ms", C.c_double), ("sliced_macs", C.c_double)]
     )
 
     def as_dict(self) -> dict:
@@ -64,6 +67,7 @@ EXPORTS = {
     "nngp_abi_version": (C.c_int, []),
     "nngp_build_id": (C.c_char_p, []),
     "nngp_num_gpus": (C.c_int, [_P]),
+    "nngp_sliced_product": (C.c_int, [_P, _P, _I64, _I64, _P, _I64, C.c_int32, C.c_int32, _P, _P]),
     "nngp_state_packed_size": (C.c_int, [_P, C.POINTER(_I64)]),
     "nngp_state_pack": (C.c_int, [_P, _I64, _I64, _P]),
     "nngp_state_import_begin": (C.c_int, [_P, _I64, _I64]),
@@ -204,7 +208,7 @@ class Handle:
 
     def __init__(self, depth=2, sigma_w=1.0, sigma_b=0.0, diag_reg=1e-3, diag_reg_absolute=False,
                  device=-1, max_block_bytes=0, stats_level=1, kernel_type="nngp", n_gpus=1, device_ids=None,
-                 latency_mode=False):
+                 latency_mode=False, variance_slices=0):
         self._lib = load()
         cfg = NngpConfig()
         self._lib.nngp_default_config(C.byref(cfg))
@@ -236,6 +240,7 @@ class Handle:
         for i in range(8):
             cfg.device_ids[i] = int(ids[i]) if i < len(ids) else -1
         cfg.latency_mode = int(bool(latency_mode))
+        cfg.variance_slices = int(variance_slices)
         self.cfg = cfg
         h = C.c_void_p()
         rc = self._lib.nngp_create(C.byref(cfg), C.byref(h))
@@ -270,6 +275,21 @@ class Handle:
         op = _out_ptr(out, (M, N2), "out")
         self._ck(self._lib.nngp_kernel(self._h, x1p, M, x2p, N2, D, op))
         return out
+
+    def sliced_product(self, a, b, slices=7, lower=False, want_rowsq=False):
+        """Diagnostic: ``a @ b.T`` through ``slices`` int8 digit planes per operand on the tcgen05 kind::i8 kernel
+        (the product behind ``variance_slices``).  Returns V, or (V, row sums of V**2) with ``want_rowsq``."""
+        ap, ka = _ptr(a)
+        bp, kb = _ptr(b)
+        M, K = ka.shape
+        N = kb.shape[0]
+        if kb.shape[1] != K:
+            raise ValueError(f"nngp_b200: a has {K} columns but b has {kb.shape[1]}")
+        v = np.empty((M, N), dtype=np.float64)
+        rs = np.empty(M, dtype=np.float64) if want_rowsq else None
+        self._ck(self._lib.nngp_sliced_product(self._h, ap, M, K, bp, N, int(bool(lower)), int(slices),
+                                               _out_ptr(v, (M, N), "v"), _out_ptr(rs, (M,), "rowsq") if want_rowsq else None))
+        return (v, rs) if want_rowsq else v
 
     def fit(self, x, y):
         xp, kx = _ptr(x)

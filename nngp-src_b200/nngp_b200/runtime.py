@@ -15,6 +15,7 @@ _gpus_env = os.environ.get("NNGP_B200_GPUS", "")
 _device_ids = [int(v) for v in _gpus_env.split(",")] if "," in _gpus_env else None
 _n_gpus = int(_gpus_env) if _gpus_env and _device_ids is None else (len(_device_ids) if _device_ids else 1)
 _latency_mode = os.environ.get("NNGP_B200_LATENCY_MODE", "0") not in ("", "0")
+_variance_slices = int(os.environ.get("NNGP_B200_VARIANCE_SLICES", "0") or 0)
 
 
 def set_device(index: int) -> None:
@@ -51,11 +52,18 @@ def set_latency_mode(on: bool) -> None:
     _latency_mode = bool(on)
 
 
+def set_variance_slices(s: int) -> None:
+    """Fits from now on keep int8 digit planes of the inverse factor (s = 5..9 planes, 0 = off); the variance of
+    large prediction batches then runs on the INT8 tensor cores (tcgen05) instead of the FP64 substitution."""
+    global _variance_slices
+    _variance_slices = int(s)
+
+
 def new_handle(spec, diag_reg=0.0, diag_reg_absolute=False, kernel_type="nngp") -> "_lib.Handle":
     return _lib.Handle(depth=spec.depth, sigma_w=spec.sigma_w, sigma_b=spec.sigma_b, diag_reg=diag_reg,
                        diag_reg_absolute=diag_reg_absolute, device=_device, max_block_bytes=_max_block_bytes,
                        stats_level=_stats_level, kernel_type=kernel_type, n_gpus=_n_gpus, device_ids=_device_ids,
-                       latency_mode=_latency_mode)
+                       latency_mode=_latency_mode, variance_slices=_variance_slices if kernel_type == "nngp" else 0)
 
 
 def as_matrix(x, name="x"):
