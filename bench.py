@@ -63,6 +63,7 @@ def parse_args():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--slices", type=int, default=7, help="digit planes of the int8 variance side record (0 = skip it)")
     ap.add_argument("--no-extras", action="store_true", help="skip the C2 side record / fit_n32k / in-process multi-GPU legs")
     return ap.parse_args()
 
@@ -192,7 +193,7 @@ def _guard(fn):
         return {"error": repr(e)}
 
 
-def _time_predict(torch, dist, world, h, local, xte_host, steps, warmup, sample_clocks=True):
+def _time_predict(torch, dist, world, h, local, xte_host, steps, warmup, sample_clocks=True, keep=None):
     """(device-resident ms, e2e ms, stats, e2e stats, clocks) of one handle predicting xte_host per step."""
     t = xte_host.shape[0]
     stream = torch.cuda.ExternalStream(h.stream, device=torch.device("cuda", local))
@@ -246,6 +247,8 @@ def _time_predict(torch, dist, world, h, local, xte_host, steps, warmup, sample_
     st_e2e = h.stats()
     if not np.all(np.isfinite(mean_dev[:1024].cpu().numpy())) or not np.array_equal(mean_pin.numpy(), mean_dev.cpu().numpy()):
         raise SystemExit("bench.py: non-finite predictions, or the host-buffer and device-buffer paths disagree")
+    if keep is not None:
+        keep["mean"], keep["var"] = mean_dev.cpu().numpy(), var_dev.cpu().numpy()
     return ms_total, ms_e2e, e2e_steps, st, st_e2e, clocks
 
 
@@ -310,7 +313,9 @@ def run_b200(args):
         bcast = {"ms": sec * 1e3, "bytes_per_rank": nbytes, "gb_per_s": nbytes / sec / 1e9,
                  "what": "packed state (X, alpha, lower triangle of L) in 256 MB chunks: pack -> NCCL broadcast -> unpack"}
 
-    ms_total, ms_e2e, e2e_steps, st, st_e2e, clocks = _time_predict(torch, dist, world, h, local, xte_host, args.steps, warmup, sample_clocks=(rank == 0))
+    kept = {}
+    ms_total, ms_e2e, e2e_steps, st, st_e2e, clocks = _time_predict(torch, dist, world, h, local, xte_host, args.steps, warmup,
+                                                                    sample_clocks=(rank == 0), keep=kept if rank == 0 else None)
 
     in_process = None
     hard_exit = False
@@ -417,6 +422,47 @@ def run_b200(args):
     if world == 1 and not args.no_extras:
         h.close()
         torch.cuda.empty_cache()
+        if args.slices > 0:
+            # The same workload with the variance product on the INT8 tensor cores (cfg.variance_slices: tcgen05.mma
+            # kind::i8 on digit planes of K_* and L^-1, FP64-equivalent to ~2^-7s).  A side record: `value` above stays
+            # the all-FP64 path.
+            try:
+                hs = _lib.Handle(depth=depth, diag_reg=1e-3, device=local, stats_level=2, variance_slices=args.slices)
+                hs.fit(xtr, ytr)
+                hs.stats_reset()
+                hs.fit(xtr, ytr)
+                sfit = hs.stats()
+                ks = {}
+                k_s = min(args.steps, 5)
+                ms_s, ms_se, k_se, st_s, _st_se, clk_s = _time_predict(torch, dist, 1, hs, local, xte_host, k_s, 3, keep=ks)
+                tops = 2.0 * st_s["sliced_macs"] / max(st_s["sliced_ms"], 1e-9) / 1e9
+                pk_s, pk_b = peaks.get("bf16_tflops_sustained"), peaks.get("bf16_tflops")
+                out["sliced"] = {
+                    "what": "variance_slices=%d: V = K_* L^-T as %d exact int8 plane products on tcgen05 (kind::i8, TMEM "
+                            "accumulators) against the explicit inverse factor; the mean and the Gram stay FP64" % (
+                                args.slices, args.slices * (args.slices + 1) // 2),
+                    "value": k_s * t_rank / (ms_s / 1e3), "unit": UNIT, "ms_per_step": ms_s / k_s, "steps": k_s,
+                    "e2e_value": k_se * t_rank / (ms_se / 1e3),
+                    "speedup_vs_fp64_path": (k_s * t_rank / (ms_s / 1e3)) / value,
+                    "mean_bitwise_equal_fp64_path": bool(np.array_equal(ks["mean"], kept["mean"])),
+                    "var_max_rel_vs_fp64_path": float(np.max(np.abs(ks["var"] - kept["var"]) / np.abs(kept["var"]))),
+                    "std_max_rel_vs_fp64_path": float(np.max(np.abs(np.sqrt(ks["var"]) - np.sqrt(kept["var"])) / np.sqrt(kept["var"]))),
+                    "stage_ms_per_step": {k: st_s[k] / k_s for k in ("pred_gram_ms", "pred_trsm_ms", "sliced_ms", "pred_total_ms")},
+                    "fit_seconds_device": sfit["fit_total_ms"] / 1e3, "inverse_ms": sfit["inverse_ms"],
+                    "clocks": clk_s,
+                    "roofline": {"bound": "tensor", "kernel": "sliced_gemm_kernel (TMA + tcgen05.mma kind::i8 M128 N256 K32, int32 accumulators in TMEM)",
+                                 "achieved": tops, "unit": "TOP/s (int8, issued)",
+                                 "peak": 2.0 * pk_s if pk_s else None, "frac": tops / (2.0 * pk_s) if pk_s else None,
+                                 "frac_of_burst": tops / (2.0 * pk_b) if pk_b else None,
+                                 "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops_sustained (kind::i8 issues twice the MACs of "
+                                                "kind::f16 per instruction slot; the kernel runs for seconds under the power cap)",
+                                 "fp64_equivalent_tflops": float(t_rank) * n * n * k_s / (st_s["sliced_ms"] / 1e3) / 1e12,
+                                 "share_of_step": st_s["sliced_ms"] / max(st_s["pred_total_ms"], 1e-9)},
+                }
+                hs.close()
+                torch.cuda.empty_cache()
+            except Exception as e:  # noqa: BLE001
+                out["sliced"] = {"error": repr(e)}
         if args.workload != "c2":          # the round-1 headline config, for continuity
             try:
                 n2, t2, d2, dep2, jd2, desc2 = WORKLOADS["c2"]

@@ -780,7 +780,8 @@ double sliced_macs(int64_t row_tiles, int64_t col_tiles, int64_t K, int tri, int
   return macs * (double)(s * (s + 1) / 2);
 }
 
-// V = A W^T from the digit planes: vpart[col_tiles][rows] row sums of V^2 per 256-column tile and/or V itself
+// V = A W^T from the digit planes: vpart[2 col_tiles][rows] row sums of V^2 per 128-column half tile and/or V itself
+// (ra: rows per K_* plane, a multiple of 256)
 int launch_sliced(nngp_handle* h, const int8_t* qa, int64_t ra, const double* sa, const int8_t* qw, int64_t rb,
                   const double* sw, int64_t ldq, int s, int tri, int64_t rows, int64_t N, int64_t K, double* vpart, double* V,
                   int64_t ldv) {
@@ -791,14 +792,14 @@ int launch_sliced(nngp_handle* h, const int8_t* qa, int64_t ra, const double* sa
   p.ra = ra; p.rb = rb; p.rscale = sa; p.cscale = sw; p.vpart = vpart; p.V = V; p.ldv = ldv;
   if ((int64_t)s * ra >= (1LL << 31) || (int64_t)s * rb >= (1LL << 31))
     return fail(h, NNGP_EINVAL, "internal: digit-plane row range too large");
-  const int64_t tiles = (int64_t)p.row_tiles * p.col_tiles;
+  const int64_t tiles = (int64_t)((p.row_tiles + SL_RT - 1) / SL_RT) * p.col_tiles;
   static const int grid_env = [] { const char* e = getenv("NNGP_SLICED_GRID"); return e ? atoi(e) : 0; }();
   int grid = grid_env > 0 ? grid_env : (h->sm_count / SL_SUPER) * SL_SUPER;   // CTAs 4k..4k+3 share a K_* row tile
   grid = (int)std::min<int64_t>(grid, tiles);
-  CKR(ensure(h, h->slscratch, (size_t)grid * SL_BM * SL_BN * sizeof(double)));
+  CKR(ensure(h, h->slscratch, (size_t)grid * SL_RT * SL_BM * SL_BN * sizeof(double)));
   p.scratch = h->slscratch.as<double>();
   CUtensorMap tmA, tmB;
-  CKR(get_tmap_u8(h, qa, (uint64_t)s * ra, (uint64_t)ldq, SL_BM, &tmA));
+  CKR(get_tmap_u8(h, qa, (uint64_t)s * ra, (uint64_t)ldq, SL_RT * SL_BM, &tmA));
   CKR(get_tmap_u8(h, qw, (uint64_t)s * rb, (uint64_t)ldq, SL_BN, &tmB));
   CK(cudaFuncSetAttribute(sliced_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM_BYTES));   // (per device)
   sliced_gemm_kernel<<<grid, SL_THREADS, SL_SMEM_BYTES, h->stream>>>(tmA, tmB, p);
@@ -830,21 +831,21 @@ int run_sliced_variance(nngp_handle* h, const double* B, int64_t ldb, int64_t ro
   const int s = h->cfg.variance_slices;
   const int64_t N = h->N, ldq = h->wq_ldq;
   const int col_tiles = (int)((N + SL_BN - 1) / SL_BN);
-  const int64_t wave_rows = (int64_t)(h->sm_count / SL_SUPER) * SL_BM;
+  const int64_t wave_rows = (int64_t)(h->sm_count / SL_SUPER) * SL_RT * SL_BM;
   int64_t sb = ((16LL << 30) / ((int64_t)s * ldq)) / wave_rows * wave_rows;
-  sb = std::max<int64_t>(sb, SL_BM);
-  sb = std::min<int64_t>(sb, round_up(rows, SL_BM));
+  sb = std::max<int64_t>(sb, SL_RT * SL_BM);
+  sb = std::min<int64_t>(sb, round_up(rows, SL_RT * SL_BM));
   CKR(ensure(h, h->Aq, (size_t)s * sb * ldq));
   CKR(ensure(h, h->ascale, (size_t)sb * sizeof(double)));
-  CKR(ensure(h, h->partial, (size_t)col_tiles * sb * sizeof(double)));
+  CKR(ensure(h, h->partial, (size_t)2 * col_tiles * sb * sizeof(double)));
   cudaEvent_t a = get_event(h), b = get_event(h);
   cudaEventRecord(a, h->stream);
   for (int64_t r0 = 0; r0 < rows; r0 += sb) {
-    const int64_t nr = std::min<int64_t>(sb, rows - r0), ra = round_up(nr, SL_BM);
+    const int64_t nr = std::min<int64_t>(sb, rows - r0), ra = round_up(nr, SL_RT * SL_BM);
     CKR(slice_matrix(h, B + r0 * ldb, ldb, nr, N, 0, s, ra, ldq, h->Aq.as<int8_t>(), h->ascale.as<double>()));
     CKR(launch_sliced(h, h->Aq.as<int8_t>(), ra, h->ascale.as<double>(), h->Wq.as<int8_t>(), h->wq_rb,
                       h->wscale.as<double>(), ldq, s, 1, nr, N, N, h->partial.as<double>(), nullptr, 0));
-    var_from_partial_kernel<<<(unsigned)((nr + 255) / 256), 256, 0, h->stream>>>(kss + r0, h->partial.as<double>(), col_tiles, (int)nr, var + r0);
+    var_from_partial_kernel<<<(unsigned)((nr + 255) / 256), 256, 0, h->stream>>>(kss + r0, h->partial.as<double>(), 2 * col_tiles, (int)nr, var + r0);
     h->st.kernel_launches++;
   }
   cudaEventRecord(b, h->stream);
@@ -1252,7 +1253,7 @@ int nngp_sliced_product(nngp_handle* h, const double* a, int64_t M, int64_t K, c
     return fail(h, NNGP_EINVAL, "nngp_sliced_product: bad argument (M=%lld K=%lld N=%lld)", (long long)M, (long long)K, (long long)N);
   if (slices < 1 || slices > SL_MAX_SLICES) return fail(h, NNGP_EINVAL, "nngp_sliced_product: slices must be 1..%d", SL_MAX_SLICES);
   if (lower && N != K) return fail(h, NNGP_EINVAL, "nngp_sliced_product: a triangular B must be square (N=%lld K=%lld)", (long long)N, (long long)K);
-  const int64_t ldq = round_up(K, SL_BK), ra = round_up(M, SL_BM), rb = round_up(N, SL_BN);
+  const int64_t ldq = round_up(K, SL_BK), ra = round_up(M, SL_RT * SL_BM), rb = round_up(N, SL_BN);
   if ((int64_t)slices * 4096 * ldq >= (1LL << 31)) return fail(h, NNGP_EINVAL, "nngp_sliced_product: K too large for int32 plane sums");
   CKR(bind_device(h));
   const int col_tiles = (int)(rb / SL_BN);
@@ -1265,7 +1266,7 @@ int nngp_sliced_product(nngp_handle* h, const double* a, int64_t M, int64_t K, c
   if (rc == NNGP_OK) rc = ensure(h, sa, (size_t)M * 8);
   if (rc == NNGP_OK) rc = ensure(h, sb, (size_t)N * 8);
   if (rc == NNGP_OK && v_out) rc = ensure(h, dV, (size_t)M * N * 8);
-  if (rc == NNGP_OK) rc = ensure(h, vp, (size_t)col_tiles * M * 8);
+  if (rc == NNGP_OK) rc = ensure(h, vp, (size_t)2 * col_tiles * M * 8);
   if (rc == NNGP_OK) rc = ensure(h, rs, (size_t)M * 8);
   auto run = [&]() -> int {
     CK(cudaMemcpyAsync(dA.p, a, (size_t)M * K * 8, cudaMemcpyDefault, h->stream));
@@ -1276,7 +1277,7 @@ int nngp_sliced_product(nngp_handle* h, const double* a, int64_t M, int64_t K, c
                       M, N, K, vp.as<double>(), v_out ? dV.as<double>() : nullptr, N));
     if (v_out) CK(cudaMemcpyAsync(v_out, dV.p, (size_t)M * N * 8, cudaMemcpyDefault, h->stream));
     if (rowsq_out) {
-      rowsq_from_partial_kernel<<<(unsigned)((M + 255) / 256), 256, 0, h->stream>>>(vp.as<double>(), col_tiles, (int)M, rs.as<double>());
+      rowsq_from_partial_kernel<<<(unsigned)((M + 255) / 256), 256, 0, h->stream>>>(vp.as<double>(), 2 * col_tiles, (int)M, rs.as<double>());
       CK(cudaMemcpyAsync(rowsq_out, rs.p, (size_t)M * 8, cudaMemcpyDefault, h->stream));
     }
     CK(cudaStreamSynchronize(h->stream));

@@ -11,28 +11,34 @@
 // (tools/ozaki_study.py, tests/test_gpu_sliced.py).  s (s+1) / 2 integer GEMMs replace one FP64 GEMM.
 //
 // Kernel: persistent, one CTA per SM, warp-specialised the Blackwell way:
-//   warp 0 (one lane)  TMA producer: 128-byte-swizzled boxes of the digit planes into a 4-stage ring (mbarrier tx)
-//   warp 1 (one lane)  MMA issuer: tcgen05.mma M=128 N=256 K=32, int32 accumulators in TMEM, double-buffered
-//                      (2 x 256 columns); tcgen05.commit releases ring stages / publishes accumulators
-//   warps 2-5          epilogue: tcgen05.ld the finished group, fold it into the FP64 running sum (Horner in 2^-7)
+//   warp 0 (one lane)  TMA producer: 128-byte-swizzled boxes of the digit planes into a 3-stage ring (mbarrier tx);
+//                      a stage holds 128 bytes of K for TWO row tiles of K_* (256 rows) and one column tile of W
+//   warp 1 (one lane)  MMA issuer: tcgen05.mma M=128 N=256 K=32, the two row tiles into two int32 accumulators that
+//                      fill the 512 TMEM columns; tcgen05.commit releases ring stages / publishes the accumulators
+//   warps 2-9          epilogue: tcgen05.ld the finished group, fold it into the FP64 running sum (Horner in 2^-7)
 //                      held in an L2-resident per-CTA scratch tile; on the last group scale by the two row exponents,
-//                      square, reduce along the row -> one partial per (row, column tile); V itself is never stored.
-// Tile order: column tiles in groups of 4 ("supercolumns") from the widest triangular extent down, row tiles inside,
-// the 4 column tiles of one row tile adjacent -- CTAs 4k..4k+3 stream the same K_* planes in lockstep (the second to
-// fourth read hit L2) and all CTAs of a wave stream the same W planes.
+//                      square, reduce along the row -> two partials per (row, column tile); V itself is never stored.
+// The kernel is bound by the L2 -> SM fabric, not by the tensor pipe (one 128 x 256 x 128 MMA set takes 512 clk, the
+// fabric delivers ~43 B/clk/SM): sharing each W stage between two accumulators cuts the bytes per MMA set from 48 KiB
+// to 32 KiB (first version: 2.3 POP/s, exactly the fabric limit for 48 KiB).
+// Tile order: column tiles in groups of 4 ("supercolumns") from the widest triangular extent down, row-tile pairs
+// inside, the 4 column tiles of one pair adjacent -- CTAs 4k..4k+3 stream the same K_* planes in lockstep (the second
+// to fourth read hit L2, sparing HBM) and all CTAs of a wave stream the same W planes.
 #pragma once
 #include "ptx.cuh"
 
 namespace nngp {
 
-constexpr int SL_BM = 128;                 // rows of K_* per tile = TMEM lanes
+constexpr int SL_BM = 128;                 // rows per MMA = TMEM lanes
+constexpr int SL_RT = 2;                   // row tiles per CTA tile: two M=128 MMAs share every W stage (2 accumulators)
 constexpr int SL_BN = 256;                 // rows of W (columns of V) per tile = MMA N
 constexpr int SL_BK = 128;                 // bytes (= int8 elements) of K per ring stage: one swizzle row
 constexpr int SL_UK = 32;                  // K of one tcgen05.mma kind::i8
-constexpr int SL_STAGES = 4;
-constexpr int SL_A_BYTES = SL_BM * SL_BK;  // 16 KiB
-constexpr int SL_B_BYTES = SL_BN * SL_BK;  // 32 KiB
-constexpr int SL_THREADS = 192;
+constexpr int SL_STAGES = 3;
+constexpr int SL_A_BYTES = SL_RT * SL_BM * SL_BK;  // 32 KiB: one TMA box of 256 rows
+constexpr int SL_B_BYTES = SL_BN * SL_BK;          // 32 KiB
+constexpr int SL_EPI_WARPS = 8;            // two per TMEM lane quarter, each half of the columns
+constexpr int SL_THREADS = 64 + 32 * SL_EPI_WARPS;
 constexpr int SL_SUPER = 4;                // column tiles per supercolumn
 constexpr int SL_MAX_SLICES = 9;
 constexpr int SL_SMEM_BYTES = SL_STAGES * (SL_A_BYTES + SL_B_BYTES) + 1024 /*alignment*/ + 256 /*barriers*/;
@@ -48,8 +54,8 @@ struct SlicedParams {
   long long ra, rb;        // rows per plane in the stacked plane arrays of K_* / W
   const double* rscale;    // [rows]  2^(e-6) of the K_* rows
   const double* cscale;    // [N]     2^(e-6) of the W rows
-  double* scratch;         // gridDim.x x 256 x 128 running sums
-  double* vpart;           // [col_tiles][rows] sum over the tile's columns of V^2      (may be null)
+  double* scratch;         // gridDim.x x 2 x 256 x 128 running sums
+  double* vpart;           // [2 col_tiles][rows] sum over each 128-column half tile of V^2 (may be null)
   double* V;               // [rows][ldv] the product itself (diagnostics / tests)     (may be null)
   long long ldv;
 };
@@ -140,21 +146,22 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {   /
 }
 
 // ---- tile order -------------------------------------------------------------------------------------------------
-struct SlicedTile { int it, jt, nkb; };
+struct SlicedTile { int ip, jt, nkb; };   // row-tile pair, column tile, K blocks
 __device__ __forceinline__ bool sliced_tile(const SlicedParams& p, long long idx, SlicedTile& t) {
-  const long long total = (long long)p.row_tiles * p.col_tiles;
+  const int row_pairs = (p.row_tiles + SL_RT - 1) / SL_RT;
+  const long long total = (long long)row_pairs * p.col_tiles;
   if (idx >= total) return false;
   const int nsup = (p.col_tiles + SL_SUPER - 1) / SL_SUPER;
   const int wlast = p.col_tiles - (nsup - 1) * SL_SUPER;          // width of the last (widest-K) supercolumn
-  const long long first = (long long)p.row_tiles * wlast;
+  const long long first = (long long)row_pairs * wlast;
   int sup, c;
   if (idx < first) {
-    sup = nsup - 1; t.it = (int)(idx / wlast); c = (int)(idx % wlast);
+    sup = nsup - 1; t.ip = (int)(idx / wlast); c = (int)(idx % wlast);
   } else {
-    const long long r = idx - first, per = (long long)p.row_tiles * SL_SUPER;
+    const long long r = idx - first, per = (long long)row_pairs * SL_SUPER;
     sup = nsup - 2 - (int)(r / per);
     const long long in = r % per;
-    t.it = (int)(in / SL_SUPER); c = (int)(in % SL_SUPER);
+    t.ip = (int)(in / SL_SUPER); c = (int)(in % SL_SUPER);
   }
   t.jt = sup * SL_SUPER + c;
   // the whole supercolumn runs the K extent of its last column tile, so that its CTAs stay in lockstep
@@ -175,15 +182,16 @@ sliced_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ringB + SL_STAGES * SL_B_BYTES);
   uint64_t* empty_bar = full_bar + SL_STAGES;
   uint64_t* acc_full = empty_bar + SL_STAGES;
-  uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* acc_empty = acc_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < SL_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 32 * SL_EPI_WARPS);
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -205,13 +213,13 @@ sliced_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (long long idx = blockIdx.x; sliced_tile(p, idx, t); idx += gridDim.x) {
         for (int g = p.s - 1; g >= 0; --g)
           for (int pa = 0; pa <= g; ++pa) {
-            const int a_row = (int)(pa * p.ra) + t.it * SL_BM;
+            const int a_row = (int)(pa * p.ra) + t.ip * (SL_RT * SL_BM);
             const int b_row = (int)((g - pa) * p.rb) + t.jt * SL_BN;
             for (int kb = 0; kb < t.nkb; ++kb, ++n) {
               const uint32_t st = n % SL_STAGES, ph = (n / SL_STAGES) & 1u;
               mbar_wait(&empty_bar[st], ph ^ 1u);
               mbar_arrive_expect_tx(&full_bar[st], SL_A_BYTES + SL_B_BYTES);
-              tma_load_2d(ringA + st * SL_A_BYTES, &tmA, kb * SL_BK, a_row, &full_bar[st]);
+              tma_load_2d(ringA + st * SL_A_BYTES, &tmA, kb * SL_BK, a_row, &full_bar[st]);   // both row tiles: 256 rows
               tma_load_2d(ringB + st * SL_B_BYTES, &tmB, kb * SL_BK, b_row, &full_bar[st]);
             }
           }
@@ -222,73 +230,82 @@ sliced_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       uint32_t n = 0, a = 0;
       SlicedTile t;
       for (long long idx = blockIdx.x; sliced_tile(p, idx, t); idx += gridDim.x) {
+        const bool two = t.ip * SL_RT + 1 < p.row_tiles;     // the second row tile exists
         for (int g = p.s - 1; g >= 0; --g, ++a) {
-          const uint32_t ab = a & 1u, aph = (a >> 1) & 1u;
-          mbar_wait(&acc_empty[ab], aph ^ 1u);          // the epilogue has drained this accumulator
+          mbar_wait(acc_empty, (a & 1u) ^ 1u);              // the epilogue has drained both accumulators
           tc_fence_after();
-          const uint32_t tmem_d = tmem_base + ab * SL_BN;
           uint32_t acc = 0;
           for (int pa = 0; pa <= g; ++pa)
             for (int kb = 0; kb < t.nkb; ++kb, ++n) {
               const uint32_t st = n % SL_STAGES, ph = (n / SL_STAGES) & 1u;
               mbar_wait(&full_bar[st], ph);
               tc_fence_after();
-              const uint64_t da = tc_smem_desc(smem_u32(ringA + st * SL_A_BYTES));
+              const uint64_t da0 = tc_smem_desc(smem_u32(ringA + st * SL_A_BYTES));
+              const uint64_t da1 = tc_smem_desc(smem_u32(ringA + st * SL_A_BYTES + SL_BM * SL_BK));
               const uint64_t db = tc_smem_desc(smem_u32(ringB + st * SL_B_BYTES));
 #pragma unroll
               for (int k = 0; k < SL_BK / SL_UK; ++k) {   // +32 bytes of K inside the swizzle row: +2 in the address field
-                tc_mma_i8(tmem_d, da + 2u * k, db + 2u * k, SL_IDESC, acc);
+                tc_mma_i8(tmem_base, da0 + 2u * k, db + 2u * k, SL_IDESC, acc);
+                if (two) tc_mma_i8(tmem_base + SL_BN, da1 + 2u * k, db + 2u * k, SL_IDESC, acc);
                 acc = 1;
               }
               tc_commit(&empty_bar[st]);                 // stage free once these MMAs have read it
             }
-          tc_commit(&acc_full[ab]);                      // group complete: hand the accumulator to the epilogue
+          tc_commit(acc_full);                           // group complete: hand the accumulators to the epilogue
         }
       }
     }
-  } else {             // ===== epilogue warps 2..5 =====
+  } else {             // ===== epilogue warps =====
     const int quarter = warp & 3;                        // TMEM lanes this warp may read: 32 quarter .. +31
+    const int half = (warp - 2) >> 2;                    // which 128 of the 256 columns
     const int row = quarter * 32 + lane;
-    double* sc = p.scratch + (long long)blockIdx.x * (SL_BN * SL_BM) + row;
+    double* sc = p.scratch + (long long)blockIdx.x * (SL_RT * SL_BN * SL_BM) + row;
     uint32_t a = 0;
     SlicedTile t;
     for (long long idx = blockIdx.x; sliced_tile(p, idx, t); idx += gridDim.x) {
-      const int grow = t.it * SL_BM + row;
-      const double rs = (grow < p.rows) ? p.rscale[grow] : 0.0;
-      double sum = 0.0;
+      const int ntile = (t.ip * SL_RT + 1 < p.row_tiles) ? 2 : 1;
+      double sum[SL_RT] = {0.0, 0.0};
       for (int g = p.s - 1; g >= 0; --g, ++a) {
-        const uint32_t ab = a & 1u, aph = (a >> 1) & 1u;
-        mbar_wait(&acc_full[ab], aph);
+        mbar_wait(acc_full, a & 1u);
         __syncwarp();
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + ab * SL_BN;
         const bool first = (g == p.s - 1);
-        for (int c0 = 0; c0 < SL_BN; c0 += 32) {
-          uint32_t r[32];
-          tc_ld32(taddr + c0, r);
-          if (g > 0) {
+        for (int h = 0; h < ntile; ++h) {
+          const int grow = (t.ip * SL_RT + h) * SL_BM + row;
+          const double rs = (grow < p.rows) ? p.rscale[grow] : 0.0;
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + h * SL_BN + half * (SL_BN / 2);
+          double* sch = sc + (h * SL_BN + half * (SL_BN / 2)) * SL_BM;
+          for (int c0 = 0; c0 < SL_BN / 2; c0 += 32) {
+            uint32_t r[32];
+            tc_ld32(taddr + c0, r);
+            if (g > 0) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              double* sp = sc + (c0 + j) * SL_BM;
-              const double c = (double)(int)r[j];
-              *sp = first ? c : fma(*sp, 0.0078125, c);   // S_g = C_g + 2^-7 S_(g+1)
-            }
-          } else {
+              for (int j = 0; j < 32; ++j) {
+                double* sp = sch + (c0 + j) * SL_BM;
+                const double c = (double)(int)r[j];
+                *sp = first ? c : fma(*sp, 0.0078125, c);   // S_g = C_g + 2^-7 S_(g+1)
+              }
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = t.jt * SL_BN + c0 + j;
-              const double c = (double)(int)r[j];
-              const double sv = first ? c : fma(sc[(c0 + j) * SL_BM], 0.0078125, c);
-              const double v = (col < p.N) ? sv * rs * __ldg(p.cscale + col) : 0.0;
-              sum = fma(v, v, sum);
-              if (p.V && grow < p.rows && col < p.N) p.V[(long long)grow * p.ldv + col] = v;
+              for (int j = 0; j < 32; ++j) {
+                const int col = t.jt * SL_BN + half * (SL_BN / 2) + c0 + j;
+                const double c = (double)(int)r[j];
+                const double sv = first ? c : fma(sch[(c0 + j) * SL_BM], 0.0078125, c);
+                const double v = (col < p.N) ? sv * rs * __ldg(p.cscale + col) : 0.0;
+                sum[h] = fma(v, v, sum[h]);
+                if (p.V && grow < p.rows && col < p.N) p.V[(long long)grow * p.ldv + col] = v;
+              }
             }
           }
         }
         tc_fence_before();
-        mbar_arrive(&acc_empty[ab]);
+        mbar_arrive(acc_empty);
       }
-      if (p.vpart && grow < p.rows) p.vpart[(long long)t.jt * p.rows + grow] = sum;
+      if (p.vpart)
+        for (int h = 0; h < ntile; ++h) {
+          const int grow = (t.ip * SL_RT + h) * SL_BM + row;
+          if (grow < p.rows) p.vpart[((long long)t.jt * 2 + half) * p.rows + grow] = sum[h];   // two partials per column tile
+        }
     }
   }
 

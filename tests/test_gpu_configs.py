@@ -50,13 +50,15 @@ def _record(name, rec):
         pass
 
 
-def _full_size_case(lib, synth, name, n, t, d, depth, join_dims, sample):
+def _full_size_case(lib, synth, name, n, t, d, depth, join_dims, sample, slices=0):
     """Fit at the config's full N, predict `t` test rows (the bench's per-GPU batch), check
        (i)   lambda = 1e-3 * mean(q_L) from the COMPUTED diagonal,
        (ii)  the posterior at the training rows: mean = y - lambda*alpha, 0 < var < lambda,
        (iii) a sampled-row ORACLE check (`sample` rows spread over the batch) at 1e-6 (1e-3 on q-error),
        (iv)  the sampled rows predicted alone (few row tiles: the pipelined kernel variant) == the same rows inside the
-             big batch, bit for bit."""
+             big batch, bit for bit,
+       (v)   with `slices`: the same batch on a handle with variance_slices (variance product on the int8 tensor
+             cores): mean bitwise the FP64 handle's, sampled variances against the oracle at the same 1e-6."""
     xtr = synth.encodings(n, d, 1, join_dims=join_dims)
     ytr = synth.labels(xtr, join_dims)
     if np.ptp(ytr) < 1.0:                       # the independence surrogate saturates at wide encodings
@@ -83,6 +85,16 @@ def _full_size_case(lib, synth, name, n, t, d, depth, join_dims, sample):
     assert np.array_equal(m_s, mean[idx]) and np.array_equal(v_s, var[idx])
     stats = h.stats()
     h.close()
+    sliced = None
+    if slices:
+        hs = lib.Handle(depth=depth, stats_level=1, variance_slices=slices)
+        hs.fit(xtr, ytr)
+        t0 = time.perf_counter()
+        mean_s, var_s = hs.predict(xte)
+        sliced = {"slices": slices, "predict_wall_s": time.perf_counter() - t0, "sliced_ms": hs.stats()["sliced_ms"],
+                  "var_max_rel_vs_fp64_path": float(np.max(np.abs(var_s - var) / np.abs(var)))}
+        assert np.array_equal(mean_s, mean) and np.all(var_s > 0)
+        hs.close()
     t0 = time.perf_counter()
     ref = oracle.Fit(xtr, ytr, depth)
     ofit_s = time.perf_counter() - t0
@@ -91,19 +103,24 @@ def _full_size_case(lib, synth, name, n, t, d, depth, join_dims, sample):
     rm, rv = ref.predict(xte[idx])
     e_mean, e_var = relmax(m_s, rm), float(np.max(np.abs(v_s - rv) / np.abs(rv)))
     e_q = float(np.max(np.abs(2.0 ** np.abs(m_s - rm) - 1.0)))
-    _record(name, {"config": {"n_train": n, "test_rows": t, "dim": d, "depth": depth, "join_dims": join_dims},
+    if sliced:
+        sliced["max_rel_err_var_vs_oracle"] = float(np.max(np.abs(var_s[idx] - rv) / np.abs(rv)))
+        sliced["max_rel_err_std_vs_oracle"] = float(np.max(np.abs(np.sqrt(var_s[idx]) - np.sqrt(rv)) / np.sqrt(rv)))
+    _record(name, {"sliced": sliced, "config": {"n_train": n, "test_rows": t, "dim": d, "depth": depth, "join_dims": join_dims},
                    "sampled_rows": int(sample), "max_rel_err_mean": e_mean, "max_rel_err_var": e_var,
                    "max_q_error_dev": e_q, "alpha_rel_err": relmax(alpha, ref.alpha), "lambda": lam,
                    "oracle_lambda": ref.lam, "gpu_fit_wall_s": fit_s, "gpu_fit_device_s": stats["fit_total_ms"] / 1e3,
                    "gpu_predict_wall_s": pred_s, "oracle_fit_s": ofit_s, "host_cores": len(os.sched_getaffinity(0)),
                    "tolerance": "1e-6 relative on mean / variance, 1e-3 on q-error (north_star)"})
     assert e_mean < 1e-6 and e_var < 1e-6 and e_q < 1e-3
+    if sliced:
+        assert sliced["max_rel_err_var_vs_oracle"] < 1e-6, sliced
 
 
 def test_c3_full_size_parity(lib, synth):
     """BASELINE config C3 per GPU: N = 32 768 (W = 512 Cholesky panels), D = 256, depth 3, 131 072 test rows (one
     34 GB row block).  The oracle's fit at this size is ~1-2 minutes of host CPU."""
-    _full_size_case(lib, synth, "c3", 32768, 131072, 256, 3, 0, 512)
+    _full_size_case(lib, synth, "c3", 32768, 131072, 256, 3, 0, 512, slices=7)
 
 
 def test_c5_full_size_parity(lib, synth):

@@ -60,6 +60,11 @@ def full(path, out):
         for w in WANT:
             if w in idx:
                 d[w] = f"{r[idx[w]]} {units[idx[w]]}".strip()
+        for h in hdr:      # tcgen05 kernels: every tensor / TMEM / L2-fabric counter the capture holds
+            if re.search(r"pipe_tensor|tmem|utc|lts__t_sectors_srcunit_tex|l1tex__m_xbar2l1tex_read_bytes|lts__throughput|sm__cycles_active.avg$|clocks", h) and h not in d:
+                val = r[idx[h]]
+                if val not in ("", "0", "n/a"):
+                    d[h] = f"{val} {units[idx[h]]}".strip()
         for h in hdr:
             if "issue_stalled" in h and h.endswith("_per_warp_active.pct") or ("warp_issue_stalled" in h and h.endswith(".pct")):
                 try:

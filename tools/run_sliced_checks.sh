@@ -7,3 +7,5 @@ timeout 300 python tests/checks/sliced_check.py model > gpurun_out/sliced_model.
 tail -6 gpurun_out/sliced_model.log
 timeout 300 python tests/checks/sliced_check.py time 8192 65536 128 2 > gpurun_out/sliced_time.log 2>&1; echo "time rc=$?"
 tail -4 gpurun_out/sliced_time.log
+timeout 600 python tests/checks/sliced_check.py time 32768 131072 256 3 > gpurun_out/sliced_time_c3.log 2>&1; echo "time c3 rc=$?"
+tail -4 gpurun_out/sliced_time_c3.log
