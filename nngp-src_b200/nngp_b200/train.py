@@ -15,7 +15,8 @@ lines (:157-170), ``[upper, lower]`` per numerical column scaled to [0, 1000] wi
   * the report is the symmetric q-error summary instead of ``util.PredictionStatistics`` (seaborn / matplotlib);
   * join queries (``--relations a,b``) need the reference's schema loaders (pandas, out of the hot-path scope): run the
     reference's own ``train.py`` on the import shims instead (INTEGRATION.md section 1);
-  * ``--gpus G`` predicts on G GPUs of this process (``runtime.set_gpus``), ``--latency`` builds the explicit inverse.
+  * ``--gpus G`` predicts on G GPUs of this process (``runtime.set_gpus``), ``--latency`` builds the explicit inverse,
+    ``--variance_slices S`` moves the variance product of large batches to the INT8 tensor cores.
 The reference's ``--kernel_type gp`` branch (train.py:60-150) is broken upstream (``jit`` undefined) and not mirrored.
 """
 from __future__ import annotations
@@ -110,6 +111,8 @@ def main(args):
         runtime.set_gpus(args.gpus)
     if args.latency:
         runtime.set_latency_mode(True)
+    if args.variance_slices:
+        runtime.set_variance_slices(args.variance_slices)
     X, Y = load_training_data(args)
     print("number of query: {}".format(X.shape[0]))
     X_train, Y_train, X_test, Y_test, _xv, _yv = train_test_val_split(X, Y, train_frac=0.6, test_frac=0.2)
@@ -133,6 +136,8 @@ def build_parser() -> ArgumentParser:
     p.add_argument("--col_ranges", type=str, default="", help='JSON {"col": [min, max], ...} instead of <data_path>/<relation>.csv')
     p.add_argument("--gpus", type=int, default=1, help="GPUs of this process to shard prediction over")
     p.add_argument("--latency", action="store_true", help="latency mode: explicit inverse factor for small batches")
+    p.add_argument("--variance_slices", type=int, default=0,
+                   help="5..9: variance of large batches on the INT8 tensor cores (digit planes, tcgen05); 0 = all FP64")
     return p
 
 
