@@ -688,11 +688,12 @@ int build_inverse(nngp_handle* h) {
   return NNGP_OK;
 }
 
-// Row count up to which nngp_predict uses the explicit inverse (NNGP_LATENCY_ROWS overrides; read per call).
+// Row count up to which nngp_predict uses the explicit inverse in FP64 (NNGP_LATENCY_ROWS overrides; read per call).
+// With digit planes (variance_slices) the int8 product takes over as soon as the batch fills the GPU with tiles.
 int64_t latency_rows(const nngp_handle* h) {
   if (!h->have_inv) return 0;
   const char* e = getenv("NNGP_LATENCY_ROWS");
-  return e ? atoll(e) : 4096;
+  return e ? atoll(e) : (h->have_wq ? 767 : 4096);
 }
 
 // var[r] = kss[r] - |K_*[r,:] W^T|^2 through the explicit inverse: one triangular GEMM whose epilogue reduces the
@@ -792,9 +793,14 @@ int launch_sliced(nngp_handle* h, const int8_t* qa, int64_t ra, const double* sa
   p.ra = ra; p.rb = rb; p.rscale = sa; p.cscale = sw; p.vpart = vpart; p.V = V; p.ldv = ldv;
   if ((int64_t)s * ra >= (1LL << 31) || (int64_t)s * rb >= (1LL << 31))
     return fail(h, NNGP_EINVAL, "internal: digit-plane row range too large");
-  const int64_t tiles = (int64_t)((p.row_tiles + SL_RT - 1) / SL_RT) * p.col_tiles;
   static const int grid_env = [] { const char* e = getenv("NNGP_SLICED_GRID"); return e ? atoi(e) : 0; }();
+  static const int rt_env = [] { const char* e = getenv("NNGP_SLICED_RT"); return e ? atoi(e) : 0; }();
   int grid = grid_env > 0 ? grid_env : (h->sm_count / SL_SUPER) * SL_SUPER;   // CTAs 4k..4k+3 share a K_* row tile
+  // two row tiles per CTA tile: 32 KiB of operands per MMA set instead of 48.  (Single row tiles -- twice as many,
+  // lighter tiles -- were measured for small batches and lose: 1024 rows at N = 8192 take 1.82 ms instead of 1.55 ms,
+  // the kernel is bound by bytes per MAC even there.  NNGP_SLICED_RT=1 keeps the variant for A/B runs.)
+  p.rt = rt_env == 1 ? 1 : 2;
+  const int64_t tiles = (int64_t)((p.row_tiles + p.rt - 1) / p.rt) * p.col_tiles;
   grid = (int)std::min<int64_t>(grid, tiles);
   CKR(ensure(h, h->slscratch, (size_t)grid * SL_RT * SL_BM * SL_BN * sizeof(double)));
   p.scratch = h->slscratch.as<double>();

@@ -51,6 +51,7 @@ struct SlicedParams {
   int K;                   // inner dimension (= N for the triangular W)
   int row_tiles, col_tiles;
   int tri;                 // W lower triangular: column tile j needs K < 256 (j + 1) only
+  int rt;                  // row tiles per CTA tile: 2 (both accumulators), or 1 for small batches (more, lighter tiles)
   long long ra, rb;        // rows per plane in the stacked plane arrays of K_* / W
   const double* rscale;    // [rows]  2^(e-6) of the K_* rows
   const double* cscale;    // [N]     2^(e-6) of the W rows
@@ -148,7 +149,7 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {   /
 // ---- tile order -------------------------------------------------------------------------------------------------
 struct SlicedTile { int ip, jt, nkb; };   // row-tile pair, column tile, K blocks
 __device__ __forceinline__ bool sliced_tile(const SlicedParams& p, long long idx, SlicedTile& t) {
-  const int row_pairs = (p.row_tiles + SL_RT - 1) / SL_RT;
+  const int row_pairs = (p.row_tiles + p.rt - 1) / p.rt;
   const long long total = (long long)row_pairs * p.col_tiles;
   if (idx >= total) return false;
   const int nsup = (p.col_tiles + SL_SUPER - 1) / SL_SUPER;
@@ -213,7 +214,7 @@ sliced_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (long long idx = blockIdx.x; sliced_tile(p, idx, t); idx += gridDim.x) {
         for (int g = p.s - 1; g >= 0; --g)
           for (int pa = 0; pa <= g; ++pa) {
-            const int a_row = (int)(pa * p.ra) + t.ip * (SL_RT * SL_BM);
+            const int a_row = (int)(pa * p.ra) + t.ip * (p.rt * SL_BM);   // (rt = 1: the second half of the box is not used)
             const int b_row = (int)((g - pa) * p.rb) + t.jt * SL_BN;
             for (int kb = 0; kb < t.nkb; ++kb, ++n) {
               const uint32_t st = n % SL_STAGES, ph = (n / SL_STAGES) & 1u;
@@ -230,7 +231,7 @@ sliced_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       uint32_t n = 0, a = 0;
       SlicedTile t;
       for (long long idx = blockIdx.x; sliced_tile(p, idx, t); idx += gridDim.x) {
-        const bool two = t.ip * SL_RT + 1 < p.row_tiles;     // the second row tile exists
+        const bool two = p.rt == 2 && t.ip * 2 + 1 < p.row_tiles;     // the second row tile exists
         for (int g = p.s - 1; g >= 0; --g, ++a) {
           mbar_wait(acc_empty, (a & 1u) ^ 1u);              // the epilogue has drained both accumulators
           tc_fence_after();
@@ -263,7 +264,7 @@ sliced_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     uint32_t a = 0;
     SlicedTile t;
     for (long long idx = blockIdx.x; sliced_tile(p, idx, t); idx += gridDim.x) {
-      const int ntile = (t.ip * SL_RT + 1 < p.row_tiles) ? 2 : 1;
+      const int ntile = (p.rt == 2 && t.ip * 2 + 1 < p.row_tiles) ? 2 : 1;
       double sum[SL_RT] = {0.0, 0.0};
       for (int g = p.s - 1; g >= 0; --g, ++a) {
         mbar_wait(acc_full, a & 1u);
@@ -271,7 +272,7 @@ sliced_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         tc_fence_after();
         const bool first = (g == p.s - 1);
         for (int h = 0; h < ntile; ++h) {
-          const int grow = (t.ip * SL_RT + h) * SL_BM + row;
+          const int grow = (t.ip * p.rt + h) * SL_BM + row;
           const double rs = (grow < p.rows) ? p.rscale[grow] : 0.0;
           const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + h * SL_BN + half * (SL_BN / 2);
           double* sch = sc + (h * SL_BN + half * (SL_BN / 2)) * SL_BM;
@@ -303,7 +304,7 @@ sliced_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
       if (p.vpart)
         for (int h = 0; h < ntile; ++h) {
-          const int grow = (t.ip * SL_RT + h) * SL_BM + row;
+          const int grow = (t.ip * p.rt + h) * SL_BM + row;
           if (grow < p.rows) p.vpart[((long long)t.jt * 2 + half) * p.rows + grow] = sum[h];   // two partials per column tile
         }
     }
