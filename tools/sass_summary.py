@@ -2,8 +2,8 @@
     python tools/sass_summary.py [out.txt]
 For every kernel: registers, stack, local, static shared memory, and a histogram of the instructions that show what
 the kernel is built from -- DMMA (FP64 tensor core), UTMALDG (TMA tensor loads), SYNCS (mbarrier), LDS/STS, DFMA/DMUL/
-DADD (FP64 CUDA cores), MUFU (sqrt / reciprocal seeds), plus the absence of UTC*MMA / LDTM / STTM (tcgen05 has no FP64
-kind: DESIGN.md section 3)."""
+DADD (FP64 CUDA cores), MUFU (sqrt / reciprocal seeds), and UTC* / LDTM / STTM (tcgen05: only sliced_gemm_kernel, the
+int8 digit-plane product -- tcgen05 has no FP64 kind: DESIGN.md sections 3 and 5.10)."""
 import collections
 import re
 import subprocess
@@ -45,8 +45,9 @@ def main():
                            capture_output=True, text=True).stdout.strip()
     nvcc = subprocess.run(["/usr/local/cuda/bin/nvcc", "--version"], capture_output=True, text=True).stdout.strip().splitlines()[-2]
     lines = [f"# libnngp_b200.so  build id {build}  ({nvcc}); cuobjdump -sass / --dump-resource-usage, sm_100a",
-             "# tcgen05 instructions (UTC*MMA, LDTM, STTM) are absent by design: tcgen05.mma has no FP64 kind; the FP64 tensor",
-             "# route on sm_100a is mma.sync.m8n8k4.f64 -> DMMA.8x8x4, fed by TMA (UTMALDG) through mbarriers (SYNCS).",
+             "# FP64 kernels: tcgen05.mma has no FP64 kind, their tensor route on sm_100a is mma.sync.m8n8k4.f64 -> DMMA.8x8x4,",
+             "# fed by TMA (UTMALDG) through mbarriers (SYNCS).  sliced_gemm_kernel (variance_slices) is the tcgen05 kernel:",
+             "# UTCIMMA (kind::i8 MMA), UTCBAR (tcgen05.commit), UTCATOMSWS (TMEM alloc), LDTM (tcgen05.ld), counted under UTC / LDTM.",
              f"{'kernel':44s} {'REG':>4s} {'STACK':>5s} {'SMEM':>6s} {'LOCAL':>5s} {'instr':>6s} " + " ".join(f"{k:>7s}" for k in KEYS)]
     tot = collections.Counter()
     for n in names:
