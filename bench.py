@@ -456,6 +456,8 @@ def run_b200(args):
                                  "frac_of_burst": tops / (2.0 * pk_b) if pk_b else None,
                                  "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops_sustained (kind::i8 issues twice the MACs of "
                                                 "kind::f16 per instruction slot; the kernel runs for seconds under the power cap)",
+                                 "traffic": _traffic(args.workload + "_sliced", 1)[0], "traffic_source": _traffic(args.workload + "_sliced", 1)[1],
+                                 "algorithmic_bytes_per_step": float(args.slices) * n * (t_rank + n / 2.0),
                                  "fp64_equivalent_tflops": float(t_rank) * n * n * k_s / (st_s["sliced_ms"] / 1e3) / 1e12,
                                  "share_of_step": st_s["sliced_ms"] / max(st_s["pred_total_ms"], 1e-9)},
                 }

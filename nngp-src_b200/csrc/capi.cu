@@ -92,7 +92,7 @@ struct nngp_handle {
   bool have_inv = false;
   // cfg.variance_slices: int8 digit planes of L^-1 ([s][wq_rb][wq_ldq]) + 2^(e-6) of its rows; planes of the current
   // K_* row block, their row scales, and the per-CTA running-sum tiles of sliced_gemm_kernel
-  DevBuf Wq, wscale, Aq, ascale, slscratch;
+  DevBuf Wq, wscale, Aq, ascale, slscratch, slsync;
   bool have_wq = false;
   int64_t wq_ldq = 0, wq_rb = 0;
   DevBuf L2;      // second factor buffer: target of the incremental (fixed-lambda) append, then swapped with L
@@ -808,7 +808,24 @@ int launch_sliced(nngp_handle* h, const int8_t* qa, int64_t ra, const double* sa
   CKR(get_tmap_u8(h, qa, (uint64_t)s * ra, (uint64_t)ldq, SL_RT * SL_BM, &tmA));
   CKR(get_tmap_u8(h, qw, (uint64_t)s * rb, (uint64_t)ldq, SL_BN, &tmB));
   CK(cudaFuncSetAttribute(sliced_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM_BYTES));   // (per device)
-  sliced_gemm_kernel<<<grid, SL_THREADS, SL_SMEM_BYTES, h->stream>>>(tmA, tmB, p);
+  // Wave re-alignment (sliced_gemm.cuh: wave_barrier) needs every CTA resident: cooperative launch; when the driver
+  // cannot co-schedule the grid (another context holds SMs) the kernel runs free instead.
+  static const int sync_env = [] { const char* e = getenv("NNGP_SLICED_SYNC"); return e ? atoi(e) : SL_SYNC_DEFAULT; }();
+  const int64_t rounds = (tiles + grid - 1) / grid;
+  p.sync_mode = (sync_env == 1 || sync_env == 2) && rounds >= 2 ? sync_env : 0;
+  bool launched = false;
+  if (p.sync_mode) {
+    const size_t nsync = (size_t)rounds * (p.sync_mode == 2 ? s : 1);
+    CKR(ensure(h, h->slsync, nsync * sizeof(int)));
+    CK(cudaMemsetAsync(h->slsync.p, 0, nsync * sizeof(int), h->stream));
+    p.wave_sync = h->slsync.as<int>();
+    void* args[] = {(void*)&tmA, (void*)&tmB, (void*)&p};
+    cudaError_t le = cudaLaunchCooperativeKernel((const void*)sliced_gemm_kernel, dim3((unsigned)grid), dim3(SL_THREADS), args,
+                                                 SL_SMEM_BYTES, h->stream);
+    if (le == cudaSuccess) launched = true;
+    else { cudaGetLastError(); p.sync_mode = 0; p.wave_sync = nullptr; }
+  }
+  if (!launched) sliced_gemm_kernel<<<grid, SL_THREADS, SL_SMEM_BYTES, h->stream>>>(tmA, tmB, p);
   CK(cudaGetLastError());
   h->st.kernel_launches++;
   h->st.sliced_macs += sliced_macs(p.row_tiles, p.col_tiles, K, tri, s);
@@ -1310,7 +1327,7 @@ void nngp_destroy(nngp_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->X, &h->q, &h->L, &h->alpha, &h->flags, &h->lam_d, &h->xt, &h->qt, &h->kss,
                     &h->blk, &h->mean_d, &h->var_d, &h->ssq, &h->sync_ints, &h->Mmat, &h->Kdd, &h->blk2, &h->cross, &h->partial, &h->mean_partial, &h->ka, &h->kb, &h->kqa, &h->kqb, &h->kout, &h->Linv, &h->Linvfull, &h->panel_inv, &h->panel_sync, &h->zkeep, &h->L2, &h->y, &h->app_x, &h->app_y, &h->sel_mean, &h->sel_var, &h->sel_score, &h->sel_key,
-                    &h->sel_state, &h->sel_okey, &h->sel_oidx, &h->sel_max, &h->Wq, &h->wscale, &h->Aq, &h->ascale, &h->slscratch})
+                    &h->sel_state, &h->sel_okey, &h->sel_oidx, &h->sel_max, &h->Wq, &h->wscale, &h->Aq, &h->ascale, &h->slscratch, &h->slsync})
     release(*b);
   for (auto& r : h->pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : h->ev_pool) cudaEventDestroy(e);

@@ -43,6 +43,7 @@ constexpr int SL_SUPER = 4;                // column tiles per supercolumn
 constexpr int SL_MAX_SLICES = 9;
 constexpr int SL_SMEM_BYTES = SL_STAGES * (SL_A_BYTES + SL_B_BYTES) + 1024 /*alignment*/ + 256 /*barriers*/;
 constexpr int SL_SLICE_THREADS = 256;
+constexpr int SL_SYNC_DEFAULT = 1;         // wave re-alignment at every tile (NNGP_SLICED_SYNC=0|1|2): see wave_barrier
 
 struct SlicedParams {
   int s;                   // digit planes per operand
@@ -59,6 +60,8 @@ struct SlicedParams {
   double* vpart;           // [2 col_tiles][rows] sum over each 128-column half tile of V^2 (may be null)
   double* V;               // [rows][ldv] the product itself (diagnostics / tests)     (may be null)
   long long ldv;
+  int* wave_sync;          // sync_mode > 0: one arrival counter per tile round (x s for per-group syncs), zeroed before launch
+  int sync_mode;           // 0: free-running CTAs; 1: the producers re-align at every tile; 2: at every digit group
 };
 
 // ---- digit planes ---------------------------------------------------------------------------------------------
@@ -171,6 +174,21 @@ __device__ __forceinline__ bool sliced_tile(const SlicedParams& p, long long idx
   return true;
 }
 
+// Re-alignment of the CTAs of a wave (cooperative launch: all CTAs resident).  The tile order makes neighbouring CTAs
+// stream the same operand planes at the same time; without a common clock they drift apart by more stages than L2
+// holds and the shared planes are fetched from HBM again.  Only the TMA producers wait; bounded like every wait here.
+__device__ __forceinline__ void wave_barrier(int* counter, int participants) {
+  __threadfence();
+  atomicAdd(counter, 1);
+  for (uint32_t spin = 0;; ++spin) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    if (v >= participants) break;
+    if (spin > (1u << 28)) __trap();
+    __nanosleep(64);
+  }
+}
+
 // ---- the kernel -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SL_THREADS, 1)
 sliced_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -211,8 +229,13 @@ sliced_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (lane == 0) {   // ===== TMA producer =====
       uint32_t n = 0;
       SlicedTile t;
-      for (long long idx = blockIdx.x; sliced_tile(p, idx, t); idx += gridDim.x) {
-        for (int g = p.s - 1; g >= 0; --g)
+      const long long total = (long long)((p.row_tiles + p.rt - 1) / p.rt) * p.col_tiles;
+      int round = 0;
+      for (long long idx = blockIdx.x; sliced_tile(p, idx, t); idx += gridDim.x, ++round) {
+        const int participants = (int)min((long long)gridDim.x, total - (long long)round * gridDim.x);
+        for (int g = p.s - 1; g >= 0; --g) {
+          if (p.sync_mode == 2 || (p.sync_mode == 1 && g == p.s - 1))
+            wave_barrier(p.wave_sync + (p.sync_mode == 2 ? round * p.s + g : round), participants);
           for (int pa = 0; pa <= g; ++pa) {
             const int a_row = (int)(pa * p.ra) + t.ip * (p.rt * SL_BM);   // (rt = 1: the second half of the box is not used)
             const int b_row = (int)((g - pa) * p.rb) + t.jt * SL_BN;
@@ -224,6 +247,7 @@ sliced_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               tma_load_2d(ringB + st * SL_B_BYTES, &tmB, kb * SL_BK, b_row, &full_bar[st]);
             }
           }
+        }
       }
     }
   } else if (warp == 1) {
