@@ -252,6 +252,55 @@ def _time_predict(torch, dist, world, h, local, xte_host, steps, warmup, sample_
     return ms_total, ms_e2e, e2e_steps, st, st_e2e, clocks
 
 
+def _sliced_record(torch, dist, world, rank, local, _lib, args, depth, xtr, ytr, xte_host, t_rank, n, kept):
+    """The same workload with the variance product on the INT8 tensor cores (cfg.variance_slices: tcgen05.mma kind::i8
+    on digit planes of K_* and L^-1, FP64-equivalent to ~2^-7s).  Every rank fits its own handle (same data -> same
+    bits) and predicts its shard; timed like the main region (barrier, CUDA events, max over ranks).  A side record:
+    `value` stays the all-FP64 path.  Returns the record on rank 0, None elsewhere."""
+    peaks_file = ROOT / "MEASURED_PEAKS.json"
+    peaks = json.loads(peaks_file.read_text()) if peaks_file.exists() else {}
+    hs = _lib.Handle(depth=depth, diag_reg=1e-3, device=local, stats_level=2, variance_slices=args.slices)
+    hs.fit(xtr, ytr)
+    hs.stats_reset()
+    hs.fit(xtr, ytr)
+    sfit = hs.stats()
+    ks = {}
+    k_s = min(args.steps, 5)
+    ms_s, ms_se, k_se, st_s, _st_se, clk_s = _time_predict(torch, dist, world, hs, local, xte_host, k_s, 3,
+                                                           sample_clocks=(rank == 0), keep=ks if rank == 0 else None)
+    hs.close()
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    tops = 2.0 * st_s["sliced_macs"] / max(st_s["sliced_ms"], 1e-9) / 1e9
+    pk_s, pk_b = peaks.get("bf16_tflops_sustained"), peaks.get("bf16_tflops")
+    tr = _traffic(args.workload + "_sliced", world)
+    return {
+        "what": "variance_slices=%d: V = K_* L^-T as %d exact int8 plane products on tcgen05 (kind::i8, TMEM "
+                "accumulators) against the explicit inverse factor; the mean and the Gram stay FP64; every rank fits "
+                "its own handle" % (args.slices, args.slices * (args.slices + 1) // 2),
+        "value": world * k_s * t_rank / (ms_s / 1e3), "unit": UNIT, "n_gpus": world, "ms_per_step": ms_s / k_s, "steps": k_s,
+        "e2e_value": world * k_se * t_rank / (ms_se / 1e3),
+        "mean_bitwise_equal_fp64_path": bool(np.array_equal(ks["mean"], kept["mean"])),
+        "var_max_rel_vs_fp64_path": float(np.max(np.abs(ks["var"] - kept["var"]) / np.abs(kept["var"]))),
+        "std_max_rel_vs_fp64_path": float(np.max(np.abs(np.sqrt(ks["var"]) - np.sqrt(kept["var"])) / np.sqrt(kept["var"]))),
+        "stage_ms_per_step": {k: st_s[k] / k_s for k in ("pred_gram_ms", "pred_trsm_ms", "sliced_ms", "pred_total_ms")},
+        "fit_seconds_device": sfit["fit_total_ms"] / 1e3, "inverse_ms": sfit["inverse_ms"],
+        "clocks": clk_s,
+        "roofline": {"bound": "tensor", "kernel": "sliced_gemm_kernel (TMA + tcgen05.mma kind::i8 M128 N256 K32, int32 accumulators in TMEM)",
+                     "achieved": tops, "unit": "TOP/s (int8, issued; rank 0)",
+                     "peak": 2.0 * pk_b if pk_b else None, "frac": tops / (2.0 * pk_b) if pk_b else None,
+                     "frac_of_sustained": tops / (2.0 * pk_s) if pk_s else None,
+                     "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (burst; kind::i8 issues twice the MACs of kind::f16 per "
+                                    "instruction slot).  The kernel runs for seconds under the 1 kW power cap (see clocks): "
+                                    "frac_of_sustained is against 2 x bf16_tflops_sustained, the library's rate in that regime",
+                     "traffic": tr[0], "traffic_source": tr[1],
+                     "algorithmic_bytes_per_step": float(args.slices) * n * (t_rank + n / 2.0),
+                     "fp64_equivalent_tflops": float(t_rank) * n * n * k_s / (st_s["sliced_ms"] / 1e3) / 1e12,
+                     "share_of_step": st_s["sliced_ms"] / max(st_s["pred_total_ms"], 1e-9)},
+    }
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -316,6 +365,13 @@ def run_b200(args):
     kept = {}
     ms_total, ms_e2e, e2e_steps, st, st_e2e, clocks = _time_predict(torch, dist, world, h, local, xte_host, args.steps, warmup,
                                                                     sample_clocks=(rank == 0), keep=kept if rank == 0 else None)
+
+    sliced = None
+    if args.slices > 0 and not args.no_extras:
+        try:
+            sliced = _sliced_record(torch, dist, world, rank, local, _lib, args, depth, xtr, ytr, xte_host, t_rank, n, kept)
+        except Exception as e:  # noqa: BLE001  (a side record must not cost the headline line; all ranks fail alike)
+            sliced = {"error": repr(e)}
 
     in_process = None
     hard_exit = False
@@ -418,54 +474,14 @@ def run_b200(args):
         out["fit_broadcast"] = bcast
     if in_process is not None:
         out["in_process"] = in_process
+    if sliced is not None:
+        if "value" in sliced:
+            sliced["speedup_vs_fp64_path"] = sliced["value"] / value
+        out["sliced"] = sliced
 
     if world == 1 and not args.no_extras:
         h.close()
         torch.cuda.empty_cache()
-        if args.slices > 0:
-            # The same workload with the variance product on the INT8 tensor cores (cfg.variance_slices: tcgen05.mma
-            # kind::i8 on digit planes of K_* and L^-1, FP64-equivalent to ~2^-7s).  A side record: `value` above stays
-            # the all-FP64 path.
-            try:
-                hs = _lib.Handle(depth=depth, diag_reg=1e-3, device=local, stats_level=2, variance_slices=args.slices)
-                hs.fit(xtr, ytr)
-                hs.stats_reset()
-                hs.fit(xtr, ytr)
-                sfit = hs.stats()
-                ks = {}
-                k_s = min(args.steps, 5)
-                ms_s, ms_se, k_se, st_s, _st_se, clk_s = _time_predict(torch, dist, 1, hs, local, xte_host, k_s, 3, keep=ks)
-                tops = 2.0 * st_s["sliced_macs"] / max(st_s["sliced_ms"], 1e-9) / 1e9
-                pk_s, pk_b = peaks.get("bf16_tflops_sustained"), peaks.get("bf16_tflops")
-                out["sliced"] = {
-                    "what": "variance_slices=%d: V = K_* L^-T as %d exact int8 plane products on tcgen05 (kind::i8, TMEM "
-                            "accumulators) against the explicit inverse factor; the mean and the Gram stay FP64" % (
-                                args.slices, args.slices * (args.slices + 1) // 2),
-                    "value": k_s * t_rank / (ms_s / 1e3), "unit": UNIT, "ms_per_step": ms_s / k_s, "steps": k_s,
-                    "e2e_value": k_se * t_rank / (ms_se / 1e3),
-                    "speedup_vs_fp64_path": (k_s * t_rank / (ms_s / 1e3)) / value,
-                    "mean_bitwise_equal_fp64_path": bool(np.array_equal(ks["mean"], kept["mean"])),
-                    "var_max_rel_vs_fp64_path": float(np.max(np.abs(ks["var"] - kept["var"]) / np.abs(kept["var"]))),
-                    "std_max_rel_vs_fp64_path": float(np.max(np.abs(np.sqrt(ks["var"]) - np.sqrt(kept["var"])) / np.sqrt(kept["var"]))),
-                    "stage_ms_per_step": {k: st_s[k] / k_s for k in ("pred_gram_ms", "pred_trsm_ms", "sliced_ms", "pred_total_ms")},
-                    "fit_seconds_device": sfit["fit_total_ms"] / 1e3, "inverse_ms": sfit["inverse_ms"],
-                    "clocks": clk_s,
-                    "roofline": {"bound": "tensor", "kernel": "sliced_gemm_kernel (TMA + tcgen05.mma kind::i8 M128 N256 K32, int32 accumulators in TMEM)",
-                                 "achieved": tops, "unit": "TOP/s (int8, issued)",
-                                 "peak": 2.0 * pk_b if pk_b else None, "frac": tops / (2.0 * pk_b) if pk_b else None,
-                                 "frac_of_sustained": tops / (2.0 * pk_s) if pk_s else None,
-                                 "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (burst; kind::i8 issues twice the MACs of kind::f16 per "
-                                                "instruction slot).  The kernel runs for seconds under the 1 kW power cap (see clocks): "
-                                                "frac_of_sustained is against 2 x bf16_tflops_sustained, the library's rate in that regime",
-                                 "traffic": _traffic(args.workload + "_sliced", 1)[0], "traffic_source": _traffic(args.workload + "_sliced", 1)[1],
-                                 "algorithmic_bytes_per_step": float(args.slices) * n * (t_rank + n / 2.0),
-                                 "fp64_equivalent_tflops": float(t_rank) * n * n * k_s / (st_s["sliced_ms"] / 1e3) / 1e12,
-                                 "share_of_step": st_s["sliced_ms"] / max(st_s["pred_total_ms"], 1e-9)},
-                }
-                hs.close()
-                torch.cuda.empty_cache()
-            except Exception as e:  # noqa: BLE001
-                out["sliced"] = {"error": repr(e)}
         if args.workload != "c2":          # the round-1 headline config, for continuity
             try:
                 n2, t2, d2, dep2, jd2, desc2 = WORKLOADS["c2"]

@@ -863,16 +863,21 @@ int run_sliced_variance(nngp_handle* h, const double* B, int64_t ldb, int64_t ro
   CKR(ensure(h, h->partial, (size_t)2 * col_tiles * sb * sizeof(double)));
   cudaEvent_t a = get_event(h), b = get_event(h);
   cudaEventRecord(a, h->stream);
-  for (int64_t r0 = 0; r0 < rows; r0 += sb) {
+  int rc = NNGP_OK;
+  for (int64_t r0 = 0; r0 < rows && rc == NNGP_OK; r0 += sb) {
     const int64_t nr = std::min<int64_t>(sb, rows - r0), ra = round_up(nr, SL_RT * SL_BM);
-    CKR(slice_matrix(h, B + r0 * ldb, ldb, nr, N, 0, s, ra, ldq, h->Aq.as<int8_t>(), h->ascale.as<double>()));
-    CKR(launch_sliced(h, h->Aq.as<int8_t>(), ra, h->ascale.as<double>(), h->Wq.as<int8_t>(), h->wq_rb,
-                      h->wscale.as<double>(), ldq, s, 1, nr, N, N, h->partial.as<double>(), nullptr, 0));
-    var_from_partial_kernel<<<(unsigned)((nr + 255) / 256), 256, 0, h->stream>>>(kss + r0, h->partial.as<double>(), 2 * col_tiles, (int)nr, var + r0);
-    h->st.kernel_launches++;
+    rc = slice_matrix(h, B + r0 * ldb, ldb, nr, N, 0, s, ra, ldq, h->Aq.as<int8_t>(), h->ascale.as<double>());
+    if (rc == NNGP_OK)
+      rc = launch_sliced(h, h->Aq.as<int8_t>(), ra, h->ascale.as<double>(), h->Wq.as<int8_t>(), h->wq_rb,
+                         h->wscale.as<double>(), ldq, s, 1, nr, N, N, h->partial.as<double>(), nullptr, 0);
+    if (rc == NNGP_OK) {
+      var_from_partial_kernel<<<(unsigned)((nr + 255) / 256), 256, 0, h->stream>>>(kss + r0, h->partial.as<double>(), 2 * col_tiles, (int)nr, var + r0);
+      h->st.kernel_launches++;
+    }
   }
-  cudaEventRecord(b, h->stream);
+  cudaEventRecord(b, h->stream);          // (also on the error path: the span is collected or recycled either way)
   h->sliced_spans.push_back({a, b});
+  CKR(rc);
   CK(cudaGetLastError());
   return NNGP_OK;
 }
