@@ -795,37 +795,63 @@ int launch_sliced(nngp_handle* h, const int8_t* qa, int64_t ra, const double* sa
     return fail(h, NNGP_EINVAL, "internal: digit-plane row range too large");
   static const int grid_env = [] { const char* e = getenv("NNGP_SLICED_GRID"); return e ? atoi(e) : 0; }();
   static const int rt_env = [] { const char* e = getenv("NNGP_SLICED_RT"); return e ? atoi(e) : 0; }();
-  int grid = grid_env > 0 ? grid_env : (h->sm_count / SL_SUPER) * SL_SUPER;   // CTAs 4k..4k+3 share a K_* row tile
+  static const int cl_env = [] { const char* e = getenv("NNGP_SLICED_CLUSTER"); return e ? atoi(e) : SL_CLUSTER_DEFAULT; }();
+  static const int sync_env = [] { const char* e = getenv("NNGP_SLICED_SYNC"); return e ? atoi(e) : SL_SYNC_DEFAULT; }();
   // two row tiles per CTA tile: 32 KiB of operands per MMA set instead of 48.  (Single row tiles -- twice as many,
   // lighter tiles -- were measured for small batches and lose: 1024 rows at N = 8192 take 1.82 ms instead of 1.55 ms,
   // the kernel is bound by bytes per MAC even there.  NNGP_SLICED_RT=1 keeps the variant for A/B runs.)
   p.rt = rt_env == 1 ? 1 : 2;
-  const int64_t tiles = (int64_t)((p.row_tiles + p.rt - 1) / p.rt) * p.col_tiles;
-  grid = (int)std::min<int64_t>(grid, tiles);
-  CKR(ensure(h, h->slscratch, (size_t)grid * SL_RT * SL_BM * SL_BN * sizeof(double)));
-  p.scratch = h->slscratch.as<double>();
   CUtensorMap tmA, tmB;
   CKR(get_tmap_u8(h, qa, (uint64_t)s * ra, (uint64_t)ldq, SL_RT * SL_BM, &tmA));
-  CKR(get_tmap_u8(h, qw, (uint64_t)s * rb, (uint64_t)ldq, SL_BN, &tmB));
-  CK(cudaFuncSetAttribute(sliced_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM_BYTES));   // (per device)
-  // Wave re-alignment (sliced_gemm.cuh: wave_barrier) needs every CTA resident: cooperative launch; when the driver
-  // cannot co-schedule the grid (another context holds SMs) the kernel runs free instead.
-  static const int sync_env = [] { const char* e = getenv("NNGP_SLICED_SYNC"); return e ? atoi(e) : SL_SYNC_DEFAULT; }();
-  const int64_t rounds = (tiles + grid - 1) / grid;
-  p.sync_mode = (sync_env == 1 || sync_env == 2) && rounds >= 2 ? sync_env : 0;
+  // One attempt per cluster size: 2 (W stages multicast inside CTA pairs) falls back to 1 when the driver cannot place
+  // the clusters; inside an attempt the wave re-alignment (cooperative launch: every CTA resident) falls back to
+  // free-running CTAs when the grid cannot be co-scheduled (another context holds SMs).
   bool launched = false;
-  if (p.sync_mode) {
-    const size_t nsync = (size_t)rounds * (p.sync_mode == 2 ? s : 1);
-    CKR(ensure(h, h->slsync, nsync * sizeof(int)));
-    CK(cudaMemsetAsync(h->slsync.p, 0, nsync * sizeof(int), h->stream));
-    p.wave_sync = h->slsync.as<int>();
-    void* args[] = {(void*)&tmA, (void*)&tmB, (void*)&p};
-    cudaError_t le = cudaLaunchCooperativeKernel((const void*)sliced_gemm_kernel, dim3((unsigned)grid), dim3(SL_THREADS), args,
-                                                 SL_SMEM_BYTES, h->stream);
-    if (le == cudaSuccess) launched = true;
-    else { cudaGetLastError(); p.sync_mode = 0; p.wave_sync = nullptr; }
+  for (int cl = (cl_env == 2 ? 2 : 1); cl >= 1 && !launched; --cl) {
+    p.cl = cl;
+    const int64_t pairs = ((p.row_tiles + p.rt - 1) / p.rt + cl - 1) / cl * cl;
+    const int64_t tiles = pairs * p.col_tiles;
+    int grid = grid_env > 0 ? grid_env : (h->sm_count / SL_SUPER) * SL_SUPER;   // CTAs 4k..4k+3 (cl = 2: 8k..8k+7) share K_* row tiles
+    const void* fn = cl == 2 ? (const void*)sliced_gemm_kernel<2> : (const void*)sliced_gemm_kernel<1>;
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM_BYTES));   // (per device)
+    cudaLaunchConfig_t lc = {};
+    cudaLaunchAttribute attrs[2];
+    lc.blockDim = dim3(SL_THREADS); lc.dynamicSmemBytes = SL_SMEM_BYTES; lc.stream = h->stream; lc.attrs = attrs;
+    if (cl == 2) {
+      attrs[0].id = cudaLaunchAttributeClusterDimension;
+      attrs[0].val.clusterDim.x = 2; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+      lc.numAttrs = 1;
+      lc.gridDim = dim3((unsigned)(grid / 2 * 2));
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, fn, &lc) != cudaSuccess || nclusters < 1) { cudaGetLastError(); continue; }
+      grid = std::min(grid, 2 * nclusters) / SL_SUPER * SL_SUPER;
+      if (grid < 2) continue;
+    }
+    grid = (int)std::min<int64_t>(grid, tiles);
+    CKR(ensure(h, h->slscratch, (size_t)grid * SL_RT * SL_BM * SL_BN * sizeof(double)));
+    p.scratch = h->slscratch.as<double>();
+    CKR(get_tmap_u8(h, qw, (uint64_t)s * rb, (uint64_t)ldq, SL_BN / cl, &tmB));
+    const int64_t rounds = (tiles + grid - 1) / grid;
+    lc.gridDim = dim3((unsigned)grid);
+    for (int sync = ((sync_env == 1 || sync_env == 2) && rounds >= 2 ? sync_env : 0); !launched; sync = 0) {
+      p.sync_mode = sync; p.wave_sync = nullptr;
+      lc.numAttrs = cl == 2 ? 1 : 0;
+      if (sync) {
+        const size_t nsync = (size_t)rounds * (sync == 2 ? s : 1);
+        CKR(ensure(h, h->slsync, nsync * sizeof(int)));
+        CK(cudaMemsetAsync(h->slsync.p, 0, nsync * sizeof(int), h->stream));
+        p.wave_sync = h->slsync.as<int>();
+        attrs[lc.numAttrs].id = cudaLaunchAttributeCooperative;
+        attrs[lc.numAttrs].val.cooperative = 1;
+        lc.numAttrs++;
+      }
+      const cudaError_t le = cl == 2 ? cudaLaunchKernelEx(&lc, sliced_gemm_kernel<2>, tmA, tmB, p)
+                                     : cudaLaunchKernelEx(&lc, sliced_gemm_kernel<1>, tmA, tmB, p);
+      if (le == cudaSuccess) launched = true;
+      else { cudaGetLastError(); if (!sync || cl == 2) break; }   // (clusters without re-alignment are not worth keeping: try cl = 1)
+    }
   }
-  if (!launched) sliced_gemm_kernel<<<grid, SL_THREADS, SL_SMEM_BYTES, h->stream>>>(tmA, tmB, p);
+  if (!launched) return fail(h, NNGP_ECUDA, "sliced_gemm_kernel could not be launched");
   CK(cudaGetLastError());
   h->st.kernel_launches++;
   h->st.sliced_macs += sliced_macs(p.row_tiles, p.col_tiles, K, tri, s);

@@ -43,6 +43,7 @@ constexpr int SL_SUPER = 4;                // column tiles per supercolumn
 constexpr int SL_MAX_SLICES = 9;
 constexpr int SL_SMEM_BYTES = SL_STAGES * (SL_A_BYTES + SL_B_BYTES) + 1024 /*alignment*/ + 256 /*barriers*/;
 constexpr int SL_SLICE_THREADS = 256;
+constexpr int SL_CLUSTER_DEFAULT = 1;      // CTAs per cluster (NNGP_SLICED_CLUSTER=1|2): 2 = W stages by TMA multicast
 constexpr int SL_SYNC_DEFAULT = 1;         // wave re-alignment at every tile (NNGP_SLICED_SYNC=0|1|2): see wave_barrier
 
 struct SlicedParams {
@@ -60,6 +61,7 @@ struct SlicedParams {
   double* vpart;           // [2 col_tiles][rows] sum over each 128-column half tile of V^2 (may be null)
   double* V;               // [rows][ldv] the product itself (diagnostics / tests)     (may be null)
   long long ldv;
+  int cl;                  // CTAs per cluster sharing every W stage by TMA multicast: 1 or 2 (== the kernel's template argument)
   int* wave_sync;          // sync_mode > 0: one arrival counter per tile round (x s for per-group syncs), zeroed before launch
   int sync_mode;           // 0: free-running CTAs; 1: the producers re-align at every tile; 2: at every digit group
 };
@@ -126,6 +128,28 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t desc_a, uint
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t cta_mask) {   // same, on `bar` of every CTA in the mask
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)), "h"(cta_mask)
+               : "memory");
+}
+// TMA load delivered to the same shared-memory offset (and signalled on the same mbarrier offset) of every CTA in the mask
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 // shared-memory matrix descriptor: K-major, 128-byte swizzle, rows 128 B apart, 8-row groups 1024 B apart
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) /*LBO (unused)*/ | (64ull << 32) /*SBO = 1024 B*/ |
@@ -152,7 +176,9 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {   /
 // ---- tile order -------------------------------------------------------------------------------------------------
 struct SlicedTile { int ip, jt, nkb; };   // row-tile pair, column tile, K blocks
 __device__ __forceinline__ bool sliced_tile(const SlicedParams& p, long long idx, SlicedTile& t) {
-  const int row_pairs = (p.row_tiles + p.rt - 1) / p.rt;
+  // cl = 2: consecutive tile indices (= the two CTAs of a cluster) are two row pairs of the SAME column tile, so that
+  // they can share its W stages; the pair count is rounded up to even (a phantom pair computes on padding, writes nothing)
+  const int row_pairs = ((p.row_tiles + p.rt - 1) / p.rt + p.cl - 1) / p.cl * p.cl;
   const long long total = (long long)row_pairs * p.col_tiles;
   if (idx >= total) return false;
   const int nsup = (p.col_tiles + SL_SUPER - 1) / SL_SUPER;
@@ -160,12 +186,15 @@ __device__ __forceinline__ bool sliced_tile(const SlicedParams& p, long long idx
   const long long first = (long long)row_pairs * wlast;
   int sup, c;
   if (idx < first) {
-    sup = nsup - 1; t.ip = (int)(idx / wlast); c = (int)(idx % wlast);
+    sup = nsup - 1;
+    const long long q = idx / p.cl;
+    t.ip = (int)(q / wlast) * p.cl + (int)(idx % p.cl); c = (int)(q % wlast);
   } else {
     const long long r = idx - first, per = (long long)row_pairs * SL_SUPER;
     sup = nsup - 2 - (int)(r / per);
     const long long in = r % per;
-    t.ip = (int)(in / SL_SUPER); c = (int)(in % SL_SUPER);
+    const long long q = in / p.cl;
+    t.ip = (int)(q / SL_SUPER) * p.cl + (int)(in % p.cl); c = (int)(q % SL_SUPER);
   }
   t.jt = sup * SL_SUPER + c;
   // the whole supercolumn runs the K extent of its last column tile, so that its CTAs stay in lockstep
@@ -190,6 +219,10 @@ __device__ __forceinline__ void wave_barrier(int* counter, int participants) {
 }
 
 // ---- the kernel -------------------------------------------------------------------------------------------------
+// CL = 2: launched as clusters of two CTAs (same column tile, neighbouring row pairs).  Each CTA fetches HALF of the
+// W stage (128 rows, tensor map tmB with a 128-row box) and TMA-multicasts it into both CTAs, so every W byte crosses
+// the L2 -> SM fabric once per cluster; a stage is free when BOTH CTAs' MMAs have read it (multicast tcgen05.commit).
+template <int CL>
 __global__ void __launch_bounds__(SL_THREADS, 1)
 sliced_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const SlicedParams p) {
@@ -208,7 +241,7 @@ sliced_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < SL_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < SL_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CL); }
     mbar_init(acc_full, 1);
     mbar_init(acc_empty, 32 * SL_EPI_WARPS);
     fence_mbar_init();
@@ -224,12 +257,18 @@ sliced_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  uint32_t crank = 0;
+  if constexpr (CL > 1) {   // the peer's barriers must exist before a multicast load or commit can reach them
+    cluster_sync_all();
+    crank = cluster_rank();
+  }
+  constexpr uint16_t cl_mask = (uint16_t)((1u << CL) - 1u);
 
   if (warp == 0) {
     if (lane == 0) {   // ===== TMA producer =====
       uint32_t n = 0;
       SlicedTile t;
-      const long long total = (long long)((p.row_tiles + p.rt - 1) / p.rt) * p.col_tiles;
+      const long long total = (long long)(((p.row_tiles + p.rt - 1) / p.rt + p.cl - 1) / p.cl * p.cl) * p.col_tiles;
       int round = 0;
       for (long long idx = blockIdx.x; sliced_tile(p, idx, t); idx += gridDim.x, ++round) {
         const int participants = (int)min((long long)gridDim.x, total - (long long)round * gridDim.x);
@@ -244,7 +283,11 @@ sliced_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               mbar_wait(&empty_bar[st], ph ^ 1u);
               mbar_arrive_expect_tx(&full_bar[st], SL_A_BYTES + SL_B_BYTES);
               tma_load_2d(ringA + st * SL_A_BYTES, &tmA, kb * SL_BK, a_row, &full_bar[st]);   // both row tiles: 256 rows
-              tma_load_2d(ringB + st * SL_B_BYTES, &tmB, kb * SL_BK, b_row, &full_bar[st]);
+              if constexpr (CL == 1)
+                tma_load_2d(ringB + st * SL_B_BYTES, &tmB, kb * SL_BK, b_row, &full_bar[st]);
+              else        // my half of the W stage, into both CTAs (the peer sends the other half)
+                tma_load_2d_mc(ringB + st * SL_B_BYTES + crank * (SL_B_BYTES / CL), &tmB, kb * SL_BK,
+                               b_row + (int)crank * (SL_BN / CL), &full_bar[st], cl_mask);
             }
           }
         }
@@ -274,7 +317,8 @@ sliced_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 if (two) tc_mma_i8(tmem_base + SL_BN, da1 + 2u * k, db + 2u * k, SL_IDESC, acc);
                 acc = 1;
               }
-              tc_commit(&empty_bar[st]);                 // stage free once these MMAs have read it
+              if constexpr (CL == 1) tc_commit(&empty_bar[st]);          // stage free once these MMAs have read it
+              else tc_commit_mc(&empty_bar[st], cl_mask);               // ... in every CTA that multicasts into it
             }
           tc_commit(acc_full);                           // group complete: hand the accumulators to the epilogue
         }
@@ -336,6 +380,7 @@ sliced_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();   // no CTA leaves while its peer may still write into it / arrive on its barriers
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
