@@ -18,12 +18,15 @@
 //   warps 2-9          epilogue: tcgen05.ld the finished group, fold it into the FP64 running sum (Horner in 2^-7)
 //                      held in an L2-resident per-CTA scratch tile; on the last group scale by the two row exponents,
 //                      square, reduce along the row -> two partials per (row, column tile); V itself is never stored.
-// The kernel is bound by the L2 -> SM fabric, not by the tensor pipe (one 128 x 256 x 128 MMA set takes 512 clk, the
-// fabric delivers ~43 B/clk/SM): sharing each W stage between two accumulators cuts the bytes per MMA set from 48 KiB
-// to 32 KiB (first version: 2.3 POP/s, exactly the fabric limit for 48 KiB).
+// What bounds it: with one accumulator per stage (48 KiB of operands per 128 x 256 x 128 MMA set of
+// 512 clk) the L2 -> SM fabric (~43 B/clk/SM): 2.3 POP/s; sharing each W stage between two accumulators (32 KiB per
+// set) moves the limit to the 1 kW power cap -- the kernel runs at ~1.4 GHz with the tensor pipe ~90 % busy, so what
+// is left to gain is energy per MAC, i.e. bytes moved:
 // Tile order: column tiles in groups of 4 ("supercolumns") from the widest triangular extent down, row-tile pairs
-// inside, the 4 column tiles of one pair adjacent -- CTAs 4k..4k+3 stream the same K_* planes in lockstep (the second
-// to fourth read hit L2, sparing HBM) and all CTAs of a wave stream the same W planes.
+// inside, the 4 column tiles of one pair adjacent -- CTAs 4k..4k+3 stream the same K_* planes (the second to fourth
+// read hit L2, sparing HBM) and all CTAs of a wave stream the same W planes.  That only holds while the CTAs stay in
+// step, so the producers re-align at a grid-wide counter at every tile (wave_barrier): DRAM reads -55 %, +6.6 %.
+// Clusters of two CTAs with TMA multicast of the W stages (template CL = 2) are bit-identical but slower; kept for A/B.
 #pragma once
 #include "ptx.cuh"
 
@@ -53,7 +56,7 @@ struct SlicedParams {
   int K;                   // inner dimension (= N for the triangular W)
   int row_tiles, col_tiles;
   int tri;                 // W lower triangular: column tile j needs K < 256 (j + 1) only
-  int rt;                  // row tiles per CTA tile: 2 (both accumulators), or 1 for small batches (more, lighter tiles)
+  int rt;                  // row tiles per CTA tile: 2 (both accumulators); 1 = A/B variant (more, lighter tiles; slower)
   long long ra, rb;        // rows per plane in the stacked plane arrays of K_* / W
   const double* rscale;    // [rows]  2^(e-6) of the K_* rows
   const double* cscale;    // [N]     2^(e-6) of the W rows
