@@ -1598,6 +1598,29 @@ int nngp_active_select(nngp_handle* h, const double* x_pool, int64_t T, int64_t 
   return NNGP_OK;
 }
 
+// latency mode / variance_slices: the explicit inverse, its build scratch, the digit planes of W and of a K_* sub-block
+// at (N, T) -- so that a growing training set (the active-learning loop) does not reallocate them round after round
+static int reserve_inverse_buffers(nngp_handle* h, int64_t N, int64_t T) {
+  if (!h->cfg.latency_mode || h->cfg.kernel_type != 0) return NNGP_OK;
+  const int64_t ldl = round_up(N, 16);
+  CKR(ensure(h, h->Linvfull, (size_t)N * ldl * 8));
+  if (!h->owner) CKR(ensure(h, h->Kdd, (size_t)N * ldl * 8));       // (replicas receive L^-1, they do not build it)
+  const int s = h->cfg.variance_slices;
+  if (s <= 0) return NNGP_OK;
+  const int64_t ldq = round_up(N, SL_BK), rb = round_up(N, SL_BN);
+  CKR(ensure(h, h->Wq, (size_t)s * rb * ldq));
+  CKR(ensure(h, h->wscale, (size_t)N * sizeof(double)));
+  if (T > 0) {                                                       // as run_sliced_variance sizes its sub-blocks
+    const int64_t wave_rows = (int64_t)(h->sm_count / SL_SUPER) * SL_RT * SL_BM;
+    int64_t sb = ((16LL << 30) / ((int64_t)s * ldq)) / wave_rows * wave_rows;
+    sb = std::min<int64_t>(std::max<int64_t>(sb, SL_RT * SL_BM), round_up(T, SL_RT * SL_BM));
+    CKR(ensure(h, h->Aq, (size_t)s * sb * ldq));
+    CKR(ensure(h, h->ascale, (size_t)sb * sizeof(double)));
+    CKR(ensure(h, h->partial, (size_t)2 * (rb / SL_BN) * sb * sizeof(double)));
+  }
+  return NNGP_OK;
+}
+
 int nngp_reserve(nngp_handle* h, int64_t n_train_max, int64_t dim, int64_t n_test_max) {
   if (!h) return NNGP_EINVAL;
   if (n_train_max <= 0 || dim <= 0 || n_test_max < 0 || n_train_max > 65535LL * GEMM_BM)
@@ -1633,6 +1656,7 @@ int nngp_reserve(nngp_handle* h, int64_t n_train_max, int64_t dim, int64_t n_tes
     CKR(ensure(h, h->var_d, (size_t)T * 8));
     for (DevBuf* b : {&h->sel_mean, &h->sel_var, &h->sel_score, &h->sel_key}) CKR(ensure(h, *b, (size_t)T * 8));
   }
+  CKR(reserve_inverse_buffers(h, N, T));
   // replicas (cfg.n_gpus > 1): the state buffers at full size and the workspace for this GPU's share of the rows, so
   // that a growing training set does not make every replica free and reallocate multi-GB buffers round after round
   const int G = 1 + (int)h->peers.size();
@@ -1644,7 +1668,7 @@ int nngp_reserve(nngp_handle* h, int64_t n_train_max, int64_t dim, int64_t n_tes
     if (rc == NNGP_OK) rc = ensure(p, p->L, (size_t)(N + 1) * ldl * 8);
     if (rc == NNGP_OK) rc = ensure(p, p->alpha, (size_t)ldl * 8);
     if (rc == NNGP_OK) rc = ensure(p, p->Linv, (size_t)round_up(N, NB) * NB * 8);
-    if (rc == NNGP_OK && h->cfg.latency_mode && h->cfg.kernel_type == 0) rc = ensure(p, p->Linvfull, (size_t)N * ldl * 8);
+    if (rc == NNGP_OK) rc = reserve_inverse_buffers(p, N, T > 0 ? (T + G - 1) / G + 1 : 0);
     if (rc == NNGP_OK && T > 0) {
       const int64_t Tg = (T + G - 1) / G + 1;
       int64_t cap_rows = p->cfg.max_block_bytes / (ldl * 8);
