@@ -278,7 +278,7 @@ def _sliced_record(torch, dist, world, rank, local, _lib, args, depth, xtr, ytr,
     return {
         "what": "variance_slices=%d: V = K_* L^-T as %d exact int8 plane products on tcgen05 (kind::i8, TMEM "
                 "accumulators) against the explicit inverse factor; the mean and the Gram stay FP64; every rank fits "
-                "its own handle" % (args.slices, args.slices * (args.slices + 1) // 2),
+                "its own handle" % (args.slices, args.slices * (args.slices + 1) // 2 - 1),
         "value": world * k_s * t_rank / (ms_s / 1e3), "unit": UNIT, "n_gpus": world, "ms_per_step": ms_s / k_s, "steps": k_s,
         "e2e_value": world * k_se * t_rank / (ms_se / 1e3),
         "mean_bitwise_equal_fp64_path": bool(np.array_equal(ks["mean"], kept["mean"])),

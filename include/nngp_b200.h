@@ -90,8 +90,8 @@ typedef struct nngp_config {
   int32_t variance_slices;    /* 0: off.  s = 5..9 ('nngp' only; implies the explicit inverse factor of latency_mode):
                                  the variance product K_* L^-T of LARGE prediction batches runs on the INT8 tensor cores
                                  (tcgen05.mma kind::i8, accumulators in TMEM): both operands are split row-wise into s
-                                 signed 7-bit digit planes, the s(s+1)/2 exact int32 plane products with p + q < s are
-                                 recombined in FP64.  s = 7 keeps the posterior variance within ~1e-8 relative of the
+                                 signed 7-bit digit planes, the s(s+1)/2 - 1 exact int32 plane products with p + q < s (all but
+                                 the weakest, plane s-1 of K_* times plane 0 of L^-1) are recombined in FP64.  s = 7 keeps the posterior variance within ~1e-8 relative of the
                                  FP64 path at cond(K + lambda I) = 1e7 (s = 8: 1e-10); the mean is untouched.  N <= 2^19 / s. */
   int32_t reserved0;
 } nngp_config;
@@ -239,7 +239,8 @@ NNGP_API int nngp_num_gpus(const nngp_handle* h);
 
 /* Diagnostic / test entry of the digit-plane product behind cfg.variance_slices: V = A B^T for A [M, K] and B [N, K]
  * (dense row-major, host or device), computed with `slices` int8 planes per operand on the tcgen05 kind::i8 path;
- * `lower` != 0 treats B as lower triangular (entries with k > row ignored, N == K).  v_out [M, N] receives the product,
+ * `lower` != 0 treats B as lower triangular (entries with k > row ignored, N == K); `lower` == 2 also drops the plane
+ * pair (slices-1, 0), exactly as the variance path does for B = L^-1 (whose rows are dominated by their diagonal entry).  v_out [M, N] receives the product,
  * rowsq_out [M] (optional) the row sums of V^2 in the order the variance uses.  Independent of any fitted model.
  * [no reference counterpart: the reference's only matrix product is XLA's dot, train.py:157-158]              */
 NNGP_API int nngp_sliced_product(nngp_handle* h, const double* a, int64_t M, int64_t K, const double* b, int64_t N,

@@ -770,7 +770,7 @@ int slice_matrix(nngp_handle* h, const double* A, int64_t lda, int64_t rows, int
 }
 
 // int8 MACs the kernel issues for this shape (every supercolumn runs the K extent of its last column tile)
-double sliced_macs(int64_t row_tiles, int64_t col_tiles, int64_t K, int tri, int s) {
+double sliced_macs(int64_t row_tiles, int64_t col_tiles, int64_t K, int tri, int s, int skip_weak) {
   double macs = 0.0;
   const int64_t nsup = (col_tiles + SL_SUPER - 1) / SL_SUPER;
   for (int64_t sup = 0; sup < nsup; ++sup) {
@@ -778,16 +778,16 @@ double sliced_macs(int64_t row_tiles, int64_t col_tiles, int64_t K, int tri, int
     const int64_t kext = tri ? std::min<int64_t>(K, std::min<int64_t>((sup + 1) * SL_SUPER, col_tiles) * SL_BN) : K;
     macs += (double)row_tiles * (double)width * (double)(SL_BM * SL_BN) * (double)round_up(kext, SL_BK);
   }
-  return macs * (double)(s * (s + 1) / 2);
+  return macs * (double)(s * (s + 1) / 2 - (skip_weak && s > 1 ? 1 : 0));
 }
 
 // V = A W^T from the digit planes: vpart[2 col_tiles][rows] row sums of V^2 per 128-column half tile and/or V itself
 // (ra: rows per K_* plane, a multiple of 256)
 int launch_sliced(nngp_handle* h, const int8_t* qa, int64_t ra, const double* sa, const int8_t* qw, int64_t rb,
                   const double* sw, int64_t ldq, int s, int tri, int64_t rows, int64_t N, int64_t K, double* vpart, double* V,
-                  int64_t ldv) {
+                  int64_t ldv, int skip_weak) {
   SlicedParams p{};
-  p.s = s; p.rows = (int)rows; p.N = (int)N; p.K = (int)K; p.tri = tri;
+  p.s = s; p.rows = (int)rows; p.N = (int)N; p.K = (int)K; p.tri = tri; p.skip_weak = skip_weak;
   p.row_tiles = (int)((rows + SL_BM - 1) / SL_BM);
   p.col_tiles = (int)((N + SL_BN - 1) / SL_BN);
   p.ra = ra; p.rb = rb; p.rscale = sa; p.cscale = sw; p.vpart = vpart; p.V = V; p.ldv = ldv;
@@ -854,7 +854,7 @@ int launch_sliced(nngp_handle* h, const int8_t* qa, int64_t ra, const double* sa
   if (!launched) return fail(h, NNGP_ECUDA, "sliced_gemm_kernel could not be launched");
   CK(cudaGetLastError());
   h->st.kernel_launches++;
-  h->st.sliced_macs += sliced_macs(p.row_tiles, p.col_tiles, K, tri, s);
+  h->st.sliced_macs += sliced_macs(p.row_tiles, p.col_tiles, K, tri, s, skip_weak);
   return NNGP_OK;
 }
 
@@ -872,6 +872,12 @@ int build_w_planes(nngp_handle* h) {
   CK(cudaStreamSynchronize(h->stream));
   h->wq_ldq = ldq; h->wq_rb = rb; h->have_wq = true;
   return NNGP_OK;
+}
+
+// The variance path drops the plane pair (s-1, 0) (SlicedParams::skip_weak); NNGP_SLICED_KEEP_ALL_PAIRS=1 keeps it.
+static int sliced_skip_weak() {
+  static const int keep = [] { const char* e = getenv("NNGP_SLICED_KEEP_ALL_PAIRS"); return e ? atoi(e) : 0; }();
+  return keep ? 0 : 1;
 }
 
 // var[r] = kss[r] - |K_*[r,:] W^T|^2 with the product on the int8 tensor cores, in row sub-blocks whose planes fit
@@ -895,7 +901,7 @@ int run_sliced_variance(nngp_handle* h, const double* B, int64_t ldb, int64_t ro
     rc = slice_matrix(h, B + r0 * ldb, ldb, nr, N, 0, s, ra, ldq, h->Aq.as<int8_t>(), h->ascale.as<double>());
     if (rc == NNGP_OK)
       rc = launch_sliced(h, h->Aq.as<int8_t>(), ra, h->ascale.as<double>(), h->Wq.as<int8_t>(), h->wq_rb,
-                         h->wscale.as<double>(), ldq, s, 1, nr, N, N, h->partial.as<double>(), nullptr, 0);
+                         h->wscale.as<double>(), ldq, s, 1, nr, N, N, h->partial.as<double>(), nullptr, 0, sliced_skip_weak());
     if (rc == NNGP_OK) {
       var_from_partial_kernel<<<(unsigned)((nr + 255) / 256), 256, 0, h->stream>>>(kss + r0, h->partial.as<double>(), 2 * col_tiles, (int)nr, var + r0);
       h->st.kernel_launches++;
@@ -1328,7 +1334,7 @@ int nngp_sliced_product(nngp_handle* h, const double* a, int64_t M, int64_t K, c
     CKR(slice_matrix(h, dA.as<double>(), K, M, K, 0, slices, ra, ldq, qa.as<int8_t>(), sa.as<double>()));
     CKR(slice_matrix(h, dB.as<double>(), K, N, K, lower ? 1 : 0, slices, rb, ldq, qb.as<int8_t>(), sb.as<double>()));
     CKR(launch_sliced(h, qa.as<int8_t>(), ra, sa.as<double>(), qb.as<int8_t>(), rb, sb.as<double>(), ldq, slices, lower ? 1 : 0,
-                      M, N, K, vp.as<double>(), v_out ? dV.as<double>() : nullptr, N));
+                      M, N, K, vp.as<double>(), v_out ? dV.as<double>() : nullptr, N, lower == 2 ? 1 : 0));
     if (v_out) CK(cudaMemcpyAsync(v_out, dV.p, (size_t)M * N * 8, cudaMemcpyDefault, h->stream));
     if (rowsq_out) {
       rowsq_from_partial_kernel<<<(unsigned)((M + 255) / 256), 256, 0, h->stream>>>(vp.as<double>(), 2 * col_tiles, (int)M, rs.as<double>());

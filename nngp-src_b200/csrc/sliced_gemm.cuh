@@ -8,7 +8,8 @@
 // product of two digit planes is an exact int32 GEMM (|sum| <= (g+1) * 2^12 * K < 2^31 for K <= 65536), planes with
 // the same p + q = g share the scale 2^(-7g), and keeping the groups g < s gives V to 2^(-7s) of
 // |row a|_max |row b|_max K -- s = 7: posterior variance within 1e-8 of the FP64 path at cond 1e7
-// (tools/ozaki_study.py, tests/test_gpu_sliced.py).  s (s+1) / 2 integer GEMMs replace one FP64 GEMM.
+// (tools/ozaki_study.py, tests/test_gpu_sliced.py).  s (s+1) / 2 integer GEMMs replace one FP64 GEMM (the variance
+// path drops the weakest pair: SlicedParams::skip_weak).
 //
 // Kernel: persistent, one CTA per SM, warp-specialised the Blackwell way:
 //   warp 0 (one lane)  TMA producer: 128-byte-swizzled boxes of the digit planes into a 3-stage ring (mbarrier tx);
@@ -64,6 +65,9 @@ struct SlicedParams {
   double* vpart;           // [2 col_tiles][rows] sum over each 128-column half tile of V^2 (may be null)
   double* V;               // [rows][ldv] the product itself (diagnostics / tests)     (may be null)
   long long ldv;
+  int skip_weak;           // 1 (variance path): drop the pair (A plane s-1, W plane 0).  A row of W = L^-1 is dominated by
+                           // its diagonal entry, so plane 0 of W holds digits 0 / +-1 almost everywhere and this pair
+                           // weighs like the first DROPPED group (tools/ozaki_pairskip_study.py): 1 / 28 of the MACs
   int cl;                  // CTAs per cluster sharing every W stage by TMA multicast: 1 or 2 (== the kernel's template argument)
   int* wave_sync;          // sync_mode > 0: one arrival counter per tile round (x s for per-group syncs), zeroed before launch
   int sync_mode;           // 0: free-running CTAs; 1: the producers re-align at every tile; 2: at every digit group
@@ -278,7 +282,8 @@ sliced_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int g = p.s - 1; g >= 0; --g) {
           if (p.sync_mode == 2 || (p.sync_mode == 1 && g == p.s - 1))
             wave_barrier(p.wave_sync + (p.sync_mode == 2 ? round * p.s + g : round), participants);
-          for (int pa = 0; pa <= g; ++pa) {
+          const int pa_last = (p.skip_weak && g == p.s - 1 && g > 0) ? g - 1 : g;
+          for (int pa = 0; pa <= pa_last; ++pa) {
             const int a_row = (int)(pa * p.ra) + t.ip * (p.rt * SL_BM);   // (rt = 1: the second half of the box is not used)
             const int b_row = (int)((g - pa) * p.rb) + t.jt * SL_BN;
             for (int kb = 0; kb < t.nkb; ++kb, ++n) {
@@ -306,7 +311,8 @@ sliced_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           mbar_wait(acc_empty, (a & 1u) ^ 1u);              // the epilogue has drained both accumulators
           tc_fence_after();
           uint32_t acc = 0;
-          for (int pa = 0; pa <= g; ++pa)
+          const int pa_last = (p.skip_weak && g == p.s - 1 && g > 0) ? g - 1 : g;
+          for (int pa = 0; pa <= pa_last; ++pa)
             for (int kb = 0; kb < t.nkb; ++kb, ++n) {
               const uint32_t st = n % SL_STAGES, ph = (n / SL_STAGES) & 1u;
               mbar_wait(&full_bar[st], ph);

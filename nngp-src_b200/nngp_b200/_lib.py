@@ -278,7 +278,9 @@ class Handle:
 
     def sliced_product(self, a, b, slices=7, lower=False, want_rowsq=False):
         """Diagnostic: ``a @ b.T`` through ``slices`` int8 digit planes per operand on the tcgen05 kind::i8 kernel
-        (the product behind ``variance_slices``).  Returns V, or (V, row sums of V**2) with ``want_rowsq``."""
+        (the product behind ``variance_slices``).  ``lower=True``: b is lower triangular; ``lower=2``: additionally drop
+        the plane pair (slices-1, 0) as the variance path does for b = L^-1.  Returns V, or (V, row sums of V**2) with
+        ``want_rowsq``."""
         ap, ka = _ptr(a)
         bp, kb = _ptr(b)
         M, K = ka.shape
@@ -287,7 +289,7 @@ class Handle:
             raise ValueError(f"nngp_b200: a has {K} columns but b has {kb.shape[1]}")
         v = np.empty((M, N), dtype=np.float64)
         rs = np.empty(M, dtype=np.float64) if want_rowsq else None
-        self._ck(self._lib.nngp_sliced_product(self._h, ap, M, K, bp, N, int(bool(lower)), int(slices),
+        self._ck(self._lib.nngp_sliced_product(self._h, ap, M, K, bp, N, 2 if lower == 2 else int(bool(lower)), int(slices),
                                                _out_ptr(v, (M, N), "v"), _out_ptr(rs, (M,), "rowsq") if want_rowsq else None))
         return (v, rs) if want_rowsq else v
 

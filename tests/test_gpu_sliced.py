@@ -34,14 +34,16 @@ def _split_rows(a, s, tri=False):
     return planes, e
 
 
-def _digit_restatement(a, b, s, tri):
+def _digit_restatement(a, b, s, tri, skip_weak=False):
     """What sliced_gemm_kernel computes, in numpy: exact integer plane products (FP64 matmuls of small integers),
-    groups p + q = g folded by Horner in 2^-7, two row scales."""
+    groups p + q = g folded by Horner in 2^-7, two row scales.  ``skip_weak``: without the pair (s-1, 0), as the
+    variance path runs it."""
     pa, ea = _split_rows(a, s)
     pb, eb = _split_rows(b, s, tri)
     acc = None
     for g in range(s - 1, -1, -1):
-        c = sum(pa[p] @ pb[g - p].T for p in range(g + 1))
+        last = g - 1 if (skip_weak and g == s - 1 and g > 0) else g
+        c = sum(pa[p] @ pb[g - p].T for p in range(last + 1))
         assert np.max(np.abs(c)) < 2 ** 31
         acc = c if acc is None else acc * 0.0078125 + c
     return acc * np.ldexp(1.0, ea - 6)[:, None] * np.ldexp(1.0, eb - 6)[None, :]
@@ -67,6 +69,26 @@ def test_sliced_product_is_bit_exact_against_the_digit_restatement(lib, m, k, n,
         assert np.max(np.abs(v - a @ b.T) / scale) < 2.0 ** (-7 * s + 8)
     v2 = h.sliced_product(a, b, slices=s, lower=tri)
     assert np.array_equal(v, v2)
+    h.close()
+
+
+def test_variance_path_drops_only_the_weakest_pair(lib):
+    """lower=2 is the product exactly as nngp_predict runs it against W = L^-1: all pairs p + q < s except (s-1, 0).
+    Bit-exact against the restatement with the same rule; on a diagonally dominated factor (what L^-1 is) the result
+    stays at the accuracy of the full set, on a generic triangular matrix it would not -- hence variance path only."""
+    rng = np.random.default_rng(21)
+    n, m, s = 1536, 300, 7
+    a = rng.random((m, n)) + 0.5                                     # flat rows, like kernel values
+    w = np.tril(rng.normal(size=(n, n))) * 0.01 + np.diag(1.0 + rng.random(n))     # diagonal ~100x the rest, like L^-1
+    h = lib.Handle()
+    v_all = h.sliced_product(a, w, slices=s, lower=True)
+    v_skip = h.sliced_product(a, w, slices=s, lower=2)
+    assert np.array_equal(v_all, _digit_restatement(a, w, s, True))
+    assert np.array_equal(v_skip, _digit_restatement(a, w, s, True, skip_weak=True))
+    exact = a @ w.T
+    scale = np.max(np.abs(exact))
+    e_all, e_skip = np.max(np.abs(v_all - exact)) / scale, np.max(np.abs(v_skip - exact)) / scale
+    assert e_skip < 4 * e_all + 1e-15, (e_all, e_skip)
     h.close()
 
 
